@@ -1,0 +1,142 @@
+"""Pin the oracle against every golden vector the reference's own tests hold for the path.
+
+Replays ``tests/case_test.py:14-206`` (3-particle periodic box) and
+``tests/rollout_test.py:74-195`` (Lennard-Jones rollout identity with a cheating model)
+of the reference against ``oracle/``.  Values below are the reference's, copied as data.
+"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import case as ocase
+from oracle import rollout as orollout
+from oracle import space as ospace
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+METADATA = {  # tests/case_test.py:14-23
+    "num_particles_max": 3,
+    "periodic_boundary_conditions": [True, True, True],
+    "default_connectivity_radius": 0.3,
+    "bounds": [[0.0, 1.0], [0.0, 1.0], [0.0, 1.0]],
+    "acc_mean": [0.0, 0.0, 0.0],
+    "acc_std": [1.0, 1.0, 1.0],
+    "vel_mean": [0.0, 0.0, 0.0],
+    "vel_std": [1.0, 1.0, 1.0],
+}
+POSITION = np.array(  # tests/case_test.py:40-64, (N, T, d) = (3, 5, 3)
+    [
+        [[0.5, 0.5, 0.5]] * 5,
+        [[0.7, 0.5, 0.5], [0.9, 0.5, 0.5], [0.1, 0.5, 0.5], [0.3, 0.5, 0.5], [0.5, 0.5, 0.5]],
+        [[0.8, 0.6, 0.5], [0.8, 0.6, 0.5], [0.9, 0.6, 0.5], [0.2, 0.6, 0.5], [0.6, 0.6, 0.5]],
+    ]
+)
+PTYPE = np.array([0, 0, 0])
+
+
+def make_case(dtype):
+    return ocase.case_builder(
+        np.array([1.0, 1.0, 1.0]), METADATA, input_seq_length=3,
+        cfg_neighbors={"backend": "jaxmd_vmap", "multiplier": 1.25},
+        cfg_model={"isotropic_norm": False, "magnitude_features": False},
+        noise_std=0.0, external_force_fn=None, dtype=dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_allocate_golden(dtype):
+    case = make_case(dtype)
+    _, features, target, nbrs = case.allocate(None, (POSITION, PTYPE))
+    # tests/case_test.py:77-82
+    assert (nbrs.idx == np.array([[0, 1, 2, 2, 1, 3], [0, 1, 1, 2, 2, 3]])).all()
+    assert not nbrs.did_buffer_overflow
+    # tests/case_test.py:86-100
+    assert np.isclose(target["vel"], [[0, 0, 0], [0.2, 0, 0], [0.3, 0, 0]]).all()
+    assert np.isclose(target["acc"], [[0, 0, 0], [0, 0, 0], [0.2, 0, 0]], atol=1e-7).all()
+    # tests/case_test.py:102-114
+    assert np.isclose(features["vel_hist"],
+                      [[0, 0, 0, 0, 0, 0], [0.2, 0, 0, 0.2, 0, 0], [0, 0, 0, 0.1, 0, 0]], atol=1e-7).all()
+    # tests/case_test.py:116-137
+    disp = np.array([[0, 0, 0], [0, 0, 0], [-0.2, 0.1, 0], [0, 0, 0], [0.2, -0.1, 0], [0, 0, 0]]) / 0.3
+    dist = ((disp**2).sum(-1, keepdims=True)) ** 0.5
+    assert np.isclose(features["rel_disp"], disp, atol=1e-6).all()
+    assert np.isclose(features["rel_dist"], dist, atol=1e-6).all()
+
+
+def test_preprocess_golden():
+    case = make_case(np.float32)
+    _, _, _, nbrs = case.allocate(None, (POSITION, PTYPE))
+    _, _, _, nbrs_new = case.preprocess(None, (POSITION, PTYPE), 0.0, nbrs, 0)  # case_test.py:139-148
+    assert (nbrs.idx == nbrs_new.idx).all()
+    _, _, target, _ = case.preprocess(None, (POSITION, PTYPE), 0.0, nbrs, 1)  # case_test.py:150-163
+    assert np.isclose(target["acc"], [[0, 0, 0], [0, 0, 0], [0.1, 0, 0]], atol=1e-7).all()
+
+
+def test_integrate_golden():
+    case = make_case(np.float32)
+    acc = {"acc": np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 0.0], [0.2, 0.0, 0.0]])}  # case_test.py:195-206
+    new_pos = case.integrate(acc, POSITION[:, :3])
+    assert np.isclose(new_pos, POSITION[:, 3]).all()
+
+
+@pytest.mark.parametrize("n_extrap_steps", [0, 5, 10])
+def test_lj_rollout_identity(n_extrap_steps):
+    """tests/rollout_test.py:74-195 with x64 (rollout_test.py:14)."""
+    with open(os.path.join(GOLDEN, "lj3d_metadata.json")) as f:
+        metadata = json.load(f)
+    pos_tnd = np.load(os.path.join(GOLDEN, "lj3d_valid_position.npy"))
+    isl, n_rollout = 3, 100
+    # H5Dataset valid split: first chunk of subseq_length = isl + extra (data.py:136-141,199-211)
+    positions = pos_tnd[: isl + n_rollout].transpose(1, 0, 2)  # (N, T, d) float32
+    ptype = np.zeros(positions.shape[0], dtype=np.int32)
+    bounds = np.array(metadata["bounds"])
+    box = bounds[:, 1] - bounds[:, 0]
+    case = ocase.case_builder(box, metadata, isl, noise_std=0.0, dtype=np.float64)
+    disp, shift = ospace.periodic(box)
+    pos64 = positions.astype(np.float64)
+    vels = disp(pos64[:, 1:], pos64[:, :-1])
+    accs = vels[:, 1:] - vels[:, :-1]
+    stats = case.normalization_stats["acceleration"]
+    accs = (accs - stats["mean"]) / stats["std"]
+
+    # "Wrong setup" check (rollout_test.py:117-127)
+    pred_pos = shift(pos64[:, isl - 1], vels[:, isl - 2] + (stats["mean"] + accs[:, 0] * stats["std"]))
+    assert np.isclose(pred_pos.astype(np.float32), positions[:, isl], atol=1e-7).all()
+
+    def model_apply(params, state, sample):  # CheatingModel, rollout_test.py:92-106
+        i = state["counter"]
+        i_c = min(i, accs.shape[1] - 1)
+        return {"acc": accs[:, i_c]}, {"counter": i + 1}
+
+    _, nbrs = case.allocate_eval((positions[:, :isl], ptype))
+    # the LJ box is smaller than 3 cutoffs: all-pairs candidate path
+    assert nbrs.cell_list_capacity is None
+    pred, _ = orollout.eval_batched_rollout(
+        model_apply, case, None, {"counter": isl - 2}, (positions[None], ptype[None]), nbrs,
+        n_rollout_steps=n_rollout, t_window=isl, n_extrap_steps=n_extrap_steps)
+    assert pred.shape[1] == n_rollout + n_extrap_steps
+    target = positions[:, isl:isl + n_rollout].transpose(1, 0, 2)
+    mse = orollout.mse(case.displacement, pred[0, :n_rollout].astype(np.float64), target.astype(np.float64))
+    assert np.isclose(mse.mean(), 0.0, atol=1e-6)
+    full = np.concatenate([positions.transpose(1, 0, 2)[:isl], pred[0]], axis=0)
+    assert np.isclose(full[100, 0], positions.transpose(1, 0, 2)[100, 0], atol=1e-6).all()
+
+
+def test_gns_param_count():
+    """docs/pages/baselines.rst:55,62 publish 161K / 1.2M parameters."""
+    from oracle import gns
+
+    # RPF-2D: K*d + d = 12 node features (vel_hist 10 + force 2), edges d+1 = 3
+    assert gns.num_params(gns.init_params(12, 3, 2, latent=128, num_mp_steps=10)) == 1211794
+    assert gns.num_params(gns.init_params(12, 3, 2, latent=64, num_mp_steps=5)) == 161042
+
+
+def test_segment_sum_drops_pad():
+    from oracle import gns
+
+    data = np.arange(12, dtype=np.float64).reshape(6, 2)
+    out = gns.segment_sum(data, np.array([0, 2, 2, 3, 0, 3]), 3)
+    assert np.array_equal(out, [[8, 10], [0, 0], [6, 8]])
