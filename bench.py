@@ -1,0 +1,356 @@
+"""Benchmark of the GNS rollout hot path (BASELINE.json metric: particle-steps/s).
+
+    python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
+
+A "step" is one rollout step of the whole particle cloud: neighbor search -> features ->
+GNS forward (10 message-passing steps) -> integrate.  Prints ONE JSON line (rank 0).
+See DESIGN.md "Measurement" for what each key means and how it is computed.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/s GNS rollout (LDC-3D)"
+UNIT = "particle-steps/s"
+MP_STEPS = 10
+EDGE_BYTES = 1032  # read e (512) + write e' (512) + 2 int32 indices, per edge per MP step
+NODE_BYTES = 1024  # read the node row once for the gather side (512) + write the aggregate (512)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name, n_future, seed, dtype_name):
+    from lagrangebench_b200 import synthetic
+
+    npd = np.float64 if dtype_name == "float64" else np.float32
+    return synthetic.make_case(name, 6, n_future, seed, npd)
+
+
+def node_in_of(case_spec):
+    d = case_spec["metadata"]["dim"]
+    n = 5 * d
+    if not any(case_spec["metadata"]["periodic_boundary_conditions"]):
+        n += 2 * d
+    if case_spec["force"] is not None:
+        n += d
+    return n
+
+
+# --------------------------------------------------------------------------------------
+# oracle legs (cpu_baseline / --impl reference).  The ONLY place bench.py executes oracle/.
+def oracle_steps(spec, n_steps, warmup, seed, dtype_name):
+    """Time the oracle port of the path: per step neighbor update + features + float32 GNS
+    forward + integrate, NumPy on all host cores.  Returns (seconds for n_steps, N, E)."""
+    from oracle import case as ocase
+    from oracle import gns as ogns
+    from oracle import rollout as orollout
+
+    npd = np.float64 if dtype_name == "float64" else np.float32
+    force = spec["force"]
+    ofn = None
+    if force is not None:
+        lo, hi = np.array(force.lo), np.array(force.hi)
+        ofn = lambda r: hi if r[force.axis] > force.threshold else lo  # noqa: E731
+    case = ocase.case_builder(spec["box"], spec["metadata"], 6, cfg_neighbors={"multiplier": spec["multiplier"]},
+                              external_force_fn=ofn, dtype=npd)
+    d = spec["metadata"]["dim"]
+    params = ogns.init_params(node_in_of(spec), d + 1, d, num_mp_steps=MP_STEPS, seed=seed, perturb=False)
+    current = spec["positions"][:, :6].astype(npd)
+    ptype = spec["particle_type"]
+    _, nbrs = case.allocate_eval((current, ptype))
+
+    def apply(p, state, sample):
+        feats, pt = sample
+        f32 = {k: (np.asarray(v).astype(np.float32) if np.asarray(v).dtype.kind == "f" else v)
+               for k, v in feats.items()}
+        return ogns.forward(p, f32, pt, MP_STEPS, np.float32), state
+
+    elapsed = 0.0
+    for step in range(warmup + n_steps):
+        t0 = time.perf_counter()
+        feats, nbrs = case.preprocess_eval((current, ptype), nbrs)
+        if nbrs.did_buffer_overflow:
+            _, nbrs = case.allocate_eval((current, ptype))
+            feats, nbrs = case.preprocess_eval((current, ptype), nbrs)
+        tgt = current[:, -1]
+        current, _ = orollout.forward_eval(apply, case.integrate, params, {}, (feats, ptype), current, tgt)
+        if step >= warmup:
+            elapsed += time.perf_counter() - t0
+    return elapsed, current.shape[0], nbrs.n_edges
+
+
+def sub_lattice_dims(dims, n_target):
+    """Shrink a lattice to about n_target sites keeping its aspect ratio (min 8 per side)."""
+    dims = np.array(dims, dtype=np.float64)
+    scale = (n_target / dims.prod()) ** (1.0 / len(dims))
+    return tuple(int(max(8, round(v * scale))) for v in dims)
+
+
+def oracle_sample_spec(workload, n_target, seed, dtype_name):
+    from lagrangebench_b200 import synthetic
+
+    npd = np.float64 if dtype_name == "float64" else np.float32
+    full = synthetic.CASES[workload]["dims"]
+    dims = full if n_target >= int(np.prod(full)) else sub_lattice_dims(full, n_target)
+    if workload == "dam2d":
+        dims = full  # masked lattice: always the full tank
+    return synthetic.make_case(workload, 6, 0, seed, npd, dims=dims), dims
+
+
+def run_reference_arm(args):
+    """--impl reference: the oracle port timed on the host cores (JAX is not installable
+    here, so there is no oracle/_ref build of the reference itself)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total_steps = args.steps + args.warmup
+    budget_s = 150.0
+    probe, _ = oracle_sample_spec(args.workload, 3000, args.seed, args.dtype)
+    t_probe, n_probe, _ = oracle_steps(probe, 1, 0, args.seed, args.dtype)
+    rate = n_probe / max(t_probe, 1e-9)
+    from lagrangebench_b200 import synthetic
+
+    n_full = int(np.prod(synthetic.CASES[args.workload]["dims"]))
+    n_target = int(min(n_full, max(2000, rate * budget_s / total_steps)))
+    spec, dims = oracle_sample_spec(args.workload, n_target, args.seed, args.dtype)
+    elapsed, n, e = oracle_steps(spec, args.steps, args.warmup, args.seed, args.dtype)
+    value = n * args.steps / elapsed
+    cores = os.cpu_count()
+    sample = f"{args.workload} sub-lattice {dims} = {n} particles, {e} edges, {args.steps} full rollout steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "mp_steps": MP_STEPS, "latent": 128, "positions": args.dtype},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "NumPy oracle port of the reference path on host cores (reference JAX stack not installable offline)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from lagrangebench_b200 import GNS, RolloutEngine, _cabi, case_builder
+    from lagrangebench_b200 import models as lbmodels
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _cabi.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, args.warmup
+    # replicas: every rank rolls out its own trajectory of the same shape (clouds of
+    # this size do not shard; the reference's batch vmap maps to one trajectory per GPU)
+    spec = build_workload(args.workload, K + W, args.seed + rank, args.dtype)
+    d = spec["metadata"]["dim"]
+    n = spec["positions"].shape[0]
+    case = case_builder(spec["box"], spec["metadata"], 6, cfg_neighbors={"multiplier": spec["multiplier"]},
+                        external_force_fn=spec["force"], dtype=args.dtype)
+    params = lbmodels.init_params(node_in_of(spec), d, 128, MP_STEPS, 16, seed=args.seed)
+    model = GNS(d, 128, 2, MP_STEPS, 16)
+    engine = RolloutEngine(case, model, params, steps_per_sync=max(K, W, 1))
+    tdt = torch.float64 if args.dtype == "float64" else torch.float32
+    window = torch.as_tensor(spec["positions"][:, :6]).to(dev, tdt).contiguous()
+    targets_all = torch.as_tensor(spec["positions"][:, 6:6 + K + W]).permute(1, 0, 2).to(dev, tdt).contiguous()
+    ptype = torch.as_tensor(spec["particle_type"]).to(dev)
+
+    # warm-up (also sizes the neighbor capacities and scratch)
+    _, nbrs = engine.run(window, ptype, targets_all[:W], W)
+    barrier()
+    launches0 = lib.lb200_launch_count()
+    realloc0 = engine.n_reallocations
+    lib.lb200_profile(1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    preds, nbrs = engine.run(window, ptype, targets_all[W:W + K], K, nbrs)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.lb200_launch_count() - launches0
+    import ctypes as C
+
+    kms = (C.c_double * 2)()
+    kl = (C.c_int64 * 2)()
+    _cabi.check(lib.lb200_profile_read(kms, kl))
+    lib.lb200_profile(0)
+    n_edges = nbrs.n_edges
+    assert torch.isfinite(preds).all(), "rollout diverged"
+
+    # end-to-end leg: the same steps through the public per-step API with HOST buffers --
+    # every step uploads that step's kinematic-target frame from pinned memory and reads the
+    # predicted positions back (one host synchronisation per step, as the reference loop has)
+    esz = 8 if args.dtype == "float64" else 4
+    h_targets = torch.as_tensor(spec["positions"][:, 6:6 + K + W]).permute(1, 0, 2).to(tdt).contiguous().pin_memory()
+    h_out = torch.empty((n, d), dtype=tdt).pin_memory()
+    d_tgt = torch.empty((1, n, d), dtype=tdt, device=dev)
+    window_e = torch.as_tensor(spec["positions"][:, :6]).to(dev, tdt).contiguous()
+    engine_e = RolloutEngine(case, model, params, steps_per_sync=1)
+    nb_e = None
+    for t in range(min(W, 3)):
+        d_tgt[0].copy_(h_targets[t], non_blocking=True)
+        p, nb_e = engine_e.run(window_e, ptype, d_tgt, 1, nb_e)
+        h_out.copy_(p[0], non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(K):
+        d_tgt[0].copy_(h_targets[W + t], non_blocking=True)
+        p, nb_e = engine_e.run(window_e, ptype, d_tgt, 1, nb_e)
+        h_out.copy_(p[0], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+        cnt = torch.tensor([float(launches)], device=dev, dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        launches = int(cnt.item())
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        edge_ms_avg = kms[0] / max(kl[0], 1)
+        alg_bytes = EDGE_BYTES * n_edges + NODE_BYTES * n
+        achieved = alg_bytes / (edge_ms_avg * 1e-3) / 1e9 if edge_ms_avg > 0 else 0.0
+        flops_launch = n_edges * 65536.0  # restructured count: W1 node terms hoisted
+        value = world * n * K / (ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "particles": n, "edges": n_edges, "mp_steps": MP_STEPS,
+                       "latent": 128, "positions": args.dtype, "multi_gpu": "replicas" if world > 1 else "single",
+                       "l2": "inputs larger than L2 (edge latents %.0f MB)" % (n_edges * 512 / 1e6)
+                       if n_edges * 512 > 126e6 else "working set below L2 (edge latents %.0f MB): latency-bound"
+                       % (n_edges * 512 / 1e6),
+                       "reallocations_in_timed_region": engine.n_reallocations - realloc0},
+            "roofline": {"bound": "hbm", "kernel": "edge_mp_kernel (fused gather + edge MLP + LayerNorm + residual "
+                         "+ segmented sum)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                         "avg_launch_ms": edge_ms_avg, "launches": int(kl[0]),
+                         "share_of_step": kms[0] / ms, "node_kernel_share_of_step": kms[1] / ms,
+                         "fp32_tflops": flops_launch / (edge_ms_avg * 1e-3) / 1e12 if edge_ms_avg > 0 else 0.0},
+            "e2e": {"value": world * n * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * d * esz,
+                    "d2h_bytes_per_step": n * d * esz},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sample_spec, dims = oracle_sample_spec(args.workload, args.cpu_sample, args.seed, args.dtype)
+            t_cpu, n_cpu, e_cpu = oracle_steps(sample_spec, 1, 0, args.seed, args.dtype)
+            line["cpu_baseline"] = {
+                "value": n_cpu / t_cpu, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                "sample": f"1 full rollout step of the NumPy oracle on a {args.workload} sub-lattice {dims} = "
+                          f"{n_cpu} particles / {e_cpu} edges ({t_cpu:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ldc3d_28k")
+    ap.add_argument("--dtype", default="float64", choices=["float32", "float64"],
+                    help="position / preprocessing dtype (reference default float64); the network is float32")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=12000, help="particles in the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

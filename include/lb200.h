@@ -1,0 +1,242 @@
+/*
+ * lb200.h -- C ABI of the B200-native GNS rollout hot path (liblb200 / _lb200.so).
+ *
+ * The reference (tumaer/lagrangebench) has no FFI: its hot path is Python on JAX/XLA.
+ * Each entry point below replaces one JAX-traced stage of that path; the citation names
+ * the reference interface it stands in for (paths relative to the reference root).
+ * A maintainer binds these with ctypes from the reference's Python.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer marked "dev" is DEVICE memory owned by
+ *     the caller (the Python host uses torch tensors purely as allocations);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises unless stated;
+ *   - return value: 0 on success, >0 a cudaError_t, <0 an LB200_E* argument error;
+ *   - positions are `float` or `double` (`pos_f64` = 0/1): the reference preprocesses in
+ *     float64 by default (lagrangebench/defaults.py:22) and runs the network in float32;
+ *   - index arrays are int32; the pad value of the edge list is N (jax-md convention).
+ */
+#ifndef LB200_H
+#define LB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB200_LATENT 128          /* latent_dim the kernels are specialised for (defaults.py:49) */
+#define LB200_MAX_NODE_IN 64      /* max node-encoder input width (features + type embedding) */
+
+#define LB200_EINVAL (-1)
+#define LB200_EUNSUPPORTED (-2)
+
+/* overflow flag bits, mirroring jax-md's PartitionErrorCode */
+#define LB200_OVF_NEIGHBOR_LIST 1 /* E > E_cap: list truncated */
+#define LB200_OVF_CELL_LIST 2     /* a cell holds more particles than cell_capacity */
+
+int lb200_version(void);
+const char* lb200_error_string(int code);
+
+/* ------------------------------------------------------------------------------------
+ * Geometry of the search grid.  Replaces jax_md.partition._cell_dimensions /
+ * neighbor_list's `use_cell_list` decision (third-party jax-sph 0.0.3; call site
+ * lagrangebench/case_setup/case.py:120-130).  Host-only, no CUDA work.
+ */
+typedef struct {
+  int32_t n;               /* particles */
+  int32_t dim;             /* 2 or 3 */
+  int32_t pos_f64;         /* 0: float positions, 1: double positions */
+  int32_t periodic;        /* case.py:104-108: periodic in all dims, or free */
+  double box[3];
+  double r_cutoff;
+  int32_t use_cells;       /* out of lb200_grid_init: 1 cell list, 0 all-pairs */
+  int32_t cells_per_side[3];
+  float cell_size[3];
+  int32_t n_cells;
+  int32_t n_cand_cells;    /* 3^dim */
+} lb200_grid;
+
+int lb200_grid_init(lb200_grid* g, int32_t n, int32_t dim, int32_t pos_f64, int32_t periodic,
+                    const double* box, double r_cutoff);
+
+/* bytes of device scratch lb200_nbr_build / lb200_csr_build need for this grid / capacity */
+int64_t lb200_nbr_scratch_bytes(const lb200_grid* g);
+int64_t lb200_csr_scratch_bytes(int32_t n, int32_t e_cap);
+
+/* ------------------------------------------------------------------------------------
+ * (i) Radius neighbor search.  Replaces NeighborListFns.allocate / NeighborList.update of
+ * jax_md.partition (Sparse, mask_self=False; call sites case.py:184-190) and yields the
+ * same (2, E_cap) int32 array, row 0 = receivers, row 1 = senders
+ * (lagrangebench/case_setup/features.py:110), in the same order, padded with N.
+ *
+ *   cell_capacity  jax-md's cell_list capacity (fixes the within-cell candidate rotation);
+ *                  pass 0 to only measure: stats are written and no list is produced.
+ *   idx            dev int32[2*e_cap] or NULL when e_cap == 0 (count only)
+ *   stats          dev int32[4]: [0] true edge count E, [1] max cell occupancy,
+ *                  [2] overflow bits (OR-ed into the previous value: sticky, like jax-md),
+ *                  [3] reserved
+ */
+int lb200_nbr_build(const lb200_grid* g, const void* pos_dev, int32_t cell_capacity,
+                    int32_t* idx_dev, int32_t e_cap, int32_t* stats_dev, void* scratch_dev,
+                    int64_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Receiver-major view of an edge list for the deterministic segmented aggregation.
+ * Replaces the scatter inside jraph.segment_sum (third-party jraph 0.0.6.dev0; call site
+ * lagrangebench/models/gns.py:117-119).  Accepts ANY (2, e_cap) list (pad = index >= n):
+ * real edges are bucketed by receiver, each bucket in ascending list position (the order a
+ * sequential scatter-add would visit them).
+ *
+ *   rowptr   dev int32[n+1]   in-edges of receiver v occupy slots rowptr[v]..rowptr[v+1]
+ *   perm     dev int32[e_cap] slot -> position in the input list
+ *   snd, rcv dev int32[e_cap] sender / receiver per slot
+ *   rowptr[n] is the number of real edges (device-side; kernels read it there).
+ */
+int lb200_csr_build(const int32_t* idx_dev, int32_t n, int32_t e_cap, int32_t* rowptr_dev,
+                    int32_t* perm_dev, int32_t* snd_dev, int32_t* rcv_dev, void* scratch_dev,
+                    int64_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Feature transform.  Replaces feature_transform (features.py:47-126) for the columns the
+ * GNS consumes (models/gns.py:139-149), written as float32 (the jmp policy casts the
+ * model inputs to float32, lagrangebench/runner.py:71-72).
+ *
+ *   window     dev T[n][t_window][dim]   position history, most recent last
+ *   node_feat  dev float[n][node_stride] columns: vel_hist (K*dim) | vel_mag (K) |
+ *                                        bound (2*dim) | force (dim), each optional
+ *   edge_feat  dev float[e_cap][4]       rel_disp (dim) | rel_dist (1) | zero pad, in LIST order
+ *   force: piecewise-constant along one axis (covers the reference datasets' force.py:
+ *          RPF +-x by y, DAM gravity); force_mode 0 = none, 1 = piecewise,
+ *          2 = caller-provided dev float[n][dim] in force_dev.
+ */
+typedef struct {
+  int32_t n, dim, t_window, pos_f64, periodic;
+  double box[3];
+  double r_cutoff;
+  double vel_mean[3], vel_std[3];
+  int32_t magnitude_features;
+  int32_t bound_features;    /* features.py:87: only when no dimension is periodic */
+  double bounds_lo[3], bounds_hi[3];
+  int32_t force_mode;
+  int32_t force_axis;
+  double force_threshold;    /* pos[axis] > threshold ? force_hi : force_lo */
+  double force_lo[3], force_hi[3];
+  int32_t node_stride;       /* floats per node_feat row (>= number of feature columns) */
+} lb200_feature_cfg;
+
+int32_t lb200_node_feature_width(const lb200_feature_cfg* c);
+
+int lb200_features(const lb200_feature_cfg* c, const void* window_dev, const float* force_dev,
+                   const int32_t* idx_dev, int32_t e_cap, float* node_feat_dev,
+                   float* edge_feat_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * GNS forward.  Replaces GNS.__call__ (models/gns.py:159-171): type embedding, encoder
+ * (gns.py:65-81), num_mp_steps x jraph.GraphNetwork with residuals (gns.py:83-124),
+ * decoder (gns.py:126-133); build_mlp = Linear-ReLU-Linear(+LayerNorm)
+ * (models/utils.py:100-115).  All arithmetic float32.
+ *
+ * Weights: one device blob of floats; every matrix row-major (in, out) exactly as
+ * hk.Linear stores `w`.  Offsets (in floats) into the blob:
+ */
+typedef struct {
+  int64_t w0, b0, w1, b1, ln_scale, ln_offset; /* ln_* < 0: no LayerNorm */
+} lb200_mlp_off;
+
+typedef struct {
+  int32_t n, dim, num_mp_steps;
+  int32_t node_in;          /* node feature columns (without embedding) */
+  int32_t node_stride;      /* floats per node_feat row */
+  int32_t embed_size;       /* particle_type_embedding_size (16); 0 = no embedding */
+  int32_t num_particle_types;
+  int32_t e_cap;
+  int64_t embedding;        /* offset of the (num_particle_types, embed_size) table */
+  lb200_mlp_off enc_node, enc_edge, dec;
+  const lb200_mlp_off* proc_edge; /* host array [num_mp_steps] */
+  const lb200_mlp_off* proc_node; /* host array [num_mp_steps] */
+} lb200_gns_cfg;
+
+/* device scratch the forward needs, in bytes (node latents, projections, edge latents ...) */
+int64_t lb200_gns_scratch_bytes(int32_t n, int32_t e_cap);
+
+/*
+ *   node_feat, edge_feat  as produced by lb200_features (edge_feat in LIST order)
+ *   ptype                 dev int32[n]
+ *   rowptr/perm/snd/rcv   as produced by lb200_csr_build
+ *   out                   dev float[n][dim]  normalised acceleration ({"acc": ...})
+ */
+int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_dev, const float* node_feat_dev,
+                      const float* edge_feat_dev, const int32_t* ptype_dev,
+                      const int32_t* rowptr_dev, const int32_t* perm_dev, const int32_t* snd_dev,
+                      const int32_t* rcv_dev, float* out_dev, void* scratch_dev,
+                      int64_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Integrate + kinematic override + window shift.  Replaces case.integrate
+ * (case.py:230-259) followed by the tail of _forward_eval (evaluate/rollout.py:61-73):
+ *   acc = mean + out*std; v = disp(p[-1], p[-2]) + acc; p' = shift(p[-1], v);
+ *   p' = target where particle_type in {SOLID_WALL, MOVING_WALL, PAD};
+ *   window <- concat(window[:, 1:], p').
+ *   out_mode 0: "acc", 1: "vel", 2: "pos" (case.py:235-256)
+ *   target    dev T[n][dim] or NULL (no override)
+ *   pred_out  dev T[n][dim] or NULL: also receives p' (the rollout's prediction row)
+ *   skip_flag dev int32* or NULL: if *skip_flag != 0 the kernel does nothing (the neighbor
+ *             list overflowed; the host re-allocates and retries the same step,
+ *             evaluate/rollout.py:135-151)
+ */
+typedef struct {
+  int32_t n, dim, t_window, pos_f64, periodic, out_mode;
+  double box[3];
+  double mean[3], std[3]; /* acceleration (or velocity) normalisation */
+} lb200_integrate_cfg;
+
+int lb200_integrate(const lb200_integrate_cfg* c, const float* out_dev, void* window_dev,
+                    const int32_t* ptype_dev, const void* target_dev, void* pred_out_dev,
+                    const int32_t* skip_flag_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Device-resident rollout.  Replaces the body of the while-loop of _eval_batched_rollout
+ * (evaluate/rollout.py:125-169) for `n_steps` consecutive steps without a host round trip:
+ * neighbor update -> features -> forward -> integrate -> store prediction.  The blocking
+ * overflow read of rollout.py:135 becomes a device flag: once a step overflows, that step
+ * and all later ones are no-ops and status[0] holds the index of the first such step; the
+ * host then re-allocates and calls again from that step (same retry contract).
+ *
+ *   targets   dev T[n_steps][n][dim] or NULL  ground-truth positions for kinematic particles
+ *   preds     dev T[n_steps][n][dim]          predicted positions per step
+ *   status    dev int32[4]: [0] steps completed, [1] overflow bits, [2] last E, [3] reserved
+ */
+typedef struct {
+  lb200_grid grid;
+  lb200_feature_cfg feat;
+  lb200_gns_cfg gns;
+  lb200_integrate_cfg integ;
+  int32_t cell_capacity;
+  int32_t e_cap;
+} lb200_rollout_cfg;
+
+int64_t lb200_rollout_scratch_bytes(const lb200_rollout_cfg* c);
+
+int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, const float* weights_dev,
+                        void* window_dev, const int32_t* ptype_dev, const float* force_dev,
+                        const void* targets_dev, void* preds_dev, int32_t* idx_dev,
+                        int32_t* status_dev, void* scratch_dev, int64_t scratch_bytes,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): a cumulative count of kernels this library launched, and
+ * optional CUDA-event timing of the two message-passing kernels on their launch stream.
+ *   lb200_profile(1) enables + resets, lb200_profile(0) disables;
+ *   lb200_profile_read synchronises the recorded events and returns the summed device
+ *   time (ms) and launch count of [0] the edge (message+aggregate) kernel and [1] the
+ *   node-update kernel since the last reset.
+ */
+int64_t lb200_launch_count(void);
+int lb200_profile(int32_t enable);
+int lb200_profile_read(double* ms_out2, int64_t* launches_out2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LB200_H */

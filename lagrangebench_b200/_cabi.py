@@ -1,0 +1,136 @@
+"""ctypes binding of ``include/lb200.h`` (the C-ABI shared library ``_lb200.so``).
+
+There is no CPU fallback: if the library is missing and cannot be built, importing the
+compute path raises.  torch tensors are passed as raw device pointers + the current
+stream; nothing in the signatures is a torch type.
+"""
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_lb200.so")
+
+MAX_NODE_IN = 64
+LATENT = 128
+OVF_NEIGHBOR_LIST = 1
+OVF_CELL_LIST = 2
+
+
+class Grid(C.Structure):
+    _fields_ = [("n", C.c_int32), ("dim", C.c_int32), ("pos_f64", C.c_int32), ("periodic", C.c_int32),
+                ("box", C.c_double * 3), ("r_cutoff", C.c_double), ("use_cells", C.c_int32),
+                ("cells_per_side", C.c_int32 * 3), ("cell_size", C.c_float * 3), ("n_cells", C.c_int32),
+                ("n_cand_cells", C.c_int32)]
+
+
+class FeatureCfg(C.Structure):
+    _fields_ = [("n", C.c_int32), ("dim", C.c_int32), ("t_window", C.c_int32), ("pos_f64", C.c_int32),
+                ("periodic", C.c_int32), ("box", C.c_double * 3), ("r_cutoff", C.c_double),
+                ("vel_mean", C.c_double * 3), ("vel_std", C.c_double * 3),
+                ("magnitude_features", C.c_int32), ("bound_features", C.c_int32),
+                ("bounds_lo", C.c_double * 3), ("bounds_hi", C.c_double * 3),
+                ("force_mode", C.c_int32), ("force_axis", C.c_int32), ("force_threshold", C.c_double),
+                ("force_lo", C.c_double * 3), ("force_hi", C.c_double * 3), ("node_stride", C.c_int32)]
+
+
+class MlpOff(C.Structure):
+    _fields_ = [("w0", C.c_int64), ("b0", C.c_int64), ("w1", C.c_int64), ("b1", C.c_int64),
+                ("ln_scale", C.c_int64), ("ln_offset", C.c_int64)]
+
+
+class GnsCfg(C.Structure):
+    _fields_ = [("n", C.c_int32), ("dim", C.c_int32), ("num_mp_steps", C.c_int32), ("node_in", C.c_int32),
+                ("node_stride", C.c_int32), ("embed_size", C.c_int32), ("num_particle_types", C.c_int32),
+                ("e_cap", C.c_int32), ("embedding", C.c_int64), ("enc_node", MlpOff), ("enc_edge", MlpOff),
+                ("dec", MlpOff), ("proc_edge", C.POINTER(MlpOff)), ("proc_node", C.POINTER(MlpOff))]
+
+
+class IntegrateCfg(C.Structure):
+    _fields_ = [("n", C.c_int32), ("dim", C.c_int32), ("t_window", C.c_int32), ("pos_f64", C.c_int32),
+                ("periodic", C.c_int32), ("out_mode", C.c_int32), ("box", C.c_double * 3),
+                ("mean", C.c_double * 3), ("std", C.c_double * 3)]
+
+
+class RolloutCfg(C.Structure):
+    _fields_ = [("grid", Grid), ("feat", FeatureCfg), ("gns", GnsCfg), ("integ", IntegrateCfg),
+                ("cell_capacity", C.c_int32), ("e_cap", C.c_int32)]
+
+
+_VP, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64
+_SIGNATURES = {
+    "lb200_version": (C.c_int, []),
+    "lb200_error_string": (C.c_char_p, [C.c_int]),
+    "lb200_grid_init": (C.c_int, [C.POINTER(Grid), _I32, _I32, _I32, _I32, C.POINTER(C.c_double), C.c_double]),
+    "lb200_nbr_scratch_bytes": (_I64, [C.POINTER(Grid)]),
+    "lb200_csr_scratch_bytes": (_I64, [_I32, _I32]),
+    "lb200_nbr_build": (C.c_int, [C.POINTER(Grid), _VP, _I32, _VP, _I32, _VP, _VP, _I64, _VP]),
+    "lb200_csr_build": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _I64, _VP]),
+    "lb200_node_feature_width": (_I32, [C.POINTER(FeatureCfg)]),
+    "lb200_features": (C.c_int, [C.POINTER(FeatureCfg), _VP, _VP, _VP, _I32, _VP, _VP, _VP]),
+    "lb200_gns_scratch_bytes": (_I64, [_I32, _I32]),
+    "lb200_gns_forward": (C.c_int, [C.POINTER(GnsCfg), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP]),
+    "lb200_integrate": (C.c_int, [C.POINTER(IntegrateCfg), _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "lb200_rollout_scratch_bytes": (_I64, [C.POINTER(RolloutCfg)]),
+    "lb200_rollout_steps": (C.c_int, [C.POINTER(RolloutCfg), _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP]),
+    "lb200_launch_count": (_I64, []),
+    "lb200_profile": (C.c_int, [_I32]),
+    "lb200_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+}
+EXPORTED = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def library_path():
+    return _SO
+
+
+def load():
+    """Load (building first if the .so is absent and nvcc is available).  Raises otherwise."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        from . import build as _build
+
+        _build.build()
+    lib = C.CDLL(_SO)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().lb200_error_string(int(rc))
+        raise RuntimeError(f"lb200 call failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Raw device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "lb200 needs contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("lagrangebench_b200 has no CPU path: a CUDA device (B200, sm_100a) is required")
+
+
+def vec3(values, fill=0.0):
+    out = (C.c_double * 3)(fill, fill, fill)
+    for k, v in enumerate(values):
+        out[k] = float(v)
+    return out

@@ -1,0 +1,377 @@
+"""Case setup: host-side mirror of ``lagrangebench/case_setup/case.py`` over the C ABI.
+
+``case_builder`` keeps the reference's signature and returns the same seven callables
+(``case.py:32-59``); the neighbor search, feature transform and integrator run as CUDA
+kernels (``csrc/neighbor.cu``, ``csrc/features.cu``).  Arrays are torch CUDA tensors used
+as plain device allocations; numpy inputs are copied to the device.
+"""
+
+import ctypes as C
+import warnings
+from dataclasses import dataclass
+from typing import Callable, Dict
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .defaults import merged
+from .utils import resolve_dtype
+
+
+class PiecewiseForce:
+    """External force that is piecewise-constant along one axis, evaluated inside the
+    feature kernel: ``f(r) = hi if r[axis] > threshold else lo``.  Covers the force fields
+    the reference's datasets ship as ``force.py`` (RPF: ``+-e_x`` by ``y``; DAM: constant
+    gravity).  Also callable on a ``(N, d)`` tensor like a vectorised ``force_fn``."""
+
+    def __init__(self, axis, threshold, lo, hi):
+        self.axis, self.threshold = int(axis), float(threshold)
+        self.lo, self.hi = [float(v) for v in lo], [float(v) for v in hi]
+
+    @classmethod
+    def constant(cls, value):
+        return cls(0, float("inf"), value, value)
+
+    def __call__(self, r):
+        r = torch.as_tensor(r)
+        lo = torch.tensor(self.lo, dtype=r.dtype, device=r.device)
+        hi = torch.tensor(self.hi, dtype=r.dtype, device=r.device)
+        return torch.where((r[..., self.axis] > self.threshold)[..., None], hi, lo)
+
+
+class FeatureDict(dict):
+    """The reference's ``FeatureDict`` (``features.py:10``) plus a handle on the packed
+    device buffers the arrays are views of, so the model does not re-pack them."""
+
+    packed = None
+
+
+class NeighborList:
+    """Mirror of jax-md's ``NeighborList`` fields that lagrangebench uses
+    (``evaluate/rollout.py:135-151``, ``case_setup/features.py:110``)."""
+
+    def __init__(self, fn, idx, stats, reference_position, cell_list_capacity, max_occupancy, scratch):
+        self._fn = fn
+        self.idx = idx  # (2, E_cap) int32: row 0 receivers, row 1 senders; pad = N
+        self._stats = stats  # device int32[4]: E, max cell occupancy, overflow bits, -
+        self.reference_position = reference_position
+        self.cell_list_capacity = cell_list_capacity
+        self.max_occupancy = max_occupancy
+        self._scratch = scratch
+
+    @property
+    def did_buffer_overflow(self):
+        """0-dim bool device tensor; reading it on the host synchronises (as in the reference)."""
+        return self._stats[2] != 0
+
+    @property
+    def n_edges(self):
+        return int(self._stats[0].item())
+
+    def update(self, position, **kwargs):
+        return self._fn.update(position, self)
+
+    def tree_map(self, fn):  # lets utils.broadcast_* treat the list as a pytree of arrays
+        return NeighborList(self._fn, fn(self.idx), fn(self._stats), fn(self.reference_position),
+                            self.cell_list_capacity, self.max_occupancy, self._scratch)
+
+
+class _NeighborFn:
+    """``partition.neighbor_list(...)`` -> object with ``allocate`` / ``update``."""
+
+    def __init__(self, box, r_cutoff, periodic, multiplier, tdtype):
+        self.box = [float(b) for b in box]
+        self.dim = len(self.box)
+        self.r_cutoff = float(r_cutoff)
+        self.periodic = bool(periodic)
+        self.multiplier = float(multiplier)
+        self.tdtype = tdtype
+
+    def _grid(self, n):
+        lib = _cabi.load()
+        g = _cabi.Grid()
+        box = (C.c_double * 3)(*(self.box + [1.0] * (3 - self.dim)))
+        _cabi.check(lib.lb200_grid_init(C.byref(g), n, self.dim, int(self.tdtype == torch.float64),
+                                        int(self.periodic), box, self.r_cutoff))
+        return g
+
+    def _position(self, position):
+        _cabi.require_cuda()
+        p = torch.as_tensor(position)
+        if not p.is_cuda:
+            p = p.cuda()
+        return p.to(self.tdtype).contiguous()
+
+    def allocate(self, position, **kwargs):
+        lib = _cabi.load()
+        pos = self._position(position)
+        n = pos.shape[0]
+        g = self._grid(n)
+        nbytes = lib.lb200_nbr_scratch_bytes(C.byref(g))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=pos.device)
+        stats = torch.zeros(4, dtype=torch.int32, device=pos.device)
+        _cabi.check(lib.lb200_nbr_build(C.byref(g), _cabi.ptr(pos), 0, None, 0, _cabi.ptr(stats),
+                                        _cabi.ptr(scratch), nbytes, _cabi.stream()))
+        n_edges, max_occ = stats[:2].tolist()  # host read: allocate is un-jitted in the reference too
+        if g.use_cells:
+            cap = max(1, int(max_occ * self.multiplier))
+            n_cand = g.n_cand_cells * cap
+        else:
+            cap, n_cand = 0, n
+        e_cap = max(1, min(int(n_edges * self.multiplier), n * n_cand, n * n))
+        idx = torch.empty((2, e_cap), dtype=torch.int32, device=pos.device)
+        stats.zero_()
+        nl = NeighborList(self, idx, stats, pos, cap if g.use_cells else None, e_cap, scratch)
+        nl._grid = g
+        self._build(nl, pos)
+        return nl
+
+    def _build(self, nl, pos):
+        lib = _cabi.load()
+        g = nl._grid
+        _cabi.check(lib.lb200_nbr_build(C.byref(g), _cabi.ptr(pos), nl.cell_list_capacity or 0, _cabi.ptr(nl.idx),
+                                        nl.max_occupancy, _cabi.ptr(nl._stats), _cabi.ptr(nl._scratch),
+                                        nl._scratch.numel(), _cabi.stream()))
+
+    def update(self, position, nbrs, **kwargs):
+        """Rebuild into the list's own buffers (fixed capacity).  The returned object shares
+        ``idx`` with ``nbrs``; the overflow bits are sticky like jax-md's error code."""
+        pos = self._position(position)
+        if pos.shape[0] != nbrs._grid.n:
+            raise ValueError("number of particles changed: allocate a new neighbor list")
+        out = NeighborList(self, nbrs.idx, nbrs._stats, pos, nbrs.cell_list_capacity, nbrs.max_occupancy,
+                           nbrs._scratch)
+        out._grid = nbrs._grid
+        self._build(out, pos)
+        return out
+
+
+@dataclass
+class CaseSetupFn:
+    """``case.py:32-59``."""
+
+    allocate: Callable
+    preprocess: Callable
+    allocate_eval: Callable
+    preprocess_eval: Callable
+    integrate: Callable
+    displacement: Callable
+    normalization_stats: Dict
+
+
+def get_dataset_stats(metadata, is_isotropic_norm, noise_std, dtype=np.float64):
+    """``lagrangebench/data/utils.py:9-45`` evaluated in ``dtype`` (constants for the kernels)."""
+    dtype = np.dtype(dtype)
+    acc_mean = np.array(metadata["acc_mean"], dtype=dtype)
+    acc_std = np.array(metadata["acc_std"], dtype=dtype)
+    vel_mean = np.array(metadata["vel_mean"], dtype=dtype)
+    vel_std = np.array(metadata["vel_std"], dtype=dtype)
+    if is_isotropic_norm:
+        acc_mean = np.mean(acc_mean) * np.ones_like(acc_mean)
+        acc_std = np.sqrt(np.mean(acc_std**2)) * np.ones_like(acc_std)
+        vel_mean = np.mean(vel_mean) * np.ones_like(vel_mean)
+        vel_std = np.sqrt(np.mean(vel_std**2)) * np.ones_like(vel_std)
+    ns = dtype.type(noise_std)
+    return {
+        "acceleration": {"mean": acc_mean, "std": np.sqrt(acc_std**2 + ns**2)},
+        "velocity": {"mean": vel_mean, "std": np.sqrt(vel_std**2 + ns**2)},
+    }
+
+
+def _make_space(box, periodic, tdtype):
+    def _side(ref):
+        return torch.tensor(box, dtype=ref.dtype, device=ref.device)
+
+    def _mod(x, side):
+        r = torch.fmod(x, side)
+        return torch.where(r < 0, r + side, r)
+
+    def displacement(a, b):
+        a, b = torch.as_tensor(a), torch.as_tensor(b)
+        d = a - b
+        if not periodic:
+            return d
+        side = _side(d)
+        return _mod(d + side * 0.5, side) - side * 0.5
+
+    def shift(r, dr):
+        s = torch.as_tensor(r) + torch.as_tensor(dr)
+        return _mod(s, _side(s)) if periodic else s
+
+    return displacement, shift
+
+
+def case_builder(box, metadata, input_seq_length, cfg_neighbors=None, cfg_model=None, noise_std=3.0e-4,
+                 external_force_fn=None, dtype="float64"):
+    """Mirror of ``case_builder`` (``case.py:62-269``).
+
+    Differences from the reference, all outside the rollout path: ``allocate`` /
+    ``preprocess`` support ``noise_std == 0`` only (``add_gns_noise`` is a training
+    strategy); ``external_force_fn`` is ``None``, a :class:`PiecewiseForce` (evaluated in
+    the feature kernel) or a callable vectorised over ``(N, d)`` positions.
+    """
+    cfg_neighbors = merged("neighbors", cfg_neighbors)
+    cfg_model = merged("model", cfg_model)
+    tdtype = resolve_dtype(dtype)
+    npdtype = np.float64 if tdtype == torch.float64 else np.float32
+    box = [float(b) for b in np.asarray(box).reshape(-1)]
+    dim = len(box)
+    stats = get_dataset_stats(metadata, cfg_model["isotropic_norm"], noise_std, npdtype)
+    pbc = list(metadata["periodic_boundary_conditions"])
+    periodic = bool(np.array(pbc).any())  # case.py:104: PBC in all directions or not at all
+    displacement_fn, shift_fn = _make_space(box, periodic, tdtype)
+    radius = float(npdtype(metadata["default_connectivity_radius"]))
+    if cfg_neighbors["multiplier"] < 1.25:
+        warnings.warn(f"cfg_neighbors.multiplier={cfg_neighbors['multiplier']} < 1.25 is very low.")
+    neighbor_fn = _NeighborFn(box, radius, periodic, cfg_neighbors["multiplier"], tdtype)
+    isl = int(input_seq_length)
+
+    bounds = np.asarray(metadata["bounds"], dtype=npdtype)
+    force_mode = 0
+    if external_force_fn is not None:
+        force_mode = 1 if isinstance(external_force_fn, PiecewiseForce) else 2
+
+    def feature_cfg(n):
+        fc = _cabi.FeatureCfg()
+        fc.n, fc.dim, fc.t_window = n, dim, isl
+        fc.pos_f64, fc.periodic = int(tdtype == torch.float64), int(periodic)
+        fc.box = _cabi.vec3(box, 1.0)
+        fc.r_cutoff = radius
+        fc.vel_mean = _cabi.vec3(stats["velocity"]["mean"])
+        fc.vel_std = _cabi.vec3(stats["velocity"]["std"], 1.0)
+        fc.magnitude_features = int(bool(cfg_model["magnitude_features"]))
+        fc.bound_features = int(not any(pbc))  # features.py:87
+        fc.bounds_lo = _cabi.vec3(bounds[:, 0])
+        fc.bounds_hi = _cabi.vec3(bounds[:, 1])
+        fc.force_mode = force_mode
+        if force_mode == 1:
+            f = external_force_fn
+            fc.force_axis, fc.force_threshold = f.axis, min(f.threshold, 1e300)
+            fc.force_lo, fc.force_hi = _cabi.vec3(f.lo), _cabi.vec3(f.hi)
+        fc.node_stride = 0
+        fc.node_stride = _cabi.load().lb200_node_feature_width(C.byref(fc))
+        return fc
+
+    def integrate_cfg(n, t_window, out_mode):
+        ic = _cabi.IntegrateCfg()
+        ic.n, ic.dim, ic.t_window = n, dim, t_window
+        ic.pos_f64, ic.periodic, ic.out_mode = int(tdtype == torch.float64), int(periodic), out_mode
+        ic.box = _cabi.vec3(box, 1.0)
+        key = "velocity" if out_mode == 1 else "acceleration"
+        ic.mean = _cabi.vec3(stats[key]["mean"])
+        ic.std = _cabi.vec3(stats[key]["std"], 1.0)
+        return ic
+
+    def _to_device(x, dt=None):
+        _cabi.require_cuda()
+        t = torch.as_tensor(x)
+        if not t.is_cuda:
+            t = t.cuda()
+        return t if dt is None else t.to(dt)
+
+    def feature_transform(pos_input, neighbors):
+        """``features.py:47-126`` through ``lb200_features``."""
+        lib = _cabi.load()
+        n = pos_input.shape[0]
+        window = pos_input.contiguous()
+        fc = feature_cfg(n)
+        force = None
+        if force_mode == 2:
+            force = torch.as_tensor(external_force_fn(window[:, -1])).to(device=window.device, dtype=torch.float32)
+            force = force.contiguous()
+        e_cap = neighbors.idx.shape[1]
+        node_feat = torch.empty((n, fc.node_stride), dtype=torch.float32, device=window.device)
+        edge_feat = torch.empty((e_cap, 4), dtype=torch.float32, device=window.device)
+        _cabi.check(lib.lb200_features(C.byref(fc), _cabi.ptr(window), _cabi.ptr(force), _cabi.ptr(neighbors.idx),
+                                       e_cap, _cabi.ptr(node_feat), _cabi.ptr(edge_feat), _cabi.stream()))
+        k = isl - 1
+        feats = FeatureDict()
+        feats["abs_pos"] = window
+        col = k * dim
+        feats["vel_hist"] = node_feat[:, :col]
+        if fc.magnitude_features:
+            feats["vel_mag"] = node_feat[:, col:col + k]
+            col += k
+        if fc.bound_features:
+            feats["bound"] = node_feat[:, col:col + 2 * dim]
+            col += 2 * dim
+        if force_mode:
+            feats["force"] = node_feat[:, col:col + dim]
+            col += dim
+        feats["senders"] = neighbors.idx[1]
+        feats["receivers"] = neighbors.idx[0]
+        feats["rel_disp"] = edge_feat[:, :dim]
+        feats["rel_dist"] = edge_feat[:, dim:dim + 1]
+        feats.packed = {"node_feat": node_feat, "edge_feat": edge_feat, "idx": neighbors.idx, "n": n}
+        return feats
+
+    def _compute_target(pos_input):  # case.py:143-160
+        current_velocity = displacement_fn(pos_input[:, 1], pos_input[:, 0])
+        next_velocity = displacement_fn(pos_input[:, 2], pos_input[:, 1])
+        acc = next_velocity - current_velocity
+        dev = pos_input.device
+        a = {k: torch.as_tensor(v, device=dev) for k, v in stats["acceleration"].items()}
+        v = {k: torch.as_tensor(v, device=dev) for k, v in stats["velocity"].items()}
+        return {"acc": (acc - a["mean"]) / a["std"], "vel": (next_velocity - v["mean"]) / v["std"],
+                "pos": pos_input[:, -1]}
+
+    def _preprocess(sample, neighbors=None, is_allocate=False, mode="train", unroll_steps=0):
+        pos_input = _to_device(sample[0], tdtype)
+        most_recent_position = pos_input[:, isl - 1].contiguous()
+        if is_allocate:
+            neighbors = neighbor_fn.allocate(most_recent_position)
+        else:
+            neighbors = neighbors.update(most_recent_position)
+        features = feature_transform(pos_input[:, :isl], neighbors)
+        if mode == "train":
+            begin = isl - 2 + unroll_steps
+            return features, _compute_target(pos_input[:, begin:begin + 3]), neighbors
+        return features, neighbors
+
+    def _no_noise(noise_std):
+        if noise_std != 0.0:
+            raise NotImplementedError("random-walk noise (train/strats.py) is outside the rollout path")
+
+    def allocate_fn(key, sample, noise_std=0.0, unroll_steps=0):
+        _no_noise(noise_std)
+        f, t, n = _preprocess(sample, is_allocate=True, unroll_steps=unroll_steps)
+        return key, f, t, n
+
+    def preprocess_fn(key, sample, noise_std, neighbors, unroll_steps=0):
+        _no_noise(noise_std)
+        f, t, n = _preprocess(sample, neighbors, unroll_steps=unroll_steps)
+        return key, f, t, n
+
+    def allocate_eval_fn(sample):
+        return _preprocess(sample, is_allocate=True, mode="eval")
+
+    def preprocess_eval_fn(sample, neighbors):
+        return _preprocess(sample, neighbors, mode="eval")
+
+    def integrate_fn(normalized_in, position_sequence):
+        """``case.py:230-259`` through ``lb200_integrate`` on the last two positions."""
+        assert any(k in normalized_in for k in ("pos", "vel", "acc"))
+        out_mode = 2 if "pos" in normalized_in else (1 if "vel" in normalized_in else 0)
+        key = ("acc", "vel", "pos")[out_mode]
+        seq = _to_device(position_sequence, tdtype)
+        n = seq.shape[0]
+        window = seq[:, -2:].contiguous() if seq.shape[1] >= 2 else seq.repeat(1, 2, 1).contiguous()
+        net_out = _to_device(normalized_in[key], torch.float32).contiguous()
+        ptype = torch.zeros(n, dtype=torch.int32, device=window.device)
+        pred = torch.empty((n, dim), dtype=tdtype, device=window.device)
+        ic = integrate_cfg(n, 2, out_mode)
+        _cabi.check(_cabi.load().lb200_integrate(C.byref(ic), _cabi.ptr(net_out), _cabi.ptr(window),
+                                                 _cabi.ptr(ptype), None, _cabi.ptr(pred), None, _cabi.stream()))
+        return pred
+
+    case = CaseSetupFn(allocate_fn, preprocess_fn, allocate_eval_fn, preprocess_eval_fn, integrate_fn,
+                       displacement_fn, stats)
+    # handles for the device-resident rollout engine (not part of the reference surface)
+    case._lb200 = {
+        "box": box, "dim": dim, "dtype": tdtype, "periodic": periodic, "radius": radius, "isl": isl,
+        "multiplier": float(cfg_neighbors["multiplier"]), "neighbor_fn": neighbor_fn, "feature_cfg": feature_cfg,
+        "integrate_cfg": integrate_cfg, "force_mode": force_mode, "external_force_fn": external_force_fn,
+        "shift": shift_fn,
+    }
+    return case

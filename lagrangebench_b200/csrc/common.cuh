@@ -1,0 +1,95 @@
+// Shared device/host helpers for the lb200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lb200.h"
+
+#define LB_CHECK(expr)                            \
+  do {                                            \
+    cudaError_t _e = (expr);                      \
+    if (_e != cudaSuccess) return (int)_e;        \
+  } while (0)
+
+#define LB_LAUNCH_CHECK()                         \
+  do {                                            \
+    cudaError_t _e = cudaGetLastError();          \
+    if (_e != cudaSuccess) return (int)_e;        \
+  } while (0)
+
+namespace lb {
+
+constexpr int kLatent = LB200_LATENT;
+// Receiver-sorted edges per message tile / nodes per node tile.  The edge kernel and the
+// node kernel agree on the carry protocol through these two constants only.
+constexpr int kEdgeTile = 64;
+constexpr int kNodeTile = 64;
+
+// cumulative number of kernels launched by the library (lb200_launch_count)
+extern int64_t g_launches;
+#define LB_LAUNCHED(k) (::lb::g_launches += (k))
+
+// optional CUDA-event timing of a kernel class on its launch stream (lb200_profile)
+void prof_begin(int cls, cudaStream_t s);
+void prof_end(int cls, cudaStream_t s);
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Bump allocator over caller-provided scratch.
+struct Arena {
+  char* base;
+  int64_t off, cap;
+  Arena(void* p, int64_t bytes) : base((char*)p), off(0), cap(bytes) {}
+  template <typename T>
+  T* take(int64_t count) {
+    off = align_up(off, 256);
+    T* r = (T*)(base + off);
+    off += count * (int64_t)sizeof(T);
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+};
+
+// ---- rounding-exact arithmetic (no FMA contraction), matching NumPy / XLA-CPU elementwise ops
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ float fmod_x(float a, float b) { return fmodf(a, b); }
+__device__ __forceinline__ double fmod_x(double a, double b) { return fmod(a, b); }
+
+// jnp.mod for side > 0: C fmod, then + side where the remainder is negative.
+template <typename T>
+__device__ __forceinline__ T floor_mod(T x, T side) {
+  T r = fmod_x(x, side);
+  return r < T(0) ? add_rn(r, side) : r;
+}
+
+// space.periodic / space.free displacement of one component.
+template <typename T>
+__device__ __forceinline__ T disp1(T a, T b, T side, T half, bool periodic) {
+  T d = sub_rn(a, b);
+  if (periodic) d = sub_rn(floor_mod(add_rn(d, half), side), half);
+  return d;
+}
+
+template <typename T>
+__device__ __forceinline__ T shift1(T r, T dr, T side, bool periodic) {
+  T s = add_rn(r, dr);
+  return periodic ? floor_mod(s, side) : s;
+}
+
+// Exclusive scan of int32 (n elements -> n+1 outputs, out[n] = total).
+// scratch: int32[cdiv(n, 1024) + 1].
+int exclusive_scan_i32(const int32_t* in, int32_t* out, int n, int32_t* scratch, cudaStream_t s);
+static inline int64_t scan_scratch_elems(int64_t n) { return (n + 1023) / 1024 + 1; }
+
+}  // namespace lb

@@ -1,0 +1,619 @@
+// GNS forward: encoder, message passing (fused gather + edge MLP + LayerNorm + residual +
+// deterministic segmented sum), node update (+ next-layer projection), decoder.
+//
+// Replaces lagrangebench/models/gns.py:65-171 (GNS._encoder/_processor/_decoder) with
+// build_mlp of lagrangebench/models/utils.py:100-115 and the gather / segment_sum of
+// jraph.GraphNetwork (third-party, call site gns.py:117-119).
+//
+// Data layout in HBM (all float32, row-major):
+//   h    [N][128]      node latents
+//   P    [N][256]      per-node projections for the NEXT edge update: cols 0..127 =
+//                      h @ W1[0:128]  (sender part), cols 128..255 = h @ W1[128:256] + b1
+//                      (receiver part).  The first edge-MLP layer is linear in its concat
+//                      input [h_s, h_r, e] (gns.py:97-100), so its two node terms are hoisted
+//                      out of the per-edge work (E ~ 6.6-12.8 N): 131 072 -> 65 536 FLOP/edge.
+//   e    [E_cap][128]  edge latents in RECEIVER-MAJOR slot order (lb200_csr_build), so each
+//                      receiver's incoming messages are contiguous and summed in ascending
+//                      list order by exactly one tile -- no atomics, no zero-fill.
+//   agg  [N][128]      aggregated messages of receivers whose bucket lies inside one tile;
+//   carry_first/last [tiles][128]  partial sums of buckets that straddle a tile boundary,
+//                      combined (in tile order) by the node kernel.
+#include "common.cuh"
+
+namespace lb {
+
+constexpr int kThreads = 256;
+constexpr int kTM = 64;         // rows per tile (== kEdgeTile == kNodeTile)
+constexpr int kWChunk = 32;     // weight rows per cp.async stage
+constexpr int kLdA = kLatent + 4;
+constexpr int kEncK = LB200_MAX_NODE_IN;  // node-encoder input width, zero padded
+static_assert(kEdgeTile == kTM && kNodeTile == kTM, "tile constants");
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// column owned by accumulator slot j of thread-column tx: two float4 groups 64 apart
+__device__ __forceinline__ int col_of(int tx, int j) { return (j < 4 ? 0 : 64) + tx * 4 + (j & 3); }
+
+__device__ __forceinline__ void load_w_chunk(float* ws, const float* __restrict__ wg) {
+  // 32 x 128 floats = 1024 float4, 4 per thread
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int f = (threadIdx.x + i * kThreads) * 4;
+    cp_async16(ws + f, wg + f);
+  }
+}
+
+// acc[4][8] += A[64][K] (smem, row stride lda) @ W[K][128] (global, streamed through ws[2][32*128])
+template <int K>
+__device__ __forceinline__ void gemm_tile(float (&acc)[4][8], const float* As, int lda,
+                                          const float* __restrict__ wg, float* ws) {
+  static_assert(K % kWChunk == 0, "K");
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  constexpr int NC = K / kWChunk;
+  load_w_chunk(ws, wg);
+  cp_async_commit();
+#pragma unroll 1
+  for (int c = 0; c < NC; ++c) {
+    if (c + 1 < NC) {
+      load_w_chunk(ws + ((c + 1) & 1) * kWChunk * kLatent, wg + (int64_t)(c + 1) * kWChunk * kLatent);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* w = ws + (c & 1) * kWChunk * kLatent;
+    const float* a_base = As + (ty * 4) * lda + c * kWChunk;
+#pragma unroll
+    for (int kk = 0; kk < kWChunk; kk += 4) {
+      float4 a[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a_base + i * lda + kk);
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const float4 b0 = *reinterpret_cast<const float4*>(w + (kk + k4) * kLatent + tx * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(w + (kk + k4) * kLatent + 64 + tx * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float av = k4 == 0 ? a[i].x : (k4 == 1 ? a[i].y : (k4 == 2 ? a[i].z : a[i].w));
+          acc[i][0] = fmaf(av, b0.x, acc[i][0]);
+          acc[i][1] = fmaf(av, b0.y, acc[i][1]);
+          acc[i][2] = fmaf(av, b0.z, acc[i][2]);
+          acc[i][3] = fmaf(av, b0.w, acc[i][3]);
+          acc[i][4] = fmaf(av, b1.x, acc[i][4]);
+          acc[i][5] = fmaf(av, b1.y, acc[i][5]);
+          acc[i][6] = fmaf(av, b1.z, acc[i][6]);
+          acc[i][7] = fmaf(av, b1.w, acc[i][7]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void zero_acc(float (&acc)[4][8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+}
+
+__device__ __forceinline__ float half_warp_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  return v;
+}
+
+// hk.LayerNorm(axis=-1): (scale * rsqrt(var + 1e-5)) * (x - mean) + offset, biased variance
+__device__ __forceinline__ void layer_norm_rows(float (&y)[4][8], const float* __restrict__ scale,
+                                                const float* __restrict__ offset) {
+  const int tx = threadIdx.x & 15;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += y[i][j];
+    const float mean = half_warp_sum(s) * (1.0f / kLatent);
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = y[i][j] - mean;
+      v = fmaf(d, d, v);
+    }
+    const float var = half_warp_sum(v) * (1.0f / kLatent);
+    const float inv = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = col_of(tx, j);
+      y[i][j] = fmaf(scale[c] * inv, y[i][j] - mean, offset[c]);
+    }
+  }
+}
+
+__device__ __forceinline__ void add_bias(float (&y)[4][8], const float* __restrict__ b, bool relu) {
+  const int tx = threadIdx.x & 15;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float bv = b[col_of(tx, j)];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v = y[i][j] + bv;
+      y[i][j] = relu ? fmaxf(v, 0.f) : v;
+    }
+  }
+}
+
+// registers -> smem tile (row stride lda), columns of this thread
+__device__ __forceinline__ void store_tile_smem(const float (&y)[4][8], float* dst, int lda) {
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float* r = dst + (ty * 4 + i) * lda;
+    *reinterpret_cast<float4*>(r + tx * 4) = make_float4(y[i][0], y[i][1], y[i][2], y[i][3]);
+    *reinterpret_cast<float4*>(r + 64 + tx * 4) = make_float4(y[i][4], y[i][5], y[i][6], y[i][7]);
+  }
+}
+
+// registers -> global rows [row0, row0 + rows) of a [*][ld] matrix at column offset col0
+__device__ __forceinline__ void store_tile_global(const float (&y)[4][8], float* __restrict__ dst, int64_t row0,
+                                                  int rows, int ld, int col0) {
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty * 4 + i;
+    if (r < rows) {
+      float* p = dst + (row0 + r) * ld + col0;
+      *reinterpret_cast<float4*>(p + tx * 4) = make_float4(y[i][0], y[i][1], y[i][2], y[i][3]);
+      *reinterpret_cast<float4*>(p + 64 + tx * 4) = make_float4(y[i][4], y[i][5], y[i][6], y[i][7]);
+    }
+  }
+}
+
+struct MlpW {
+  const float *w0, *b0, *w1, *b1, *lns, *lno;
+};
+
+// P = h @ [W1[0:128] | W1[128:256]] (+ b1 on the receiver half) for the next edge update.
+__device__ __forceinline__ void project_next(const float* hs, int lda, const MlpW& nxt, float* ws,
+                                             float* __restrict__ P, int64_t row0, int rows) {
+  float acc[4][8];
+  zero_acc(acc);
+  gemm_tile<kLatent>(acc, hs, lda, nxt.w0, ws);
+  store_tile_global(acc, P, row0, rows, 2 * kLatent, 0);
+  zero_acc(acc);
+  gemm_tile<kLatent>(acc, hs, lda, nxt.w0 + kLatent * kLatent, ws);
+  add_bias(acc, nxt.b0, false);
+  store_tile_global(acc, P, row0, rows, 2 * kLatent, kLatent);
+}
+
+// ------------------------------------------------------------------ node encoder
+struct NodeEncArgs {
+  int n, node_in, node_stride, embed, n_types;
+  const float* node_feat;
+  const int32_t* ptype;
+  const float* embedding;
+  MlpW enc;   // w0 zero-padded to kEncK rows
+  MlpW nxt;   // processor edge MLP of step 0 (for P)
+  float *h, *P;
+};
+
+__global__ void __launch_bounds__(kThreads, 2) node_encoder_kernel(NodeEncArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                       // [64][kEncK + 4]
+  float* Hs = As + kTM * (kEncK + 4);     // [64][kLdA]
+  float* ws = Hs + kTM * kLdA;            // [2][32][128]
+  const int64_t row0 = (int64_t)blockIdx.x * kTM;
+  const int rows = min(kTM, a.n - (int)row0);
+  constexpr int lda = kEncK + 4;
+  for (int f = threadIdx.x; f < kTM * kEncK; f += kThreads) {
+    const int r = f / kEncK, c = f % kEncK;
+    float v = 0.f;
+    if (r < rows) {
+      if (c < a.node_in) {
+        v = a.node_feat[(row0 + r) * a.node_stride + c];
+      } else if (c < a.node_in + a.embed) {
+        int t = a.ptype[row0 + r];
+        t = min(max(t, 0), a.n_types - 1);
+        v = a.embedding[t * a.embed + (c - a.node_in)];
+      }
+    }
+    As[r * lda + c] = v;
+  }
+  __syncthreads();
+  float acc[4][8];
+  zero_acc(acc);
+  gemm_tile<kEncK>(acc, As, lda, a.enc.w0, ws);
+  add_bias(acc, a.enc.b0, true);
+  store_tile_smem(acc, Hs, kLdA);
+  __syncthreads();
+  zero_acc(acc);
+  gemm_tile<kLatent>(acc, Hs, kLdA, a.enc.w1, ws);
+  add_bias(acc, a.enc.b1, false);
+  layer_norm_rows(acc, a.enc.lns, a.enc.lno);
+  store_tile_global(acc, a.h, row0, rows, kLatent, 0);
+  store_tile_smem(acc, Hs, kLdA);  // gemm_tile ended with a barrier: Hs is free
+  __syncthreads();
+  project_next(Hs, kLdA, a.nxt, ws, a.P, row0, rows);
+}
+
+// ------------------------------------------------------------------ edge encoder
+struct EdgeEncArgs {
+  int n;
+  const int32_t* rowptr;  // rowptr[n] = number of real edges
+  const int32_t* perm;
+  const float4* edge_feat;  // LIST order
+  MlpW enc;                 // w0 zero-padded to 4 rows
+  float* e;
+};
+
+__global__ void __launch_bounds__(kThreads, 2) edge_encoder_kernel(EdgeEncArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* Hs = smem;               // [64][kLdA]
+  float* ws = Hs + kTM * kLdA;    // [2][32][128]
+  float* w0s = ws + 2 * kWChunk * kLatent;  // [4][128]
+  float4* efs = reinterpret_cast<float4*>(w0s + 4 * kLatent);  // [64]
+  const int E = a.rowptr[a.n];
+  const int64_t slot0 = (int64_t)blockIdx.x * kTM;
+  if (slot0 >= E) return;
+  const int rows = min(kTM, E - (int)slot0);
+  for (int f = threadIdx.x; f < 4 * kLatent; f += kThreads) w0s[f] = a.enc.w0[f];
+  if (threadIdx.x < kTM)
+    efs[threadIdx.x] = threadIdx.x < rows ? a.edge_feat[a.perm[slot0 + threadIdx.x]] : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 f = efs[ty * 4 + i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = col_of(tx, j);
+      float v = f.x * w0s[c];
+      v = fmaf(f.y, w0s[kLatent + c], v);
+      v = fmaf(f.z, w0s[2 * kLatent + c], v);
+      v = fmaf(f.w, w0s[3 * kLatent + c], v);
+      acc[i][j] = v;
+    }
+  }
+  add_bias(acc, a.enc.b0, true);
+  store_tile_smem(acc, Hs, kLdA);
+  __syncthreads();
+  zero_acc(acc);
+  gemm_tile<kLatent>(acc, Hs, kLdA, a.enc.w1, ws);
+  add_bias(acc, a.enc.b1, false);
+  layer_norm_rows(acc, a.enc.lns, a.enc.lno);
+  store_tile_global(acc, a.e, slot0, rows, kLatent, 0);
+}
+
+// ------------------------------------------------------------------ message passing: edges
+struct EdgeMpArgs {
+  int n;
+  const int32_t *rowptr, *snd, *rcv;
+  const float* P;  // [n][256]
+  MlpW mlp;        // w0 = (384,128): rows 256..383 act on the edge latent; b0 is folded into P
+  float *e, *agg, *carry_first, *carry_last;
+};
+
+__global__ void __launch_bounds__(kThreads, 2) edge_mp_kernel(EdgeMpArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* A1 = smem;                 // [64][kLdA]  e_old
+  float* A2 = A1 + kTM * kLdA;      // [64][kLdA]  hidden, then e'
+  float* ws = A2 + kTM * kLdA;      // [2][32][128]
+  int* sidx = reinterpret_cast<int*>(ws + 2 * kWChunk * kLatent);  // [64]
+  int* ridx = sidx + kTM;                                          // [64 + 2] (+ neighbours of the tile)
+  const int E = a.rowptr[a.n];
+  const int64_t slot0 = (int64_t)blockIdx.x * kTM;
+  if (slot0 >= E) return;
+  const int rows = min(kTM, E - (int)slot0);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  if (threadIdx.x < kTM) {
+    const bool ok = threadIdx.x < rows;
+    sidx[threadIdx.x] = ok ? a.snd[slot0 + threadIdx.x] : 0;
+    ridx[threadIdx.x] = ok ? a.rcv[slot0 + threadIdx.x] : -1;
+  } else if (threadIdx.x == kTM) {
+    ridx[kTM] = slot0 > 0 ? a.rcv[slot0 - 1] : -2;                 // receiver just before the tile
+    ridx[kTM + 1] = slot0 + rows < E ? a.rcv[slot0 + rows] : -3;   // receiver just after the tile
+  }
+  for (int f = threadIdx.x; f < kTM * (kLatent / 4); f += kThreads) {
+    const int r = f / (kLatent / 4), c4 = f % (kLatent / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows) v = *reinterpret_cast<const float4*>(a.e + (slot0 + r) * kLatent + c4 * 4);
+    *reinterpret_cast<float4*>(A1 + r * kLdA + c4 * 4) = v;
+  }
+  __syncthreads();
+  float acc[4][8];
+  zero_acc(acc);
+  gemm_tile<kLatent>(acc, A1, kLdA, a.mlp.w0 + 2 * kLatent * kLatent, ws);
+  // hidden = relu(e @ W1e + P_s[snd] + P_r[rcv])   (b1 is inside P_r)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty * 4 + i;
+    const int s = sidx[r], rc = max(ridx[r], 0);
+    const float* ps = a.P + (int64_t)s * (2 * kLatent);
+    const float* pr = a.P + (int64_t)rc * (2 * kLatent) + kLatent;
+    const float4 s0 = *reinterpret_cast<const float4*>(ps + tx * 4);
+    const float4 s1 = *reinterpret_cast<const float4*>(ps + 64 + tx * 4);
+    const float4 r0 = *reinterpret_cast<const float4*>(pr + tx * 4);
+    const float4 r1 = *reinterpret_cast<const float4*>(pr + 64 + tx * 4);
+    acc[i][0] = fmaxf(acc[i][0] + s0.x + r0.x, 0.f);
+    acc[i][1] = fmaxf(acc[i][1] + s0.y + r0.y, 0.f);
+    acc[i][2] = fmaxf(acc[i][2] + s0.z + r0.z, 0.f);
+    acc[i][3] = fmaxf(acc[i][3] + s0.w + r0.w, 0.f);
+    acc[i][4] = fmaxf(acc[i][4] + s1.x + r1.x, 0.f);
+    acc[i][5] = fmaxf(acc[i][5] + s1.y + r1.y, 0.f);
+    acc[i][6] = fmaxf(acc[i][6] + s1.z + r1.z, 0.f);
+    acc[i][7] = fmaxf(acc[i][7] + s1.w + r1.w, 0.f);
+  }
+  store_tile_smem(acc, A2, kLdA);
+  __syncthreads();
+  zero_acc(acc);
+  gemm_tile<kLatent>(acc, A2, kLdA, a.mlp.w1, ws);
+  add_bias(acc, a.mlp.b1, false);
+  layer_norm_rows(acc, a.mlp.lns, a.mlp.lno);
+  store_tile_smem(acc, A2, kLdA);  // e' (the message), for the column-wise segmented sum
+  // residual: e <- e' + e (gns.py:120-122)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float* o = A1 + (ty * 4 + i) * kLdA;
+    const float4 o0 = *reinterpret_cast<const float4*>(o + tx * 4);
+    const float4 o1 = *reinterpret_cast<const float4*>(o + 64 + tx * 4);
+    acc[i][0] += o0.x; acc[i][1] += o0.y; acc[i][2] += o0.z; acc[i][3] += o0.w;
+    acc[i][4] += o1.x; acc[i][5] += o1.y; acc[i][6] += o1.z; acc[i][7] += o1.w;
+  }
+  store_tile_global(acc, a.e, slot0, rows, kLatent, 0);
+  __syncthreads();
+  // deterministic segmented sum over receivers: one thread per column walks the tile's rows
+  if (threadIdx.x < kLatent) {
+    const int c = threadIdx.x;
+    const bool first_cont = ridx[kTM] == ridx[0];
+    const bool last_cont = ridx[kTM + 1] == ridx[rows - 1];
+    float sum = 0.f;
+    int seg_start = 0;
+    for (int r = 0; r < rows; ++r) {
+      sum += A2[r * kLdA + c];
+      const bool end = (r == rows - 1) || (ridx[r + 1] != ridx[r]);
+      if (end) {
+        if (seg_start == 0 && first_cont)
+          a.carry_first[(int64_t)blockIdx.x * kLatent + c] = sum;
+        else if (r == rows - 1 && last_cont)
+          a.carry_last[(int64_t)blockIdx.x * kLatent + c] = sum;
+        else
+          a.agg[(int64_t)ridx[r] * kLatent + c] = sum;
+        sum = 0.f;
+        seg_start = r + 1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ message passing: nodes
+struct NodeMpArgs {
+  int n, dim, last;
+  const int32_t* rowptr;
+  const float *agg, *carry_first, *carry_last;
+  MlpW mlp;  // w0 = (256,128): rows 0..127 act on h, 128..255 on the aggregate
+  MlpW nxt;  // next step's edge MLP (projection) or the decoder when last
+  float *h, *P, *out;
+};
+
+__global__ void __launch_bounds__(kThreads, 2) node_mp_kernel(NodeMpArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int lda = 2 * kLatent + 4;
+  float* As = smem;               // [64][260]: h | agg, later h_new | hidden
+  float* ws = As + kTM * lda;     // [2][32][128]
+  const int64_t row0 = (int64_t)blockIdx.x * kTM;
+  const int rows = min(kTM, a.n - (int)row0);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  for (int f = threadIdx.x; f < kTM * (kLatent / 4); f += kThreads) {
+    const int r = f / (kLatent / 4), c4 = f % (kLatent / 4);
+    float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), av = hv;
+    if (r < rows) {
+      const int64_t v = row0 + r;
+      hv = *reinterpret_cast<const float4*>(a.h + v * kLatent + c4 * 4);
+      const int e0 = a.rowptr[v], e1 = a.rowptr[v + 1];
+      if (e1 > e0) {
+        const int ta = e0 / kEdgeTile, tb = (e1 - 1) / kEdgeTile;
+        if (ta == tb) {
+          av = *reinterpret_cast<const float4*>(a.agg + v * kLatent + c4 * 4);
+        } else {  // bucket straddles tiles: partial sums in tile order
+          av = *reinterpret_cast<const float4*>(a.carry_last + (int64_t)ta * kLatent + c4 * 4);
+          for (int t = ta + 1; t <= tb; ++t) {
+            const float4 p = *reinterpret_cast<const float4*>(a.carry_first + (int64_t)t * kLatent + c4 * 4);
+            av.x += p.x; av.y += p.y; av.z += p.z; av.w += p.w;
+          }
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(As + r * lda + c4 * 4) = hv;
+    *reinterpret_cast<float4*>(As + r * lda + kLatent + c4 * 4) = av;
+  }
+  __syncthreads();
+  float acc[4][8];
+  zero_acc(acc);
+  gemm_tile<2 * kLatent>(acc, As, lda, a.mlp.w0, ws);
+  add_bias(acc, a.mlp.b0, true);
+  store_tile_smem(acc, As + kLatent, lda);  // hidden over the aggregate half
+  __syncthreads();
+  zero_acc(acc);
+  gemm_tile<kLatent>(acc, As + kLatent, lda, a.mlp.w1, ws);
+  add_bias(acc, a.mlp.b1, false);
+  layer_norm_rows(acc, a.mlp.lns, a.mlp.lno);
+  // residual: h <- n' + h (gns.py:120-122); each thread owns its (row, col) elements of As
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float* o = As + (ty * 4 + i) * lda;
+    const float4 o0 = *reinterpret_cast<const float4*>(o + tx * 4);
+    const float4 o1 = *reinterpret_cast<const float4*>(o + 64 + tx * 4);
+    acc[i][0] += o0.x; acc[i][1] += o0.y; acc[i][2] += o0.z; acc[i][3] += o0.w;
+    acc[i][4] += o1.x; acc[i][5] += o1.y; acc[i][6] += o1.z; acc[i][7] += o1.w;
+  }
+  store_tile_smem(acc, As, lda);
+  if (!a.last) store_tile_global(acc, a.h, row0, rows, kLatent, 0);
+  __syncthreads();
+  if (!a.last) {
+    project_next(As, lda, a.nxt, ws, a.P, row0, rows);
+    return;
+  }
+  // decoder (gns.py:126-133): Linear(128,128) - ReLU - Linear(128,dim), no LayerNorm
+  zero_acc(acc);
+  gemm_tile<kLatent>(acc, As, lda, a.nxt.w0, ws);
+  add_bias(acc, a.nxt.b0, true);
+  for (int k = 0; k < a.dim; ++k) {
+    float wk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wk[j] = a.nxt.w1[col_of(tx, j) * a.dim + k];
+    const float bk = a.nxt.b1[k];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float p = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p = fmaf(acc[i][j], wk[j], p);
+      p = half_warp_sum(p);
+      const int r = ty * 4 + i;
+      if (tx == 0 && r < rows) a.out[(row0 + r) * a.dim + k] = p + bk;
+    }
+  }
+}
+
+static MlpW mlp_ptrs(const float* w, const lb200_mlp_off& o) {
+  MlpW m;
+  m.w0 = w + o.w0;
+  m.b0 = w + o.b0;
+  m.w1 = w + o.w1;
+  m.b1 = w + o.b1;
+  m.lns = o.ln_scale >= 0 ? w + o.ln_scale : nullptr;
+  m.lno = o.ln_offset >= 0 ? w + o.ln_offset : nullptr;
+  return m;
+}
+
+constexpr int kSmemNodeEnc = (kTM * (kEncK + 4) + kTM * kLdA + 2 * kWChunk * kLatent) * 4;
+constexpr int kSmemEdgeEnc = (kTM * kLdA + 2 * kWChunk * kLatent + 4 * kLatent) * 4 + kTM * 16;
+constexpr int kSmemEdgeMp = (2 * kTM * kLdA + 2 * kWChunk * kLatent) * 4 + (2 * kTM + 2) * 4;
+constexpr int kSmemNodeMp = (kTM * (2 * kLatent + 4) + 2 * kWChunk * kLatent) * 4;
+
+static int set_smem_once() {
+  static int done = 0;
+  static int rc = 0;
+  if (done) return rc;
+  cudaError_t e;
+  e = cudaFuncSetAttribute(node_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNodeEnc);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(edge_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEdgeEnc);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(edge_mp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEdgeMp);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(node_mp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNodeMp);
+  rc = (int)e;
+  done = 1;
+  return rc;
+}
+
+}  // namespace lb
+
+using namespace lb;
+
+extern "C" int64_t lb200_gns_scratch_bytes(int32_t n, int32_t e_cap) {
+  int64_t nt = cdiv(e_cap, kEdgeTile) + 1;
+  int64_t b = 0;
+  b += align_up((int64_t)n * kLatent * 4, 256);        // h
+  b += align_up((int64_t)n * 2 * kLatent * 4, 256);    // P
+  b += align_up((int64_t)n * kLatent * 4, 256);        // agg
+  b += align_up((int64_t)e_cap * kLatent * 4, 256);    // e
+  b += 2 * align_up(nt * kLatent * 4, 256);            // carries
+  return b + 4096;
+}
+
+extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_dev, const float* node_feat_dev,
+                                 const float* edge_feat_dev, const int32_t* ptype_dev, const int32_t* rowptr_dev,
+                                 const int32_t* perm_dev, const int32_t* snd_dev, const int32_t* rcv_dev,
+                                 float* out_dev, void* scratch_dev, int64_t scratch_bytes, void* stream) {
+  if (!c || !weights_dev || !node_feat_dev || !edge_feat_dev || !ptype_dev || !rowptr_dev || !perm_dev ||
+      !snd_dev || !rcv_dev || !out_dev || !scratch_dev)
+    return LB200_EINVAL;
+  if (c->num_mp_steps < 1 || c->node_in + c->embed_size > kEncK || (c->dim != 2 && c->dim != 3) || c->e_cap < 1)
+    return LB200_EUNSUPPORTED;
+  int rc = set_smem_once();
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = c->n, e_cap = c->e_cap;
+  const int nt = cdiv(e_cap, kEdgeTile);
+  Arena ar(scratch_dev, scratch_bytes);
+  float* h = ar.take<float>((int64_t)n * kLatent);
+  float* P = ar.take<float>((int64_t)n * 2 * kLatent);
+  float* agg = ar.take<float>((int64_t)n * kLatent);
+  float* e = ar.take<float>((int64_t)e_cap * kLatent);
+  float* cf = ar.take<float>((int64_t)(nt + 1) * kLatent);
+  float* cl = ar.take<float>((int64_t)(nt + 1) * kLatent);
+  if (!ar.ok()) return LB200_EINVAL;
+  const float* w = weights_dev;
+
+  NodeEncArgs ne;
+  ne.n = n;
+  ne.node_in = c->node_in;
+  ne.node_stride = c->node_stride;
+  ne.embed = c->embed_size;
+  ne.n_types = c->num_particle_types;
+  ne.node_feat = node_feat_dev;
+  ne.ptype = ptype_dev;
+  ne.embedding = w + c->embedding;
+  ne.enc = mlp_ptrs(w, c->enc_node);
+  ne.nxt = mlp_ptrs(w, c->proc_edge[0]);
+  ne.h = h;
+  ne.P = P;
+  { node_encoder_kernel<<<cdiv(n, kTM), kThreads, kSmemNodeEnc, s>>>(ne); LB_LAUNCHED(1); }
+
+  EdgeEncArgs ee;
+  ee.n = n;
+  ee.rowptr = rowptr_dev;
+  ee.perm = perm_dev;
+  ee.edge_feat = reinterpret_cast<const float4*>(edge_feat_dev);
+  ee.enc = mlp_ptrs(w, c->enc_edge);
+  ee.e = e;
+  { edge_encoder_kernel<<<nt, kThreads, kSmemEdgeEnc, s>>>(ee); LB_LAUNCHED(1); }
+
+  for (int m = 0; m < c->num_mp_steps; ++m) {
+    EdgeMpArgs em;
+    em.n = n;
+    em.rowptr = rowptr_dev;
+    em.snd = snd_dev;
+    em.rcv = rcv_dev;
+    em.P = P;
+    em.mlp = mlp_ptrs(w, c->proc_edge[m]);
+    em.e = e;
+    em.agg = agg;
+    em.carry_first = cf;
+    em.carry_last = cl;
+    prof_begin(0, s);
+    { edge_mp_kernel<<<nt, kThreads, kSmemEdgeMp, s>>>(em); LB_LAUNCHED(1); }
+    prof_end(0, s);
+
+    NodeMpArgs nm;
+    nm.n = n;
+    nm.dim = c->dim;
+    nm.last = m == c->num_mp_steps - 1;
+    nm.rowptr = rowptr_dev;
+    nm.agg = agg;
+    nm.carry_first = cf;
+    nm.carry_last = cl;
+    nm.mlp = mlp_ptrs(w, c->proc_node[m]);
+    nm.nxt = nm.last ? mlp_ptrs(w, c->dec) : mlp_ptrs(w, c->proc_edge[m + 1]);
+    nm.h = h;
+    nm.P = P;
+    nm.out = out_dev;
+    prof_begin(1, s);
+    { node_mp_kernel<<<cdiv(n, kTM), kThreads, kSmemNodeMp, s>>>(nm); LB_LAUNCHED(1); }
+    prof_end(1, s);
+  }
+  LB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,173 @@
+// Device-resident rollout: the body of _eval_batched_rollout's while-loop
+// (lagrangebench/evaluate/rollout.py:125-169) for several consecutive steps, enqueued on one
+// stream with no host round trip.  The reference's blocking overflow read (rollout.py:135)
+// becomes a sticky device flag that turns the remaining integrate steps into no-ops.
+#include <vector>
+
+#include "common.cuh"
+
+namespace lb {
+
+int64_t g_launches = 0;
+
+// ---- optional per-kernel-class CUDA-event timing (bench.py's roofline leg)
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;       // start/stop pairs, reused after each read
+  std::vector<int> cls;                // class of pair i
+  size_t used = 0;                     // pairs handed out since the last reset
+  cudaEvent_t pending_start = nullptr;
+};
+static ProfState g_prof;
+
+void prof_begin(int cls, cudaStream_t s) {
+  if (!g_prof.on) return;
+  if (g_prof.used * 2 + 2 > g_prof.pool.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    g_prof.pool.push_back(a);
+    g_prof.pool.push_back(b);
+    g_prof.cls.push_back(cls);
+  }
+  g_prof.cls[g_prof.used] = cls;
+  cudaEventRecord(g_prof.pool[g_prof.used * 2], s);
+}
+
+void prof_end(int cls, cudaStream_t s) {
+  (void)cls;
+  if (!g_prof.on || g_prof.used * 2 + 2 > g_prof.pool.size()) return;
+  cudaEventRecord(g_prof.pool[g_prof.used * 2 + 1], s);
+  g_prof.used += 1;
+}
+
+template <typename T>
+__global__ void extract_last_kernel(const T* __restrict__ window, int n, int tw, int dim, T* __restrict__ pos) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n * dim) return;
+  int i = f / dim, k = f % dim;
+  pos[f] = window[((int64_t)i * tw + (tw - 1)) * dim + k];
+}
+
+// status: [0] steps completed, [1] overflow bits, [2] last E
+__global__ void rollout_step_done_kernel(const int32_t* __restrict__ nbr_stats, int32_t* status) {
+  status[2] = nbr_stats[0];
+  status[1] |= nbr_stats[2];
+  if (nbr_stats[2] == 0) status[0] += 1;
+}
+
+__global__ void rollout_init_kernel(int32_t* nbr_stats, int32_t* status) {
+  nbr_stats[0] = nbr_stats[1] = nbr_stats[2] = nbr_stats[3] = 0;
+  status[0] = status[1] = status[2] = status[3] = 0;
+}
+
+struct RolloutBufs {
+  void* pos;
+  int32_t *stats, *rowptr, *perm, *snd, *rcv;
+  float *node_feat, *edge_feat, *out;
+  void *nbr_scratch, *csr_scratch, *gns_scratch;
+  int64_t nbr_bytes, csr_bytes, gns_bytes;
+};
+
+static bool carve(const lb200_rollout_cfg* c, void* scratch, int64_t bytes, RolloutBufs* b, int64_t* need) {
+  const int64_t n = c->grid.n, e_cap = c->e_cap;
+  Arena ar(scratch, bytes);
+  b->pos = ar.take<double>(n * 3);
+  b->stats = ar.take<int32_t>(8);
+  b->rowptr = ar.take<int32_t>(n + 1);
+  b->perm = ar.take<int32_t>(e_cap);
+  b->snd = ar.take<int32_t>(e_cap);
+  b->rcv = ar.take<int32_t>(e_cap);
+  b->node_feat = ar.take<float>(n * c->feat.node_stride);
+  b->edge_feat = ar.take<float>(e_cap * 4);
+  b->out = ar.take<float>(n * 3);
+  b->nbr_bytes = lb200_nbr_scratch_bytes(&c->grid);
+  b->csr_bytes = lb200_csr_scratch_bytes((int32_t)n, (int32_t)e_cap);
+  b->gns_bytes = lb200_gns_scratch_bytes((int32_t)n, (int32_t)e_cap);
+  b->nbr_scratch = ar.take<char>(b->nbr_bytes);
+  b->csr_scratch = ar.take<char>(b->csr_bytes);
+  b->gns_scratch = ar.take<char>(b->gns_bytes);
+  if (need) *need = ar.off + 4096;
+  return scratch == nullptr ? true : ar.ok();
+}
+
+}  // namespace lb
+
+using namespace lb;
+
+extern "C" int lb200_version(void) { return 100; }
+
+extern "C" int64_t lb200_launch_count(void) { return g_launches; }
+
+extern "C" int lb200_profile(int32_t enable) {
+  g_prof.on = enable != 0;
+  g_prof.used = 0;
+  return 0;
+}
+
+extern "C" int lb200_profile_read(double* ms_out2, int64_t* launches_out2) {
+  if (!ms_out2 || !launches_out2) return LB200_EINVAL;
+  ms_out2[0] = ms_out2[1] = 0.0;
+  launches_out2[0] = launches_out2[1] = 0;
+  for (size_t i = 0; i < g_prof.used; ++i) {
+    LB_CHECK(cudaEventSynchronize(g_prof.pool[2 * i + 1]));
+    float ms = 0.f;
+    LB_CHECK(cudaEventElapsedTime(&ms, g_prof.pool[2 * i], g_prof.pool[2 * i + 1]));
+    int c = g_prof.cls[i] == 0 ? 0 : 1;
+    ms_out2[c] += ms;
+    launches_out2[c] += 1;
+  }
+  g_prof.used = 0;
+  return 0;
+}
+
+extern "C" const char* lb200_error_string(int code) {
+  if (code == 0) return "success";
+  if (code == LB200_EINVAL) return "lb200: invalid argument";
+  if (code == LB200_EUNSUPPORTED) return "lb200: unsupported configuration";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "lb200: unknown error";
+}
+
+extern "C" int64_t lb200_rollout_scratch_bytes(const lb200_rollout_cfg* c) {
+  RolloutBufs b;
+  int64_t need = 0;
+  carve(c, nullptr, 0, &b, &need);
+  return need;
+}
+
+extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, const float* weights_dev,
+                                   void* window_dev, const int32_t* ptype_dev, const float* force_dev,
+                                   const void* targets_dev, void* preds_dev, int32_t* idx_dev,
+                                   int32_t* status_dev, void* scratch_dev, int64_t scratch_bytes, void* stream) {
+  if (!c || !weights_dev || !window_dev || !ptype_dev || !idx_dev || !status_dev || !scratch_dev || n_steps < 0)
+    return LB200_EINVAL;
+  RolloutBufs b;
+  if (!carve(c, scratch_dev, scratch_bytes, &b, nullptr)) return LB200_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = c->grid.n, dim = c->grid.dim, tw = c->feat.t_window;
+  const int64_t esz = c->grid.pos_f64 ? 8 : 4;
+  { rollout_init_kernel<<<1, 1, 0, s>>>(b.stats, status_dev); LB_LAUNCHED(1); }
+  for (int t = 0; t < n_steps; ++t) {
+    if (c->grid.pos_f64)
+      { extract_last_kernel<double><<<cdiv(n * dim, 256), 256, 0, s>>>((const double*)window_dev, n, tw, dim, (double*)b.pos); LB_LAUNCHED(1); }
+    else
+      { extract_last_kernel<float><<<cdiv(n * dim, 256), 256, 0, s>>>((const float*)window_dev, n, tw, dim, (float*)b.pos); LB_LAUNCHED(1); }
+    int rc = lb200_nbr_build(&c->grid, b.pos, c->cell_capacity, idx_dev, c->e_cap, b.stats, b.nbr_scratch,
+                             b.nbr_bytes, stream);
+    if (rc) return rc;
+    rc = lb200_csr_build(idx_dev, n, c->e_cap, b.rowptr, b.perm, b.snd, b.rcv, b.csr_scratch, b.csr_bytes, stream);
+    if (rc) return rc;
+    rc = lb200_features(&c->feat, window_dev, force_dev, idx_dev, c->e_cap, b.node_feat, b.edge_feat, stream);
+    if (rc) return rc;
+    rc = lb200_gns_forward(&c->gns, weights_dev, b.node_feat, b.edge_feat, ptype_dev, b.rowptr, b.perm, b.snd, b.rcv,
+                           b.out, b.gns_scratch, b.gns_bytes, stream);
+    if (rc) return rc;
+    const char* tgt = targets_dev ? (const char*)targets_dev + (int64_t)t * n * dim * esz : nullptr;
+    char* prd = preds_dev ? (char*)preds_dev + (int64_t)t * n * dim * esz : nullptr;
+    rc = lb200_integrate(&c->integ, b.out, window_dev, ptype_dev, tgt, prd, b.stats + 2, stream);
+    if (rc) return rc;
+    { rollout_step_done_kernel<<<1, 1, 0, s>>>(b.stats, status_dev); LB_LAUNCHED(1); }
+  }
+  LB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,301 @@
+"""Rollout evaluation: host-side mirror of ``lagrangebench/evaluate/rollout.py``.
+
+``infer`` / ``eval_rollout`` keep the reference signatures.  When the model is this
+package's :class:`~lagrangebench_b200.models.GNS`, the step loop of
+``_eval_batched_rollout`` (``rollout.py:125-169``) runs device-resident through
+``lb200_rollout_steps`` -- one host synchronisation per chunk of steps instead of one
+per step -- with the reference's overflow contract (re-allocate, retry the same step).
+Any other ``model_apply`` callable goes through the generic per-step loop, whose stages
+(neighbor update, features, integrate) are still the CUDA kernels.
+"""
+
+import ctypes as C
+import os
+import pickle
+import time
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .defaults import merged
+from .models import GNS, gns_cfg
+from .utils import broadcast_from_batch, get_kinematic_mask, load_haiku, set_seed
+
+
+# ----------------------------------------------------------------------------- metrics
+class MetricsComputer:
+    """Position metrics of ``lagrangebench/evaluate/metrics.py:17-147`` that live on the
+    rollout path: ``mse``, ``mae`` (+ horizon slices) and ``e_kin``.  ``sinkhorn`` is an
+    O(N^2) optimal-transport solve outside the hot path and is not provided."""
+
+    METRICS = ["mse", "mae", "e_kin"]
+
+    def __init__(self, active_metrics, dist_fn, metadata, input_seq_length, stride=10, loss_ranges=None,
+                 ot_backend=None):
+        active_metrics = list(active_metrics or [])
+        unsupported = [m for m in active_metrics if m not in self.METRICS]
+        if unsupported:
+            raise NotImplementedError(f"metrics {unsupported} are outside the rollout hot path")
+        self._active_metrics = active_metrics
+        self._dist_fn = dist_fn
+        self._loss_ranges = loss_ranges or [1, 5, 10, 20, 50, 100]
+        self._input_seq_length = input_seq_length
+        self._stride = stride
+        self._metadata = metadata
+
+    def __call__(self, pred_rollout, target_rollout):
+        pred = torch.as_tensor(pred_rollout)
+        target = torch.as_tensor(target_rollout).to(device=pred.device, dtype=pred.dtype)
+        metrics = {}
+        for name in self._active_metrics:
+            if name in ("mse", "mae"):
+                d = self._dist_fn(pred, target)
+                per_step = (d**2).mean(dim=(1, 2)) if name == "mse" else d.abs().mean(dim=(1, 2))
+                metrics[name] = per_step
+                for i in self._loss_ranges:
+                    if i < per_step.shape[0]:
+                        metrics[f"{name}{i}"] = per_step[:i]
+            elif name == "e_kin":
+                dt = self._metadata["dt"] * self._metadata["write_every"]
+                dx, dim = self._metadata["dx"], self._metadata["dim"]
+
+                def e_kin(roll):
+                    vel = self._dist_fn(roll[1::self._stride], roll[0:-1:self._stride]) / dt
+                    return (vel**2).sum(dim=(1, 2)) * dx**dim  # metrics.py:98-125,157-160
+
+                ep, et = e_kin(pred), e_kin(target)
+                metrics[name] = {"predicted": ep, "target": et, "mse": ((ep - et) ** 2).mean()}
+        return metrics
+
+
+def averaged_metrics(eval_metrics):
+    """Trajectory-averaged scalars (``metrics.py:233-252``) for the supported metrics."""
+    out = {}
+    for m in eval_metrics.values():
+        for k, v in m.items():
+            if k == "e_kin":
+                out.setdefault("e_kin", []).append(float(v["mse"]))
+            elif k in ("mse", "mae") or k[:3] in ("mse", "mae"):
+                out.setdefault(k, []).append(float(torch.as_tensor(v).mean()))
+    return {f"val/{k}": float(np.mean(v)) for k, v in out.items()}
+
+
+# ----------------------------------------------------------------------------- engine
+class RolloutEngine:
+    """Owns the device state of one device-resident rollout (weights blob, scratch, status)."""
+
+    def __init__(self, case, model, params, steps_per_sync=32):
+        if not isinstance(model, GNS):
+            raise TypeError("RolloutEngine drives lagrangebench_b200.models.GNS")
+        self.case, self.model = case, model
+        self.h = case._lb200
+        if self.h["force_mode"] == 2:
+            raise NotImplementedError("a generic Python force callable needs the per-step loop")
+        self.packed = model.packed_params(params)
+        self.steps_per_sync = int(steps_per_sync)
+        self._cfg = None
+        self._scratch = None
+        self.n_reallocations = 0
+        self.n_launch_calls = 0
+
+    def _configure(self, neighbors):
+        lib = _cabi.load()
+        h = self.h
+        n = neighbors._grid.n
+        cfg = _cabi.RolloutCfg()
+        cfg.grid = neighbors._grid
+        cfg.feat = h["feature_cfg"](n)
+        cfg.gns = gns_cfg(self.packed, n, neighbors.max_occupancy, cfg.feat.node_stride, cfg.feat.node_stride)
+        cfg.integ = h["integrate_cfg"](n, h["isl"], 0)
+        cfg.cell_capacity = neighbors.cell_list_capacity or 0
+        cfg.e_cap = neighbors.max_occupancy
+        nbytes = lib.lb200_rollout_scratch_bytes(C.byref(cfg))
+        if self._scratch is None or self._scratch.numel() < nbytes:
+            self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=neighbors.idx.device)
+        self._cfg = cfg
+
+    def run(self, window, particle_type, targets, n_steps, neighbors=None):
+        """Advance ``window`` (N, isl, d) in place by ``n_steps``.
+
+        ``targets`` (n_steps, N, d) or None supplies the positions of kinematic particles.
+        Returns ``(predictions (n_steps, N, d), neighbors)``."""
+        lib = _cabi.load()
+        h = self.h
+        assert window.is_cuda and window.is_contiguous() and window.dtype == h["dtype"]
+        n, isl, dim = window.shape
+        dev = window.device
+        ptype = torch.as_tensor(particle_type).to(dev, torch.int32).contiguous()
+        if neighbors is None:
+            neighbors = h["neighbor_fn"].allocate(window[:, -1].contiguous())
+        self._configure(neighbors)
+        preds = torch.empty((n_steps, n, dim), dtype=window.dtype, device=dev)
+        if targets is not None:
+            targets = targets.to(dev, window.dtype).contiguous()
+            assert targets.shape == (n_steps, n, dim)
+        status = torch.zeros(4, dtype=torch.int32, device=dev)
+        done = 0
+        while done < n_steps:
+            chunk = min(self.steps_per_sync, n_steps - done)
+            tgt = _cabi.ptr(targets[done:done + chunk]) if targets is not None else None
+            _cabi.check(lib.lb200_rollout_steps(
+                C.byref(self._cfg), chunk, _cabi.ptr(self.packed.blob), _cabi.ptr(window), _cabi.ptr(ptype), None,
+                tgt, _cabi.ptr(preds[done:done + chunk]), _cabi.ptr(neighbors.idx), _cabi.ptr(status),
+                _cabi.ptr(self._scratch), self._scratch.numel(), _cabi.stream()))
+            self.n_launch_calls += 1
+            completed, overflow, _, _ = status.tolist()  # the one host sync per chunk
+            done += completed
+            if overflow:  # rollout.py:135-151: re-allocate from the current state, retry the step
+                self.n_reallocations += 1
+                neighbors = h["neighbor_fn"].allocate(window[:, -1].contiguous())
+                self._configure(neighbors)
+        return preds, neighbors
+
+
+# ----------------------------------------------------------------------------- reference loop
+def _forward_eval(params, state, sample, current_positions, target_positions, model_apply, case_integrate):
+    """``rollout.py:31-75`` (generic path: any ``model_apply``)."""
+    _, particle_type = sample
+    pred, state = model_apply(params, state, sample)
+    next_position = torch.as_tensor(case_integrate(pred, current_positions))
+    mask = get_kinematic_mask(torch.as_tensor(particle_type).to(next_position.device))
+    target_positions = torch.as_tensor(target_positions).to(next_position.device, next_position.dtype)
+    next_position = torch.where(mask[:, None], target_positions, next_position)
+    current_positions = torch.cat([current_positions[:, 1:], next_position[:, None, :]], dim=1)
+    return current_positions, state
+
+
+def _eval_batched_rollout(model_apply, case, params, state, traj_batch_i, neighbors, metrics_computer,
+                          n_rollout_steps, t_window, n_extrap_steps=0, engine=None):
+    """``rollout.py:78-178``.  The reference ``vmap``s over the batch; here trajectories of
+    a batch are rolled out one after the other.  Returns
+    ``(predictions (B, T, N, d), [metrics per trajectory], neighbors)``."""
+    _cabi.require_cuda()
+    h = case._lb200
+    pos_input_batch = torch.as_tensor(traj_batch_i[0])
+    particle_type_batch = torch.as_tensor(traj_batch_i[1])
+    bsz, n_nodes, t_total, dim = pos_input_batch.shape
+    if n_rollout_steps == -1:
+        n_rollout_steps = t_total - t_window
+    traj_len = n_rollout_steps + n_extrap_steps
+    dev = torch.device("cuda")
+    predictions, metrics = [], []
+    for b in range(bsz):
+        pos_b = pos_input_batch[b].to(dev, h["dtype"])
+        ptype = particle_type_batch[b].to(dev, torch.int32)
+        current = pos_b[:, :t_window].contiguous()
+        targets = pos_b[:, t_window:t_window + traj_len].permute(1, 0, 2).contiguous()  # (T, N, d)
+        if targets.shape[0] < traj_len:  # extrapolation: JAX clamps the step index (rollout.py:158)
+            pad = targets[-1:].expand(traj_len - targets.shape[0], -1, -1)
+            targets = torch.cat([targets, pad], dim=0).contiguous()
+        if engine is not None:
+            preds, neighbors = engine.run(current, ptype, targets, traj_len, neighbors)
+        else:
+            preds = torch.empty((traj_len, n_nodes, dim), dtype=h["dtype"], device=dev)
+            st, step = state, 0
+            while step < traj_len:
+                features, neighbors = case.preprocess_eval((current, ptype), neighbors)
+                if bool(neighbors.did_buffer_overflow):  # rollout.py:135: blocking read
+                    _, neighbors = case.allocate_eval((current, ptype))
+                    continue
+                current, st = _forward_eval(params, st, (features, ptype), current, targets[step], model_apply,
+                                            case.integrate)
+                preds[step] = current[:, -1]
+                step += 1
+        predictions.append(preds)
+        if metrics_computer is not None:
+            gt = pos_b[:, t_window:t_window + n_rollout_steps].permute(1, 0, 2)
+            metrics.append(metrics_computer(preds[:n_rollout_steps], gt))
+        else:
+            metrics.append({})
+    return torch.stack(predictions), metrics, neighbors
+
+
+class SimpleLoader:
+    """Minimal stand-in for the reference's torch ``DataLoader`` + ``numpy_collate``
+    (``rollout.py:363-369``): yields ``(pos (B, N, T, d), particle_type (B, N))``."""
+
+    def __init__(self, dataset, batch_size):
+        self.dataset, self.batch_size = dataset, int(batch_size)
+
+    def __iter__(self):
+        n = len(self.dataset)
+        for a in range(0, n, self.batch_size):
+            items = [self.dataset[i] for i in range(a, min(n, a + self.batch_size))]
+            yield (np.stack([np.asarray(p) for p, _ in items]), np.stack([np.asarray(t) for _, t in items]))
+
+
+def _to_numpy(tree):
+    if isinstance(tree, dict):
+        return {k: _to_numpy(v) for k, v in tree.items()}
+    if isinstance(tree, torch.Tensor):
+        return tree.detach().cpu().numpy()
+    return tree
+
+
+def eval_rollout(model_apply, case, params, state, loader_eval, neighbors, metrics_computer, n_rollout_steps,
+                 n_trajs, rollout_dir, out_type="none", n_extrap_steps=0):
+    """``rollout.py:181-308``: roll out ``n_trajs`` trajectories, compute metrics, optionally
+    write ``rollout_{i}.pkl`` with keys ``predicted_rollout`` / ``ground_truth_rollout`` /
+    ``particle_type`` (``rollout.py:271-275``)."""
+    batch_size = loader_eval.batch_size
+    t_window = loader_eval.dataset.input_seq_length
+    eval_metrics = {}
+    if rollout_dir is not None:
+        os.makedirs(rollout_dir, exist_ok=True)
+    model = getattr(model_apply, "__self__", None)
+    engine = None
+    if isinstance(model, GNS) and case._lb200["force_mode"] != 2:
+        engine = RolloutEngine(case, model, params)
+    ind = -1
+    for i, traj_batch_i in enumerate(loader_eval):
+        n_traj_left = n_trajs - i * batch_size
+        if n_traj_left <= 0:
+            break
+        if n_traj_left < batch_size:
+            traj_batch_i = tuple(x[:n_traj_left] for x in traj_batch_i)
+        rollout_batch, metrics_batch, neighbors = _eval_batched_rollout(
+            model_apply, case, params, state, traj_batch_i, neighbors, metrics_computer, n_rollout_steps, t_window,
+            n_extrap_steps, engine=engine)
+        for j in range(rollout_batch.shape[0]):
+            ind = i * batch_size + j
+            eval_metrics[f"rollout_{ind}"] = metrics_batch[j]
+            if rollout_dir is not None and out_type == "pkl":
+                pos_input = np.asarray(traj_batch_i[0][j]).transpose(1, 0, 2)  # (t, nodes, dim)
+                example_full = np.concatenate([pos_input[:t_window], rollout_batch[j].cpu().numpy()])
+                payload = {"predicted_rollout": example_full, "ground_truth_rollout": pos_input,
+                           "particle_type": np.asarray(traj_batch_i[1][j])}
+                with open(os.path.join(rollout_dir, f"rollout_{ind}.pkl"), "wb") as f:
+                    pickle.dump(payload, f)
+            elif rollout_dir is not None and out_type == "vtk":
+                raise NotImplementedError("vtk output (evaluate/utils.py) is outside the rollout hot path")
+        if ind + 1 >= n_trajs:
+            break
+    if rollout_dir is not None:
+        t = time.strftime("%Y_%m_%d_%H_%M_%S", time.localtime())
+        with open(f"{rollout_dir}/metrics{t}.pkl", "wb") as f:
+            pickle.dump(_to_numpy(eval_metrics), f)
+    return eval_metrics
+
+
+def infer(model, case, data_test, params=None, state=None, load_ckp=None, cfg_eval_infer=None, rollout_dir=None,
+          n_rollout_steps=20, seed=0):
+    """``rollout.py:311-399``."""
+    assert params is not None or load_ckp is not None, \
+        "Either params or a load_ckp directory must be provided for inference."
+    cfg = merged("eval.infer", cfg_eval_infer)
+    n_trajs = cfg["n_trajs"]
+    if n_trajs == -1:
+        n_trajs = data_test.num_samples if hasattr(data_test, "num_samples") else len(data_test)
+    if params is not None:
+        state = {} if state is None else state
+    else:
+        params, state, _, _ = load_haiku(load_ckp)
+    set_seed(seed)
+    loader_test = SimpleLoader(data_test, cfg["batch_size"])
+    metrics_computer = MetricsComputer(cfg["metrics"], case.displacement, data_test.metadata,
+                                       data_test.input_seq_length, cfg["metrics_stride"])
+    pos0, ptype0 = data_test[0]
+    _, _, _, neighbors = case.allocate(seed, (pos0, ptype0))
+    return eval_rollout(model.apply, case, params, state, loader_test, neighbors, metrics_computer, n_rollout_steps,
+                        n_trajs, rollout_dir, cfg["out_type"], cfg["n_extrap_steps"])

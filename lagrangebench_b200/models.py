@@ -1,0 +1,261 @@
+"""GNS model: host-side mirror of ``lagrangebench/models/gns.py`` over the C ABI.
+
+``GNS(...)`` keeps the reference constructor (``gns.py:35-43``) and exposes the
+``init`` / ``apply`` pair the reference obtains from
+``hk.without_apply_rng(hk.transform_with_state(model_fn))`` (``runner.py:67``):
+``apply(params, state, (features, particle_type)) -> ({"acc": (N, d)}, state)``.
+``params`` is haiku's nested dict ``{module_path: {"w","b"|"scale","offset"|"embeddings"}}``
+of arrays; it is packed once into a single device blob (``pack_params``).
+The forward itself is ``lb200_gns_forward`` (``csrc/gns.cu``).
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .utils import NodeType
+
+_ALIGN = 64  # floats
+
+
+def _suffix_lookup(params, suffix):
+    hits = [k for k in params if k == suffix or k.endswith("/" + suffix) or k.endswith(suffix)]
+    if len(hits) != 1:
+        raise KeyError(f"expected exactly one parameter module ending in '{suffix}', found {hits}")
+    return params[hits[0]]
+
+
+def _mlp_modules(params, scope, idx, layer_norm=True):
+    s = "" if idx == 0 else f"_{idx}"
+    l0 = _suffix_lookup(params, f"{scope}/MLP{s}/~/linear_0")
+    l1 = _suffix_lookup(params, f"{scope}/MLP{s}/~/linear_1")
+    ln = _suffix_lookup(params, f"{scope}/layer_norm{s}") if layer_norm else None
+    return l0, l1, ln
+
+
+class PackedParams:
+    """One contiguous float32 device blob + the offset table ``lb200_gns_cfg`` expects."""
+
+    def __init__(self, blob, embedding, enc_node, enc_edge, dec, proc_edge, proc_node, node_in_total, embed_size,
+                 num_types, dim, num_mp_steps):
+        self.blob = blob
+        self.embedding = embedding
+        self.enc_node, self.enc_edge, self.dec = enc_node, enc_edge, dec
+        self.proc_edge, self.proc_node = proc_edge, proc_node  # ctypes arrays (kept alive here)
+        self.node_in_total = node_in_total  # node features + embedding
+        self.embed_size, self.num_types, self.dim, self.num_mp_steps = embed_size, num_types, dim, num_mp_steps
+
+
+def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
+    """haiku params -> :class:`PackedParams`.  Matrices stay row-major ``(in, out)`` as
+    ``hk.Linear`` stores them; the node-encoder input matrix is zero-padded to
+    ``LB200_MAX_NODE_IN`` rows and the edge-encoder one to 4 rows."""
+    if latent != _cabi.LATENT:
+        raise NotImplementedError(f"kernels are specialised for latent_dim={_cabi.LATENT}")
+    chunks, cursor = [], [0]
+
+    def put(arr, rows_pad=None):
+        a = np.asarray(arr, dtype=np.float32)
+        if rows_pad is not None:
+            if a.shape[0] > rows_pad:
+                raise NotImplementedError(f"input width {a.shape[0]} > supported {rows_pad}")
+            a = np.concatenate([a, np.zeros((rows_pad - a.shape[0],) + a.shape[1:], np.float32)], axis=0)
+        off = cursor[0]
+        flat = a.reshape(-1)
+        pad = (-flat.size) % _ALIGN
+        chunks.append(flat)
+        if pad:
+            chunks.append(np.zeros(pad, np.float32))
+        cursor[0] += flat.size + pad
+        return off
+
+    def put_mlp(mods, in_rows, out_cols, rows_pad=None):
+        l0, l1, ln = mods
+        w0, w1 = np.asarray(l0["w"]), np.asarray(l1["w"])
+        if w0.shape != (in_rows, latent) or w1.shape != (latent, out_cols):
+            raise ValueError(f"unexpected MLP shapes {w0.shape}, {w1.shape}; only 2-layer MLPs "
+                             f"(num_mlp_layers=2) of width {latent} are supported")
+        o = _cabi.MlpOff()
+        o.w0, o.b0 = put(w0, rows_pad), put(l0["b"])
+        o.w1, o.b1 = put(w1), put(l1["b"])
+        o.ln_scale = put(ln["scale"]) if ln is not None else -1
+        o.ln_offset = put(ln["offset"]) if ln is not None else -1
+        return o
+
+    emb_mod = None
+    for k in params:
+        if k.endswith("embed"):
+            emb_mod = params[k]
+    enc_node_mods = _mlp_modules(params, "_encoder", 0)
+    node_in_total = int(np.asarray(enc_node_mods[0]["w"]).shape[0])
+    if emb_mod is not None:
+        emb = np.asarray(emb_mod["embeddings"], dtype=np.float32)
+        num_types, embed_size = emb.shape
+        embedding = put(emb)
+    else:
+        num_types, embed_size, embedding = 1, 0, put(np.zeros(1, np.float32))
+    enc_edge_mods = _mlp_modules(params, "_encoder", 1)
+    edge_in = int(np.asarray(enc_edge_mods[0]["w"]).shape[0])
+    if edge_in != dim + 1:
+        raise ValueError(f"edge encoder expects {edge_in} inputs, dim+1 = {dim + 1}")
+    enc_node = put_mlp(enc_node_mods, node_in_total, latent, rows_pad=_cabi.MAX_NODE_IN)
+    enc_edge = put_mlp(enc_edge_mods, edge_in, latent, rows_pad=4)
+    proc_edge = (_cabi.MlpOff * num_mp_steps)()
+    proc_node = (_cabi.MlpOff * num_mp_steps)()
+    for m in range(num_mp_steps):
+        proc_edge[m] = put_mlp(_mlp_modules(params, "_processor", 2 * m), 3 * latent, latent)
+        proc_node[m] = put_mlp(_mlp_modules(params, "_processor", 2 * m + 1), 2 * latent, latent)
+    dec = put_mlp(_mlp_modules(params, "_decoder", 0, layer_norm=False), latent, dim)
+    blob = torch.from_numpy(np.concatenate(chunks)).to(device)
+    return PackedParams(blob, embedding, enc_node, enc_edge, dec, proc_edge, proc_node, node_in_total, embed_size,
+                        num_types, dim, num_mp_steps)
+
+
+def gns_cfg(packed, n, e_cap, node_in, node_stride):
+    c = _cabi.GnsCfg()
+    c.n, c.dim, c.num_mp_steps = n, packed.dim, packed.num_mp_steps
+    c.node_in, c.node_stride = node_in, node_stride
+    c.embed_size, c.num_particle_types = packed.embed_size, packed.num_types
+    c.e_cap = e_cap
+    c.embedding = packed.embedding
+    c.enc_node, c.enc_edge, c.dec = packed.enc_node, packed.enc_edge, packed.dec
+    c.proc_edge = C.cast(packed.proc_edge, C.POINTER(_cabi.MlpOff))
+    c.proc_node = C.cast(packed.proc_node, C.POINTER(_cabi.MlpOff))
+    if node_in + packed.embed_size != packed.node_in_total:
+        raise ValueError(f"node features ({node_in}) + embedding ({packed.embed_size}) != encoder input "
+                         f"({packed.node_in_total})")
+    return c
+
+
+def init_params(node_in, dim, latent=128, num_mp_steps=10, embed=16, num_types=int(NodeType.SIZE), seed=0):
+    """Fresh parameters with haiku's default initialisers (Linear: truncated normal
+    ``1/sqrt(fan_in)``, zero bias; LayerNorm: ones / zeros; Embed: truncated normal 1)."""
+    rng = np.random.default_rng(seed)
+
+    def tn(shape, std):
+        x = rng.standard_normal(shape)
+        bad = np.abs(x) > 2.0
+        while bad.any():
+            x[bad] = rng.standard_normal(int(bad.sum()))
+            bad = np.abs(x) > 2.0
+        return (x * std).astype(np.float32)
+
+    params = {}
+    if num_types > 1:
+        params["gns/~/embed"] = {"embeddings": tn((num_types, embed), 1.0)}
+    else:
+        embed = 0
+
+    def add(scope, idx, fan_in, out, ln=True):
+        s = "" if idx == 0 else f"_{idx}"
+        params[f"gns/~{scope}/MLP{s}/~/linear_0"] = {"w": tn((fan_in, latent), fan_in ** -0.5),
+                                                    "b": np.zeros(latent, np.float32)}
+        params[f"gns/~{scope}/MLP{s}/~/linear_1"] = {"w": tn((latent, out), latent ** -0.5),
+                                                    "b": np.zeros(out, np.float32)}
+        if ln:
+            params[f"gns/~{scope}/layer_norm{s}"] = {"scale": np.ones(out, np.float32),
+                                                    "offset": np.zeros(out, np.float32)}
+
+    add("_encoder", 0, node_in + embed, latent)
+    add("_encoder", 1, dim + 1, latent)
+    for m in range(num_mp_steps):
+        add("_processor", 2 * m, 3 * latent, latent)
+        add("_processor", 2 * m + 1, 2 * latent, latent)
+    add("_decoder", 0, latent, dim, ln=False)
+    return params
+
+
+class GNS:
+    """Graph Network-based Simulator (``gns.py:18-171``), forward on the GPU."""
+
+    def __init__(self, particle_dimension, latent_size, blocks_per_step, num_mp_steps,
+                 particle_type_embedding_size, num_particle_types=int(NodeType.SIZE)):
+        if latent_size != _cabi.LATENT:
+            raise NotImplementedError(f"kernels are specialised for latent_size={_cabi.LATENT}")
+        if blocks_per_step != 2:
+            raise NotImplementedError("kernels are specialised for 2-layer MLPs (num_mlp_layers=2)")
+        self._output_size = int(particle_dimension)
+        self._latent_size = int(latent_size)
+        self._blocks_per_step = int(blocks_per_step)
+        self._mp_steps = int(num_mp_steps)
+        self._num_particle_types = int(num_particle_types)
+        self._embedding_size = int(particle_type_embedding_size) if num_particle_types > 1 else 0
+        self._packed = {}
+        self._bufs = {}
+
+    # -- hk.transform_with_state surface ---------------------------------------------
+    def init(self, key, sample):
+        """-> ``(params, state)``; ``key`` is an int seed (or anything hashable to one)."""
+        features, _ = sample
+        node_in = sum(int(np.prod(features[k].shape[1:])) for k in ("vel_hist", "vel_mag", "bound", "force")
+                      if k in features)
+        seed = key if isinstance(key, int) else abs(hash(str(key))) % (2**31)
+        params = init_params(node_in, self._output_size, self._latent_size, self._mp_steps,
+                             self._embedding_size, self._num_particle_types, seed)
+        return params, {}
+
+    def packed_params(self, params):
+        key = id(params)
+        hit = self._packed.get(key)
+        if hit is None or hit[0] is not params:
+            _cabi.require_cuda()
+            pk = pack_params(params, self._mp_steps, self._output_size, self._latent_size)
+            self._packed = {key: (params, pk)}  # keep one (the reference re-uses one params tree)
+            hit = self._packed[key]
+        return hit[1]
+
+    def _buffers(self, n, e_cap, device):
+        key = (n, e_cap, str(device))
+        b = self._bufs.get(key)
+        if b is None:
+            lib = _cabi.load()
+            i32 = dict(dtype=torch.int32, device=device)
+            csr_bytes = lib.lb200_csr_scratch_bytes(n, e_cap)
+            gns_bytes = lib.lb200_gns_scratch_bytes(n, e_cap)
+            b = {
+                "rowptr": torch.empty(n + 1, **i32), "perm": torch.empty(e_cap, **i32),
+                "snd": torch.empty(e_cap, **i32), "rcv": torch.empty(e_cap, **i32),
+                "csr": torch.empty(csr_bytes, dtype=torch.uint8, device=device),
+                "gns": torch.empty(gns_bytes, dtype=torch.uint8, device=device),
+            }
+            self._bufs = {key: b}
+        return b
+
+    def apply(self, params, state, sample):
+        """``GNS.__call__`` (``gns.py:159-171``): ``sample = (features, particle_type)``."""
+        lib = _cabi.load()
+        features, particle_type = sample
+        pk = self.packed_params(params)
+        packed = getattr(features, "packed", None)
+        if packed is not None:
+            node_feat, edge_feat, idx, n = packed["node_feat"], packed["edge_feat"], packed["idx"], packed["n"]
+        else:  # arbitrary FeatureDict: pack the columns in the order of GNS._transform (gns.py:139-145)
+            _cabi.require_cuda()
+            dev = torch.device("cuda")
+            f32 = dict(dtype=torch.float32, device=dev)
+            n = features["vel_hist"].shape[0]
+            node_feat = torch.cat([torch.as_tensor(features[k]).to(**f32).reshape(n, -1)
+                                   for k in ("vel_hist", "vel_mag", "bound", "force") if k in features], dim=1)
+            rel = torch.cat([torch.as_tensor(features[k]).to(**f32) for k in ("rel_disp", "rel_dist")], dim=1)
+            edge_feat = torch.zeros((rel.shape[0], 4), **f32)
+            edge_feat[:, :rel.shape[1]] = rel
+            idx = torch.stack([torch.as_tensor(features["receivers"]).to(dev, torch.int32),
+                               torch.as_tensor(features["senders"]).to(dev, torch.int32)])
+        node_feat, edge_feat, idx = node_feat.contiguous(), edge_feat.contiguous(), idx.contiguous()
+        dev = node_feat.device
+        ptype = torch.as_tensor(particle_type).to(dev, torch.int32).contiguous()
+        e_cap = idx.shape[1]
+        b = self._buffers(n, e_cap, dev)
+        cfg = gns_cfg(pk, n, e_cap, node_feat.shape[1], node_feat.shape[1])
+        out = torch.empty((n, self._output_size), dtype=torch.float32, device=dev)
+        st = _cabi.stream()
+        _cabi.check(lib.lb200_csr_build(_cabi.ptr(idx), n, e_cap, _cabi.ptr(b["rowptr"]), _cabi.ptr(b["perm"]),
+                                        _cabi.ptr(b["snd"]), _cabi.ptr(b["rcv"]), _cabi.ptr(b["csr"]),
+                                        b["csr"].numel(), st))
+        _cabi.check(lib.lb200_gns_forward(C.byref(cfg), _cabi.ptr(pk.blob), _cabi.ptr(node_feat),
+                                          _cabi.ptr(edge_feat), _cabi.ptr(ptype), _cabi.ptr(b["rowptr"]),
+                                          _cabi.ptr(b["perm"]), _cabi.ptr(b["snd"]), _cabi.ptr(b["rcv"]),
+                                          _cabi.ptr(out), _cabi.ptr(b["gns"]), b["gns"].numel(), st))
+        return {"acc": out}, state

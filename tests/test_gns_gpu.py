@@ -1,0 +1,93 @@
+"""Parity of the GNS forward (kernels ii-iv) with the oracle.
+
+Tolerance: BASELINE.json asks for accelerations within 1e-5 relative in float32.  It is
+checked as max|a - ref| <= 1e-5 * max|ref| against the float64 oracle, and the float32
+oracle's own distance to float64 is printed next to it for scale."""
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_pair, rel_err
+from lagrangebench_b200 import GNS
+from oracle import gns as ogns
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _forward_both(name, dtype, num_mp_steps=10, seed=0):
+    c, ours, orac = build_pair(name, dtype, seed=seed)
+    sample = (c["positions"], c["particle_type"])
+    f_gpu, _ = ours.allocate_eval(sample)
+    f_cpu, _ = orac.allocate_eval(sample)
+    d = c["metadata"]["dim"]
+    node_in = sum(f_cpu[k].reshape(f_cpu[k].shape[0], -1).shape[1] for k in ("vel_hist", "bound", "force") if k in f_cpu)
+    params = ogns.init_params(node_in, d + 1, d, num_mp_steps=num_mp_steps, seed=seed + 11, perturb=True)
+    model = GNS(d, 128, 2, num_mp_steps, 16)
+    out, _ = model.apply(params, {}, (f_gpu, torch.as_tensor(c["particle_type"]).cuda()))
+    # the oracle consumes the float32 features the network sees (jmp casts inputs to f32)
+    f32 = {k: (np.asarray(v).astype(np.float32) if np.asarray(v).dtype.kind == "f" else v) for k, v in f_cpu.items()}
+    ref64 = ogns.forward(params, f32, c["particle_type"], num_mp_steps, np.float64)["acc"]
+    ref32 = ogns.forward(params, f32, c["particle_type"], num_mp_steps, np.float32)["acc"]
+    return out["acc"].cpu().numpy(), ref64, ref32, (c, ours, f_gpu, params, model)
+
+
+@pytest.mark.parametrize("name,dtype", [("tgv2d", "float32"), ("rpf2d", "float64"), ("dam2d", "float32"),
+                                        ("ldc3d", "float64"), ("rpf3d_8k", "float32")])
+def test_forward_parity(name, dtype):
+    got, ref64, ref32, _ = _forward_both(name, dtype)
+    assert got.shape == ref64.shape and np.isfinite(got).all()
+    e_gpu, e_cpu32 = rel_err(got, ref64), rel_err(ref32, ref64)
+    print(f"{name}/{dtype}: rel err GPU vs f64 oracle {e_gpu:.2e}; f32 oracle vs f64 oracle {e_cpu32:.2e}")
+    assert e_gpu <= TOL
+    assert rel_err(got, ref32) <= TOL
+
+
+def test_forward_single_mp_step_and_type_embedding():
+    """One message-passing step; particle types other than FLUID exercise the embedding."""
+    got, ref64, _, _ = _forward_both("ldc3d", "float32", num_mp_steps=1)
+    assert rel_err(got, ref64) <= TOL
+
+
+def test_apply_accepts_plain_feature_dict_in_any_edge_order():
+    """model.apply on a plain dict (no packed buffers) with a shuffled, padded edge list:
+    the receiver-major view must make the result independent of list order."""
+    got, ref64, _, (c, ours, f_gpu, params, model) = _forward_both("tgv2d", "float32")
+    rng = np.random.default_rng(3)
+    e_cap = f_gpu["senders"].shape[0]
+    perm = torch.as_tensor(rng.permutation(e_cap)).cuda()
+    plain = {k: f_gpu[k].clone() for k in ("vel_hist", "rel_disp", "rel_dist", "senders", "receivers")}
+    for k in ("rel_disp", "rel_dist", "senders", "receivers"):
+        plain[k] = plain[k][perm].contiguous()
+    out, _ = model.apply(params, {}, (plain, c["particle_type"]))
+    shuffled = out["acc"].cpu().numpy()
+    assert rel_err(shuffled, ref64) <= TOL
+    # same receiver buckets in a different within-bucket order: float32 sums may differ in the last bits only
+    assert rel_err(shuffled, got) <= 1e-6
+
+
+def test_high_degree_receiver_straddles_many_tiles():
+    """A receiver with hundreds of in-edges spans several message tiles (carry path)."""
+    rng = np.random.default_rng(0)
+    n, d, deg = 500, 2, 700
+    snd = np.concatenate([rng.integers(0, n, deg), np.arange(n), rng.integers(0, n, 3000)]).astype(np.int32)
+    rcv = np.concatenate([np.full(deg, 7), np.arange(n), rng.integers(0, n, 3000)]).astype(np.int32)
+    pad = np.full(100, n, np.int32)
+    snd, rcv = np.concatenate([snd, pad]), np.concatenate([rcv, pad])
+    e = snd.shape[0]
+    feats = {"vel_hist": rng.standard_normal((n, 10)).astype(np.float32),
+             "rel_disp": rng.standard_normal((e, d)).astype(np.float32),
+             "rel_dist": rng.random((e, 1)).astype(np.float32), "senders": snd, "receivers": rcv}
+    ptype = rng.integers(0, 4, n).astype(np.int32)
+    params = ogns.init_params(10, d + 1, d, num_mp_steps=2, seed=4)
+    model = GNS(d, 128, 2, 2, 16)
+    out, _ = model.apply(params, {}, (feats, ptype))
+    ref = ogns.forward(params, feats, ptype, 2, np.float64)["acc"]
+    assert rel_err(out["acc"].cpu().numpy(), ref) <= TOL
+
+
+def test_forward_is_deterministic():
+    got1, _, _, (c, ours, f_gpu, params, model) = _forward_both("rpf2d", "float32")
+    out2, _ = model.apply(params, {}, (f_gpu, c["particle_type"]))
+    assert np.array_equal(got1, out2["acc"].cpu().numpy()), "aggregation must be bitwise reproducible"

@@ -1,0 +1,136 @@
+"""Parity of kernel (i) and the feature/integrate kernels with the oracle: bit-exact edge
+lists (order included), exact float32 features."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_pair
+from lagrangebench_b200 import case_builder
+from oracle import case as ocase
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+METADATA = {  # reference tests/case_test.py:14-23
+    "num_particles_max": 3, "periodic_boundary_conditions": [True, True, True],
+    "default_connectivity_radius": 0.3, "bounds": [[0.0, 1.0]] * 3,
+    "acc_mean": [0.0] * 3, "acc_std": [1.0] * 3, "vel_mean": [0.0] * 3, "vel_std": [1.0] * 3,
+}
+POSITION = np.array([  # tests/case_test.py:40-64
+    [[0.5, 0.5, 0.5]] * 5,
+    [[0.7, 0.5, 0.5], [0.9, 0.5, 0.5], [0.1, 0.5, 0.5], [0.3, 0.5, 0.5], [0.5, 0.5, 0.5]],
+    [[0.8, 0.6, 0.5], [0.8, 0.6, 0.5], [0.9, 0.6, 0.5], [0.2, 0.6, 0.5], [0.6, 0.6, 0.5]]])
+PTYPE = np.array([0, 0, 0])
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_reference_case_test_vectors(dtype):
+    """The reference's own test_allocate / test_preprocess_* / test_integrate, on the GPU path."""
+    case = case_builder(np.ones(3), METADATA, 3, cfg_neighbors={"multiplier": 1.25},
+                        cfg_model={"isotropic_norm": False, "magnitude_features": False}, noise_std=0.0,
+                        dtype=dtype)
+    key, features, target, nbrs = case.allocate(0, (POSITION, PTYPE))
+    assert nbrs.idx.cpu().tolist() == [[0, 1, 2, 2, 1, 3], [0, 1, 1, 2, 2, 3]]
+    assert not bool(nbrs.did_buffer_overflow)
+    assert np.isclose(target["vel"].cpu(), [[0, 0, 0], [0.2, 0, 0], [0.3, 0, 0]]).all()
+    assert np.isclose(target["acc"].cpu(), [[0, 0, 0], [0, 0, 0], [0.2, 0, 0]], atol=1e-7).all()
+    assert np.isclose(features["vel_hist"].cpu(),
+                      [[0, 0, 0, 0, 0, 0], [0.2, 0, 0, 0.2, 0, 0], [0, 0, 0, 0.1, 0, 0]], atol=1e-7).all()
+    disp = np.array([[0, 0, 0], [0, 0, 0], [-0.2, 0.1, 0], [0, 0, 0], [0.2, -0.1, 0], [0, 0, 0]]) / 0.3
+    assert np.isclose(features["rel_disp"].cpu(), disp, atol=1e-6).all()
+    assert np.isclose(features["rel_dist"].cpu(), ((disp**2).sum(-1, keepdims=True)) ** 0.5, atol=1e-6).all()
+    _, _, _, nbrs_new = case.preprocess(0, (POSITION, PTYPE), 0.0, nbrs, 0)
+    assert torch.equal(nbrs.idx, nbrs_new.idx)
+    _, _, target1, _ = case.preprocess(0, (POSITION, PTYPE), 0.0, nbrs, 1)
+    assert np.isclose(target1["acc"].cpu(), [[0, 0, 0], [0, 0, 0], [0.1, 0, 0]], atol=1e-7).all()
+    new_pos = case.integrate({"acc": np.array([[0.0, 0, 0], [0, 0, 0], [0.2, 0, 0]], np.float32)}, POSITION[:, :3])
+    assert np.isclose(new_pos.cpu(), POSITION[:, 3]).all()
+
+
+CASES = [("tgv2d", "float32"), ("tgv2d", "float64"), ("rpf2d", "float32"), ("dam2d", "float64"),
+         ("ldc3d", "float32"), ("ldc3d", "float64"), ("rpf3d_8k", "float32"), ("ldc3d_28k", "float32")]
+
+
+@pytest.mark.parametrize("name,dtype", CASES)
+def test_edge_list_bit_exact(name, dtype):
+    c, ours, orac = build_pair(name, dtype)
+    sample = (c["positions"], c["particle_type"])
+    f_gpu, n_gpu = ours.allocate_eval(sample)
+    f_cpu, n_cpu = orac.allocate_eval(sample)
+    assert n_gpu.max_occupancy == n_cpu.max_occupancy
+    assert n_gpu.cell_list_capacity == n_cpu.cell_list_capacity
+    assert n_gpu.n_edges == n_cpu.n_edges
+    assert np.array_equal(n_gpu.idx.cpu().numpy(), n_cpu.idx), "edge list differs (order is part of the contract)"
+    assert bool(n_gpu.did_buffer_overflow) == n_cpu.did_buffer_overflow is False
+    # float32 features are exact casts of the same arithmetic
+    for k in ("vel_hist", "bound", "force", "rel_disp", "rel_dist"):
+        assert (k in f_gpu) == (k in f_cpu)
+        if k in f_cpu:
+            ref = np.asarray(f_cpu[k]).astype(np.float32)
+            got = f_gpu[k].cpu().numpy()
+            assert got.shape == ref.shape
+            assert np.array_equal(got, ref), f"{k}: max diff {np.abs(got - ref).max()}"
+
+
+def test_update_and_overflow_flag():
+    """Fixed capacity + moved particles: same truncated list and the same overflow flag."""
+    c, ours, orac = build_pair("tgv2d", "float32", multiplier=1.0)
+    sample = (c["positions"], c["particle_type"])
+    _, n_gpu = ours.allocate_eval(sample)
+    _, n_cpu = orac.allocate_eval(sample)
+    rng = np.random.default_rng(5)
+    moved = c["positions"].copy()
+    moved[:, -1] = np.mod(moved[:, -1] * 0.93 + 0.01 * rng.standard_normal(moved[:, -1].shape).astype(np.float32), 1.0)
+    f_gpu, u_gpu = ours.preprocess_eval((moved, c["particle_type"]), n_gpu)
+    f_cpu, u_cpu = orac.preprocess_eval((moved, c["particle_type"]), n_cpu)
+    assert u_cpu.did_buffer_overflow, "test setup: the compressed cloud must overflow"
+    assert bool(u_gpu.did_buffer_overflow)
+    assert u_gpu.n_edges == u_cpu.n_edges
+    assert np.array_equal(u_gpu.idx.cpu().numpy(), u_cpu.idx)
+    # sticky like jax-md's error code: a later in-capacity update keeps the flag
+    _, again = ours.preprocess_eval(sample, u_gpu)
+    assert bool(again.did_buffer_overflow)
+
+
+def test_all_pairs_path_lj_fixture():
+    """Box smaller than three cutoffs: jax-md's all-pairs candidate path (LJ fixture)."""
+    with open(os.path.join(GOLDEN, "lj3d_metadata.json")) as f:
+        metadata = json.load(f)
+    pos = np.load(os.path.join(GOLDEN, "lj3d_valid_position.npy"))[:3].transpose(1, 0, 2)
+    box = np.array([5.0, 5.0, 5.0])
+    ours = case_builder(box, metadata, 3, noise_std=0.0, dtype="float64")
+    orac = ocase.case_builder(box, metadata, 3, noise_std=0.0, dtype=np.float64)
+    ptype = np.zeros(3, np.int32)
+    _, n_gpu = ours.allocate_eval((pos, ptype))
+    _, n_cpu = orac.allocate_eval((pos, ptype))
+    assert n_gpu.cell_list_capacity is None and n_cpu.cell_list_capacity is None
+    assert np.array_equal(n_gpu.idx.cpu().numpy(), n_cpu.idx)
+
+
+def test_magnitude_features_and_isotropic_norm():
+    c, _, _ = build_pair("rpf2d", "float64")
+    kw = dict(cfg_model={"magnitude_features": True, "isotropic_norm": True}, noise_std=3e-4)
+    from helpers import oracle_force
+    ours = case_builder(c["box"], c["metadata"], 6, external_force_fn=c["force"], dtype="float64", **kw)
+    orac = ocase.case_builder(c["box"], c["metadata"], 6, external_force_fn=oracle_force(c["force"]),
+                              dtype=np.float64, **kw)
+    sample = (c["positions"], c["particle_type"])
+    f_gpu, _ = ours.allocate_eval(sample)
+    f_cpu, _ = orac.allocate_eval(sample)
+    assert np.array_equal(f_gpu["vel_mag"].cpu().numpy(), f_cpu["vel_mag"].astype(np.float32))
+    assert np.array_equal(f_gpu["vel_hist"].cpu().numpy(), f_cpu["vel_hist"].astype(np.float32))
+
+
+def test_integrate_matches_oracle():
+    c, ours, orac = build_pair("rpf2d", "float64")
+    rng = np.random.default_rng(1)
+    acc = rng.standard_normal((c["positions"].shape[0], 2)).astype(np.float32)
+    got = ours.integrate({"acc": acc}, c["positions"]).cpu().numpy()
+    ref = orac.integrate({"acc": acc}, c["positions"])
+    assert np.array_equal(got, ref)
+    got_v = ours.integrate({"vel": acc}, c["positions"]).cpu().numpy()
+    assert np.array_equal(got_v, orac.integrate({"vel": acc}, c["positions"]))

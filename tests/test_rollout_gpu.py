@@ -1,0 +1,136 @@
+"""Rollout loop parity: the reference's Lennard-Jones identity test on the GPU path, the
+device-resident engine against the oracle loop, and the overflow -> re-allocate -> retry
+contract (evaluate/rollout.py:135-151)."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_pair, rel_err
+from lagrangebench_b200 import GNS, MetricsComputer, RolloutEngine, case_builder, eval_rollout, infer, synthetic
+from lagrangebench_b200.evaluate import SimpleLoader, _eval_batched_rollout
+from oracle import gns as ogns
+from oracle import rollout as orollout
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("n_extrap_steps", [0, 5, 10])
+def test_lj_rollout_identity(n_extrap_steps):
+    """reference tests/rollout_test.py:74-195 through case.preprocess_eval / integrate kernels."""
+    with open(os.path.join(GOLDEN, "lj3d_metadata.json")) as f:
+        metadata = json.load(f)
+    pos_tnd = np.load(os.path.join(GOLDEN, "lj3d_valid_position.npy"))
+    isl, n_rollout = 3, 100
+    positions = pos_tnd[: isl + n_rollout].transpose(1, 0, 2)  # (N, T, d)
+    ptype = np.zeros(3, np.int32)
+    box = np.array([5.0, 5.0, 5.0])
+    case = case_builder(box, metadata, isl, noise_std=0.0, dtype="float64")
+    pos64 = torch.as_tensor(positions, dtype=torch.float64)
+    vels = case.displacement(pos64[:, 1:], pos64[:, :-1])
+    accs = vels[:, 1:] - vels[:, :-1]
+    st = case.normalization_stats["acceleration"]
+    accs = ((accs - torch.as_tensor(st["mean"])) / torch.as_tensor(st["std"])).to(torch.float32)
+
+    def model_apply(params, state, sample):  # CheatingModel (rollout_test.py:92-106)
+        i = state["counter"]
+        return {"acc": accs[:, min(i, accs.shape[1] - 1)]}, {"counter": i + 1}
+
+    _, nbrs = case.allocate_eval((positions[:, :isl], ptype))
+    mc = MetricsComputer(["mse"], case.displacement, metadata, isl)
+    pred, metrics, _ = _eval_batched_rollout(model_apply, case, None, {"counter": isl - 2},
+                                             (positions[None], ptype[None]), nbrs, mc, n_rollout, isl, n_extrap_steps)
+    assert pred.shape[1] == n_rollout + n_extrap_steps
+    assert np.isclose(float(metrics[0]["mse"].mean()), 0.0, atol=1e-6)
+    full = np.concatenate([positions.transpose(1, 0, 2)[:isl], pred[0].cpu().numpy()])
+    assert np.isclose(full[100, 0], positions.transpose(1, 0, 2)[100, 0], atol=1e-6).all()
+
+
+def _setup(name, dtype, n_steps, mp=2, seed=0):
+    c, ours, orac = build_pair(name, dtype, n_future=n_steps, seed=seed)
+    d = c["metadata"]["dim"]
+    f_cpu, nb_cpu = orac.allocate_eval((c["positions"][:, :6], c["particle_type"]))
+    node_in = sum(f_cpu[k].reshape(f_cpu[k].shape[0], -1).shape[1] for k in ("vel_hist", "bound", "force") if k in f_cpu)
+    params = ogns.init_params(node_in, d + 1, d, num_mp_steps=mp, seed=seed + 2)
+    return c, ours, orac, params, GNS(d, 128, 2, mp, 16), nb_cpu
+
+
+@pytest.mark.parametrize("name,dtype", [("tgv2d", "float32"), ("ldc3d", "float64")])
+def test_engine_rollout_matches_oracle_loop(name, dtype):
+    n_steps = 4
+    c, ours, orac, params, model, nb_cpu = _setup(name, dtype, n_steps)
+    npd = np.float32 if dtype == "float32" else np.float64
+
+    def oracle_apply(p, state, sample):
+        feats, ptype = sample
+        f32 = {k: (np.asarray(v).astype(np.float32) if np.asarray(v).dtype.kind == "f" else v) for k, v in feats.items()}
+        return ogns.forward(p, f32, ptype, 2, np.float32), state
+
+    ref, _ = orollout.eval_batched_rollout(oracle_apply, orac, params, {}, (c["positions"][None].astype(npd),
+                                           c["particle_type"][None]), nb_cpu, n_steps, 6)
+    engine = RolloutEngine(ours, model, params, steps_per_sync=3)
+    window = torch.as_tensor(c["positions"][:, :6]).cuda().contiguous()
+    targets = torch.as_tensor(c["positions"][:, 6:6 + n_steps]).permute(1, 0, 2)
+    preds, _ = engine.run(window, c["particle_type"], targets, n_steps)
+    got = preds.cpu().numpy()
+    assert engine.n_launch_calls == 2  # 3 + 1 steps: one host sync per chunk, not per step
+    dx = c["metadata"]["dx"]
+    assert np.abs(got - ref[0]).max() <= 1e-6 * dx, "positions drift from the oracle loop"
+    kin = np.isin(c["particle_type"], [1, 2, -1])
+    if kin.any():  # kinematic particles follow the ground truth exactly (rollout.py:64-69)
+        assert np.array_equal(got[:, kin], c["positions"][kin, 6:6 + n_steps].transpose(1, 0, 2))
+    assert np.array_equal(window[:, -1].cpu().numpy(), got[-1])
+
+
+def test_engine_equals_per_step_loop_bitwise():
+    """Device-resident loop and the generic per-step loop launch the same kernels."""
+    n_steps = 3
+    c, ours, _, params, model, _ = _setup("rpf2d", "float32", n_steps)
+    batch = (c["positions"][None], c["particle_type"][None])
+    _, nbrs = ours.allocate_eval((c["positions"][:, :6], c["particle_type"]))
+    slow, _, _ = _eval_batched_rollout(model.apply, ours, params, {}, batch, nbrs, None, n_steps, 6)
+    engine = RolloutEngine(ours, model, params)
+    fast, _, _ = _eval_batched_rollout(model.apply, ours, params, {}, batch, None, None, n_steps, 6, engine=engine)
+    assert torch.equal(slow, fast)
+
+
+def test_overflow_reallocates_and_retries_same_step():
+    n_steps = 3
+    c, ours, _, params, model, _ = _setup("tgv2d", "float32", n_steps)
+    window0 = torch.as_tensor(c["positions"][:, :6]).cuda().contiguous()
+    good_engine = RolloutEngine(ours, model, params)
+    ref, _ = good_engine.run(window0.clone(), c["particle_type"], None, n_steps)
+    assert good_engine.n_reallocations == 0
+    # a neighbor list whose capacity is far too small for the cloud: first step overflows
+    tiny = ours._lb200["neighbor_fn"].allocate(window0[:, -1].contiguous())
+    tiny.idx = tiny.idx[:, :1000].contiguous()
+    tiny.max_occupancy = 1000
+    assert tiny.max_occupancy < good_engine._cfg.e_cap
+    engine = RolloutEngine(ours, model, params)
+    got, nbrs = engine.run(window0.clone(), c["particle_type"], None, n_steps, neighbors=tiny)
+    assert engine.n_reallocations >= 1
+    assert torch.equal(got, ref), "the retried step must reproduce the un-overflowed rollout"
+    assert nbrs.max_occupancy >= good_engine._cfg.e_cap
+
+
+def test_infer_and_eval_rollout_api(tmp_path):
+    ds = synthetic.SyntheticDataset("rpf2d", 6, n_rollout_steps=5, n_trajs=3, seed=2)
+    case = case_builder(ds.cases[0]["box"], ds.metadata, 6, cfg_neighbors={"multiplier": 1.25},
+                        external_force_fn=ds.external_force_fn, dtype="float32")
+    model = GNS(2, 128, 2, 2, 16)
+    feats, _ = case.allocate_eval(ds[0])
+    params, state = model.init(0, (feats, ds[0][1]))
+    metrics = infer(model, case, ds, params=params, state=state, cfg_eval_infer={"batch_size": 2, "metrics": ["mse"],
+                    "out_type": "pkl", "n_trajs": -1}, rollout_dir=str(tmp_path), n_rollout_steps=5, seed=0)
+    assert sorted(metrics) == ["rollout_0", "rollout_1", "rollout_2"]
+    assert metrics["rollout_0"]["mse"].shape == (5,) and "mse1" in metrics["rollout_0"]
+    import pickle
+    with open(tmp_path / "rollout_1.pkl", "rb") as f:
+        payload = pickle.load(f)
+    assert payload["predicted_rollout"].shape == (11, 3200, 2)
+    assert payload["ground_truth_rollout"].shape == (11, 3200, 2)
+    assert np.array_equal(payload["predicted_rollout"][:6], payload["ground_truth_rollout"][:6])
