@@ -183,7 +183,9 @@ def neighbor_list(displacement_fn, box, r_cutoff, capacity_multiplier=1.25, dtyp
         overflow = bool(n_edges > e_cap) or cell_overflow
         if nbrs is not None:
             overflow = overflow or bool(nbrs.did_buffer_overflow)  # jax-md error codes are sticky
-        return NeighborList(idx, position, overflow, cap, e_cap, n_edges, update)
+        out = NeighborList(idx, position, overflow, cap, e_cap, n_edges, update)
+        out.cell_overflow = cell_overflow  # oracle extra: list contents are unspecified when set
+        return out
 
     def allocate(position, **kwargs):
         return _build(position, None)

@@ -64,7 +64,7 @@ def test_apply_accepts_plain_feature_dict_in_any_edge_order():
     shuffled = out["acc"].cpu().numpy()
     assert rel_err(shuffled, ref64) <= TOL
     # same receiver buckets in a different within-bucket order: float32 sums may differ in the last bits only
-    assert rel_err(shuffled, got) <= 1e-6
+    assert rel_err(shuffled, got) <= 5e-6
 
 
 def test_high_degree_receiver_straddles_many_tiles():

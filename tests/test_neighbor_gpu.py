@@ -77,23 +77,30 @@ def test_edge_list_bit_exact(name, dtype):
 
 
 def test_update_and_overflow_flag():
-    """Fixed capacity + moved particles: same truncated list and the same overflow flag."""
-    c, ours, orac = build_pair("tgv2d", "float32", multiplier=1.0)
-    sample = (c["positions"], c["particle_type"])
-    _, n_gpu = ours.allocate_eval(sample)
-    _, n_cpu = orac.allocate_eval(sample)
-    rng = np.random.default_rng(5)
-    moved = c["positions"].copy()
-    moved[:, -1] = np.mod(moved[:, -1] * 0.93 + 0.01 * rng.standard_normal(moved[:, -1].shape).astype(np.float32), 1.0)
-    f_gpu, u_gpu = ours.preprocess_eval((moved, c["particle_type"]), n_gpu)
-    f_cpu, u_cpu = orac.preprocess_eval((moved, c["particle_type"]), n_cpu)
-    assert u_cpu.did_buffer_overflow, "test setup: the compressed cloud must overflow"
+    """Fixed, too-small edge capacity + moved particles: same truncated list, same flag.
+
+    List contents are only specified while no CELL overflows (jax-md then drops particles
+    from its buffer through colliding scatter writes), so the edge capacity alone is shrunk
+    (to 90 % of the true count) on both sides before the update."""
+    c, ours, orac = build_pair("tgv2d", "float32", n_future=1)
+    pt = c["particle_type"]
+    _, n_gpu = ours.allocate_eval((c["positions"][:, :6], pt))
+    _, n_cpu = orac.allocate_eval((c["positions"][:, :6], pt))
+    small = int(0.9 * n_cpu.n_edges)
+    n_cpu.max_occupancy, n_cpu.idx = small, n_cpu.idx[:, :small].copy()
+    n_gpu.max_occupancy, n_gpu.idx = small, n_gpu.idx[:, :small].contiguous()
+    sample = (c["positions"][:, 1:7], pt)
+    _, u_gpu = ours.preprocess_eval(sample, n_gpu)
+    _, u_cpu = orac.preprocess_eval(sample, n_cpu)
+    assert u_cpu.did_buffer_overflow and not u_cpu.cell_overflow, "test setup"
     assert bool(u_gpu.did_buffer_overflow)
-    assert u_gpu.n_edges == u_cpu.n_edges
+    assert u_gpu.n_edges == u_cpu.n_edges > small
     assert np.array_equal(u_gpu.idx.cpu().numpy(), u_cpu.idx)
     # sticky like jax-md's error code: a later in-capacity update keeps the flag
+    big = ours._lb200["neighbor_fn"].allocate(torch.as_tensor(c["positions"][:, 5]).cuda())
+    u_gpu.idx, u_gpu.max_occupancy = big.idx, big.max_occupancy
     _, again = ours.preprocess_eval(sample, u_gpu)
-    assert bool(again.did_buffer_overflow)
+    assert bool(again.did_buffer_overflow) and again.n_edges <= again.max_occupancy
 
 
 def test_all_pairs_path_lj_fixture():
