@@ -142,6 +142,11 @@ int lb200_features(const lb200_feature_cfg* c, const void* window_dev, const flo
  */
 typedef struct {
   int64_t w0, b0, w1, b1, ln_scale, ln_offset; /* ln_* < 0: no LayerNorm */
+  /* tensor-core operands of a processor edge MLP (< 0: absent): tc_w = four 128x128 fp16
+   * matrices W1e^T hi|lo, W2c^T hi|lo in the UMMA no-swizzle K-major layout (element (m,k) at
+   * half index (k/8)*1024 + m*8 + k%8), split as x = hi + lo * 2^-11; W2c = W2 with the
+   * LayerNorm mean folded in (each row minus its mean).  tc_vec = b2c | ln_scale | ln_offset. */
+  int64_t tc_w, tc_vec;
 } lb200_mlp_off;
 
 typedef struct {
@@ -155,6 +160,8 @@ typedef struct {
   lb200_mlp_off enc_node, enc_edge, dec;
   const lb200_mlp_off* proc_edge; /* host array [num_mp_steps] */
   const lb200_mlp_off* proc_node; /* host array [num_mp_steps] */
+  int32_t edge_impl;        /* 0: tcgen05 tensor-core message kernel (product path);
+                               1: fp32 CUDA-core kernel (kept as the numerical cross-check) */
 } lb200_gns_cfg;
 
 /* device scratch the forward needs, in bytes (node latents, projections, edge latents ...) */

@@ -38,14 +38,15 @@ class FeatureCfg(C.Structure):
 
 class MlpOff(C.Structure):
     _fields_ = [("w0", C.c_int64), ("b0", C.c_int64), ("w1", C.c_int64), ("b1", C.c_int64),
-                ("ln_scale", C.c_int64), ("ln_offset", C.c_int64)]
+                ("ln_scale", C.c_int64), ("ln_offset", C.c_int64), ("tc_w", C.c_int64), ("tc_vec", C.c_int64)]
 
 
 class GnsCfg(C.Structure):
     _fields_ = [("n", C.c_int32), ("dim", C.c_int32), ("num_mp_steps", C.c_int32), ("node_in", C.c_int32),
                 ("node_stride", C.c_int32), ("embed_size", C.c_int32), ("num_particle_types", C.c_int32),
                 ("e_cap", C.c_int32), ("embedding", C.c_int64), ("enc_node", MlpOff), ("enc_edge", MlpOff),
-                ("dec", MlpOff), ("proc_edge", C.POINTER(MlpOff)), ("proc_node", C.POINTER(MlpOff))]
+                ("dec", MlpOff), ("proc_edge", C.POINTER(MlpOff)), ("proc_node", C.POINTER(MlpOff)),
+                ("edge_impl", C.c_int32)]
 
 
 class IntegrateCfg(C.Structure):

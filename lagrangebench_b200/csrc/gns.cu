@@ -19,6 +19,7 @@
 //   carry_first/last [tiles][128]  partial sums of buckets that straddle a tile boundary,
 //                      combined (in tile order) by the node kernel.
 #include "common.cuh"
+#include "gns_tc.cuh"
 
 namespace lb {
 
@@ -582,19 +583,37 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   { edge_encoder_kernel<<<nt, kThreads, kSmemEdgeEnc, s>>>(ee); LB_LAUNCHED(1); }
 
   for (int m = 0; m < c->num_mp_steps; ++m) {
-    EdgeMpArgs em;
-    em.n = n;
-    em.rowptr = rowptr_dev;
-    em.snd = snd_dev;
-    em.rcv = rcv_dev;
-    em.P = P;
-    em.mlp = mlp_ptrs(w, c->proc_edge[m]);
-    em.e = e;
-    em.agg = agg;
-    em.carry_first = cf;
-    em.carry_last = cl;
+    const lb200_mlp_off& eo = c->proc_edge[m];
     prof_begin(0, s);
-    { edge_mp_kernel<<<nt, kThreads, kSmemEdgeMp, s>>>(em); LB_LAUNCHED(1); }
+    if (c->edge_impl == 0 && eo.tc_w >= 0 && eo.tc_vec >= 0) {
+      EdgeTcArgs et;
+      et.n = n;
+      et.rowptr = rowptr_dev;
+      et.snd = snd_dev;
+      et.rcv = rcv_dev;
+      et.P = P;
+      et.w_tc = w + eo.tc_w;
+      et.vec_tc = w + eo.tc_vec;
+      et.e = e;
+      et.agg = agg;
+      et.carry_first = cf;
+      et.carry_last = cl;
+      rc = launch_edge_mp_tc(et, e_cap, s);
+      if (rc) return rc;
+    } else {
+      EdgeMpArgs em;
+      em.n = n;
+      em.rowptr = rowptr_dev;
+      em.snd = snd_dev;
+      em.rcv = rcv_dev;
+      em.P = P;
+      em.mlp = mlp_ptrs(w, eo);
+      em.e = e;
+      em.agg = agg;
+      em.carry_first = cf;
+      em.carry_last = cl;
+      { edge_mp_kernel<<<nt, kThreads, kSmemEdgeMp, s>>>(em); LB_LAUNCHED(1); }
+    }
     prof_end(0, s);
 
     NodeMpArgs nm;

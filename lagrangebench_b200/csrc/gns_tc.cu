@@ -1,0 +1,413 @@
+// Message passing, edge side, on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces update_edge_fn + segment_sum of the jraph.GraphNetwork block
+// (lagrangebench/models/gns.py:86-101,117-122) for one tile of 128 receiver-sorted edges:
+//
+//   hidden = relu(e @ W1e + P_s[snd] + P_r[rcv])        (P = per-node projections, gns.cu)
+//   yc     = hidden @ W2c + b2c                          (W2c/b2c: LayerNorm mean folded in)
+//   e'     = scale * yc * rsqrt(mean(yc^2) + 1e-5) + offset
+//   e     <- e' + e ;  agg[rcv] = sum over the receiver's edges of e'  (ascending slot order)
+//
+// fp32-level accuracy on fp16 tensor cores: every operand x is split as
+// x = hi + lo * 2^-11 with hi = fp16(x), lo = fp16((x - hi) * 2^11) (22+ significant bits);
+// D = A_hi B_hi + 2^-11 (A_hi B_lo + A_lo B_hi) uses three kind::f16 MMA passes with fp32
+// accumulation into two TMEM accumulators (the dropped lo*lo term is 2^-22 relative).
+//
+// Layout: the GEMMs are issued TRANSPOSED, D^T[feature][edge] = W^T[feature][k] * X^T[k][edge]:
+// weights are the M-side operand (resident in shared memory for the whole persistent CTA),
+// the edge tile is the N-side operand.  TMEM lane == output feature == epilogue thread, TMEM
+// column == edge.  Consequences: every global access of the epilogue (gather of P rows by
+// sender/receiver index, residual read, e store, aggregate store) is one coalesced 128-byte
+// row segment per warp instruction; the per-receiver segmented sum runs in registers over the
+// thread's columns; only LayerNorm's variance needs a cross-thread (butterfly) reduction.
+//
+// Operand tiles in shared memory use the no-swizzle K-major core-matrix layout: element
+// (row, k) at (k / 8) * LBO + row * 16 + (k % 8) * 2 bytes, 8-row groups 128 B apart (SBO).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "gns_tc.cuh"
+
+namespace lb {
+
+constexpr int kTcThreads = 256;
+constexpr int kTcTile = 128;           // edges per CTA tile = 2 carry sub-tiles of kEdgeTile
+constexpr uint32_t kLboA = 2048;       // weights: 128 rows * 16 B per 8-wide K slab
+constexpr uint32_t kLboB = 2064;       // edge tile: padded slab pitch -> conflict-free stores
+constexpr uint32_t kSbo = 128;
+constexpr uint32_t kWBytes = 16 * kLboA;  // one 128x128 fp16 weight operand (32 KB)
+constexpr uint32_t kBBytes = 16 * kLboB;  // one 128x128 fp16 edge operand (33 KB)
+// instruction descriptor: D=F32 (bit 4), A=B=F16 (0), both K-major, N=128 (>>3 at bit 17), M=128 (>>4 at bit 24)
+constexpr uint32_t kIdesc = (1u << 4) | (16u << 17) | (8u << 24);
+constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
+static_assert(kTcTile == 2 * kEdgeTile, "carry protocol: two 64-edge sub-tiles per CTA tile");
+
+// shared memory map (bytes)
+constexpr uint32_t kOffW = 0;                         // W1e_hi, W1e_lo, W2c_hi, W2c_lo
+constexpr uint32_t kOffB = kOffW + 4 * kWBytes;       // B_hi, B_lo
+constexpr uint32_t kOffVec = kOffB + 2 * kBBytes;     // b2c[128], scale[128], offset[128]
+constexpr uint32_t kOffIdx = kOffVec + 3 * 512;       // sidx[128], ridx_ext[130]
+constexpr uint32_t kOffRed = kOffIdx + (128 + 132) * 4;  // red[2 buf][2 halves][4][32]
+constexpr uint32_t kOffInv = kOffRed + 2 * 2 * 4 * 32 * 4;  // inv[8 warps][32]: 1/sqrt(var + eps) per edge
+constexpr uint32_t kOffEnd = kOffInv + 8 * 32 * 4;          // endmask[4]: bit = last edge of its receiver bucket
+constexpr uint32_t kOffBar = kOffEnd + 16;                  // mbarriers (2 x 8 B) + tmem base (4 B)
+constexpr uint32_t kSmemTc = kOffBar + 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);           // start address  [0,14)
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;        // leading byte offset (K-adjacent core matrices)
+  d |= (uint64_t)((kSbo >> 4) & 0x3FFFu) << 32;       // stride byte offset (8-row groups)
+  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+  return d;                                           // layout_type 0 = no swizzle
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// two accumulators x 32 columns of this warp's 32 TMEM lanes -> registers (thread == lane)
+__device__ __forceinline__ void tmem_ld_pair(uint32_t ta, uint32_t tb, float (&a)[32], float (&b)[32]) {
+  uint32_t x[32], y[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%64];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%65];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(x[8]),
+        "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15]), "=r"(x[16]),
+        "=r"(x[17]), "=r"(x[18]), "=r"(x[19]), "=r"(x[20]), "=r"(x[21]), "=r"(x[22]), "=r"(x[23]), "=r"(x[24]),
+        "=r"(x[25]), "=r"(x[26]), "=r"(x[27]), "=r"(x[28]), "=r"(x[29]), "=r"(x[30]), "=r"(x[31]), "=r"(y[0]),
+        "=r"(y[1]), "=r"(y[2]), "=r"(y[3]), "=r"(y[4]), "=r"(y[5]), "=r"(y[6]), "=r"(y[7]), "=r"(y[8]), "=r"(y[9]),
+        "=r"(y[10]), "=r"(y[11]), "=r"(y[12]), "=r"(y[13]), "=r"(y[14]), "=r"(y[15]), "=r"(y[16]), "=r"(y[17]),
+        "=r"(y[18]), "=r"(y[19]), "=r"(y[20]), "=r"(y[21]), "=r"(y[22]), "=r"(y[23]), "=r"(y[24]), "=r"(y[25]),
+        "=r"(y[26]), "=r"(y[27]), "=r"(y[28]), "=r"(y[29]), "=r"(y[30]), "=r"(y[31])
+      : "r"(ta), "r"(tb)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    a[i] = __uint_as_float(x[i]);
+    b[i] = __uint_as_float(y[i]);
+  }
+}
+
+__device__ __forceinline__ void split_f16(float x, unsigned short& hi, unsigned short& lo) {
+  const __half h = __float2half_rn(x);
+  const __half l = __float2half_rn((x - __half2float(h)) * kLoScale);
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(l);
+}
+
+// 3-pass split-precision GEMM: acc_hh = A_hi B_hi ; acc_x = A_hi B_lo + A_lo B_hi   (K = 128)
+__device__ __forceinline__ void issue_gemm(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                           uint32_t acc_hh, uint32_t acc_x) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    umma_f16(acc_hh, umma_desc(a_hi + j * 2 * kLboA, kLboA), umma_desc(b_hi + j * 2 * kLboB, kLboB), j > 0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    umma_f16(acc_x, umma_desc(a_hi + j * 2 * kLboA, kLboA), umma_desc(b_lo + j * 2 * kLboB, kLboB), j > 0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    umma_f16(acc_x, umma_desc(a_lo + j * 2 * kLboA, kLboA), umma_desc(b_hi + j * 2 * kLboB, kLboB), 1);
+}
+
+// lane l ends with the sum over the warp's 32 lanes of v[l]   (31 shuffles, fixed order)
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  float* vec = reinterpret_cast<float*>(smem + kOffVec);
+  int* sidx = reinterpret_cast<int*>(smem + kOffIdx);
+  int* ridx = sidx + 128;  // ridx[0] = receiver before the tile, ridx[1 + i] = row i, ridx[1 + rows] = after
+  float* red = reinterpret_cast<float*>(smem + kOffRed);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 16);
+  const uint32_t bar_w = sbase + kOffBar, bar_mma = sbase + kOffBar + 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter of this warp; which 64 edge columns it owns
+  const int f = q * 32 + lane;               // output feature == TMEM lane of this thread
+
+  const int E = a.rowptr[a.n];
+  const int n_tiles = (E + kTcTile - 1) / kTcTile;
+  if ((int)blockIdx.x >= n_tiles) return;
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t acc_hh = tmem, acc_x = tmem + 128;
+
+  // resident weights: 4 fp16 operands (128 KB) + centred bias, LayerNorm scale / offset
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, 4 * kWBytes + 3 * 512);
+    bulk_g2s(sbase + kOffW, a.w_tc, 4 * kWBytes, bar_w);
+    bulk_g2s(sbase + kOffVec, a.vec_tc, 3 * 512, bar_w);
+  }
+  mbar_wait(bar_w, 0);
+  const float b2c = vec[f], ln_scale = vec[128 + f], ln_offset = vec[256 + f];
+
+  const uint32_t w1_hi = sbase + kOffW, w1_lo = w1_hi + kWBytes, w2_hi = w1_lo + kWBytes, w2_lo = w2_hi + kWBytes;
+  const uint32_t b_hi = sbase + kOffB, b_lo = b_hi + kBBytes;
+  unsigned char* b_hi_p = smem + kOffB;
+  unsigned char* b_lo_p = b_hi_p + kBBytes;
+  const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+  // this thread's element of operand row `e` (edge), k = f:
+  const uint32_t elem_off = (uint32_t)(f >> 3) * kLboB + (uint32_t)(f & 7) * 2;
+  uint32_t phase = 0;
+
+  float* invs = reinterpret_cast<float*>(smem + kOffInv) + warp * 32;
+  uint32_t* endm = reinterpret_cast<uint32_t*>(smem + kOffEnd);
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t slot0 = (int64_t)tile * kTcTile;
+    const int rows = min(kTcTile, E - (int)slot0);
+    __syncthreads();  // previous tile's epilogue is done with sidx / ridx / B operands
+    if (tid < kTcTile) {
+      const bool ok = tid < rows;
+      const int r_here = ok ? a.rcv[slot0 + tid] : -1;
+      const int r_next = (slot0 + tid + 1 < E) ? a.rcv[slot0 + tid + 1] : -3;
+      sidx[tid] = ok ? a.snd[slot0 + tid] : 0;
+      ridx[1 + tid] = ok ? r_here : (tid == rows ? -3 : -1);  // -3: "no edge after the tile"
+      // last edge of its receiver bucket inside this 64-edge carry sub-tile
+      const bool end = ok && (r_next != r_here || (tid & 63) == 63 || tid == rows - 1);
+      const uint32_t m = __ballot_sync(0xffffffffu, end);
+      if (lane == 0) endm[warp] = m;
+      if (tid == kTcTile - 1 && ok) ridx[1 + kTcTile] = r_next;  // receiver just after a full tile
+    } else if (tid == kTcTile) {
+      ridx[0] = slot0 > 0 ? a.rcv[slot0 - 1] : -2;
+    }
+    // ---- phase A: edge latents -> fp16 hi/lo N-side operand (coalesced 512 B rows)
+    {
+      float4 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = warp * 16 + i;
+        v[i] = r < rows ? reinterpret_cast<const float4*>(a.e + (slot0 + r) * kLatent)[lane]
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = warp * 16 + i;
+        const __half2 h01 = __floats2half2_rn(v[i].x, v[i].y), h23 = __floats2half2_rn(v[i].z, v[i].w);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn((v[i].x - f01.x) * kLoScale, (v[i].y - f01.y) * kLoScale);
+        const __half2 l23 = __floats2half2_rn((v[i].z - f23.x) * kLoScale, (v[i].w - f23.y) * kLoScale);
+        const uint32_t off = (uint32_t)(lane >> 1) * kLboB + (uint32_t)r * 16 + (uint32_t)(lane & 1) * 8;
+        *reinterpret_cast<uint2*>(b_hi_p + off) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        *reinterpret_cast<uint2*>(b_lo_p + off) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_gemm(w1_hi, w1_lo, b_hi, b_lo, acc_hh, acc_x);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, phase);
+    phase ^= 1;
+    tc_fence_after();
+
+    // ---- epilogue 1: hidden = relu(acc + P_s[snd] + P_r[rcv]) -> fp16 hi/lo operand for layer 2
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int col0 = half * 64 + cc * 32;
+      float hh[32], xx[32];
+      tmem_ld_pair(acc_hh + t_lane + col0, acc_x + t_lane + col0, hh, xx);
+#pragma unroll
+      for (int j0 = 0; j0 < 32; j0 += 16) {
+        float ps[16], pr[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const int4 s4 = *reinterpret_cast<const int4*>(sidx + col0 + j0 + j4);
+          int r4[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) r4[t] = max(ridx[1 + col0 + j0 + j4 + t], 0);
+          ps[j4 + 0] = __ldg(a.P + (int64_t)s4.x * (2 * kLatent) + f);
+          ps[j4 + 1] = __ldg(a.P + (int64_t)s4.y * (2 * kLatent) + f);
+          ps[j4 + 2] = __ldg(a.P + (int64_t)s4.z * (2 * kLatent) + f);
+          ps[j4 + 3] = __ldg(a.P + (int64_t)s4.w * (2 * kLatent) + f);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) pr[j4 + t] = __ldg(a.P + (int64_t)r4[t] * (2 * kLatent) + kLatent + f);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int e = col0 + j0 + j;
+          const float hval = fmaxf(fmaf(xx[j0 + j], kLoInv, hh[j0 + j]) + ps[j] + pr[j], 0.f);
+          const __half hi = __float2half_rn(hval);
+          const __half lo = __float2half_rn((hval - __half2float(hi)) * kLoScale);
+          *reinterpret_cast<__half*>(b_hi_p + elem_off + (uint32_t)e * 16) = hi;
+          *reinterpret_cast<__half*>(b_lo_p + elem_off + (uint32_t)e * 16) = lo;
+        }
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_gemm(w2_hi, w2_lo, b_hi, b_lo, acc_hh, acc_x);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, phase);
+    phase ^= 1;
+    tc_fence_after();
+
+    // ---- epilogue 2: LayerNorm (mean folded into the weights), residual, store, segmented sum
+    const int sub = (int)(slot0 / kEdgeTile) + half;          // 64-edge carry sub-tile of this warp
+    const int rows_h = min(max(rows - half * 64, 0), 64);     // valid edges in it
+    const bool first_cont = rows_h > 0 && ridx[half * 64] == ridx[1 + half * 64];
+    const bool last_cont = rows_h > 0 && ridx[1 + half * 64 + rows_h] == ridx[half * 64 + rows_h];
+    float* const cfirst = a.carry_first + (int64_t)sub * kLatent + f;
+    float* const clast = a.carry_last + (int64_t)sub * kLatent + f;
+    float seg_sum = 0.f;
+    bool seg_first = true;  // still inside the first bucket of the sub-tile
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int col0 = half * 64 + cc * 32;
+      const int valid = min(max(rows - col0, 0), 32);  // edges of this chunk that exist
+      float eold[32];
+      float* const erow = a.e + (slot0 + col0) * kLatent + f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) eold[j] = j < valid ? erow[(int64_t)j * kLatent] : 0.f;
+      float yc[32], sq[32];
+      tmem_ld_pair(acc_hh + t_lane + col0, acc_x + t_lane + col0, yc, sq);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        yc[j] = fmaf(sq[j], kLoInv, yc[j]) + b2c;
+        sq[j] = yc[j] * yc[j];
+      }
+      const float part = warp_transpose_reduce(sq);  // lane l: this warp's 32 features, edge col0 + l
+      float* rbuf = red + (cc & 1) * 256 + half * 128;
+      rbuf[q * 32 + lane] = part;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // the 4 warps sharing these columns
+      {
+        const float var = (rbuf[lane] + rbuf[32 + lane] + rbuf[64 + lane] + rbuf[96 + lane]) * (1.0f / kLatent);
+        invs[lane] = 1.0f / sqrtf(var + 1e-5f);  // once per edge per warp (same value in the 4 warps)
+      }
+      __syncwarp();
+      const uint32_t emask = endm[col0 >> 5];
+#pragma unroll
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        const float4 inv4 = *reinterpret_cast<const float4*>(invs + j4);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int j = j4 + t;
+          const float inv = t == 0 ? inv4.x : (t == 1 ? inv4.y : (t == 2 ? inv4.z : inv4.w));
+          const float msg = fmaf(ln_scale * inv, yc[j], ln_offset);  // e' : the message
+          if (j < valid) {
+            erow[(int64_t)j * kLatent] = msg + eold[j];  // residual (gns.py:120-122)
+            seg_sum += msg;
+            if ((emask >> j) & 1u) {  // bucket ends here (uniform across the CTA half)
+              const int el = cc * 32 + j;
+              float* dst = a.agg + (int64_t)ridx[1 + col0 + j] * kLatent + f;
+              if (el == rows_h - 1 && last_cont) dst = clast;
+              if (seg_first && first_cont) dst = cfirst;
+              *dst = seg_sum;
+              seg_sum = 0.f;
+              seg_first = false;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+static int g_num_sms = 0;
+
+int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
+  static int attr_rc = -1;
+  if (attr_rc < 0) {
+    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc);
+    int dev = 0;
+    if (attr_rc == 0) attr_rc = (int)cudaGetDevice(&dev);
+    if (attr_rc == 0) attr_rc = (int)cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (attr_rc) return attr_rc;
+  const int n_tiles = cdiv(e_cap, kTcTile);
+  const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
+  { edge_mp_tc_kernel<<<grid, kTcThreads, kSmemTc, s>>>(a); LB_LAUNCHED(1); }
+  return 0;
+}
+
+}  // namespace lb

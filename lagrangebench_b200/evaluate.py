@@ -106,7 +106,8 @@ class RolloutEngine:
         cfg = _cabi.RolloutCfg()
         cfg.grid = neighbors._grid
         cfg.feat = h["feature_cfg"](n)
-        cfg.gns = gns_cfg(self.packed, n, neighbors.max_occupancy, cfg.feat.node_stride, cfg.feat.node_stride)
+        cfg.gns = gns_cfg(self.packed, n, neighbors.max_occupancy, cfg.feat.node_stride, cfg.feat.node_stride,
+                          self.model.edge_impl)
         cfg.integ = h["integrate_cfg"](n, h["isl"], 0)
         cfg.cell_capacity = neighbors.cell_list_capacity or 0
         cfg.e_cap = neighbors.max_occupancy

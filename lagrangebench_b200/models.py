@@ -71,6 +71,29 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
         cursor[0] += flat.size + pad
         return off
 
+    def umma_operand(wt):
+        """(128 m, 128 k) float32 -> (hi, lo) fp16 in the UMMA no-swizzle K-major layout
+        [k/8][m][k%8], with wt = hi + lo * 2^-11."""
+        wt = np.ascontiguousarray(wt, dtype=np.float32)
+        hi = wt.astype(np.float16)
+        lo = ((wt - hi.astype(np.float32)) * np.float32(2048.0)).astype(np.float16)
+        lay = lambda x: x.reshape(latent, latent // 8, 8).transpose(1, 0, 2).reshape(-1)  # noqa: E731
+        return lay(hi), lay(lo)
+
+    def put_tc_edge(mods, o):
+        """Tensor-core operands of a processor edge MLP (include/lb200.h, lb200_mlp_off.tc_*)."""
+        l0, l1, ln = mods
+        w1e_t = np.asarray(l0["w"], dtype=np.float32)[2 * latent:3 * latent].T  # (f, k)
+        w2 = np.asarray(l1["w"], dtype=np.float64)
+        b2 = np.asarray(l1["b"], dtype=np.float64)
+        w2c_t = (w2 - w2.mean(axis=1, keepdims=True)).astype(np.float32).T  # LayerNorm mean folded in
+        b2c = (b2 - b2.mean()).astype(np.float32)
+        h1, l1_ = umma_operand(w1e_t)
+        h2, l2_ = umma_operand(w2c_t)
+        halves = np.concatenate([h1, l1_, h2, l2_])
+        o.tc_w = put(halves.view(np.float32))
+        o.tc_vec = put(np.concatenate([b2c, np.asarray(ln["scale"], np.float32), np.asarray(ln["offset"], np.float32)]))
+
     def put_mlp(mods, in_rows, out_cols, rows_pad=None):
         l0, l1, ln = mods
         w0, w1 = np.asarray(l0["w"]), np.asarray(l1["w"])
@@ -82,6 +105,7 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
         o.w1, o.b1 = put(w1), put(l1["b"])
         o.ln_scale = put(ln["scale"]) if ln is not None else -1
         o.ln_offset = put(ln["offset"]) if ln is not None else -1
+        o.tc_w = o.tc_vec = -1
         return o
 
     emb_mod = None
@@ -105,7 +129,10 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
     proc_edge = (_cabi.MlpOff * num_mp_steps)()
     proc_node = (_cabi.MlpOff * num_mp_steps)()
     for m in range(num_mp_steps):
-        proc_edge[m] = put_mlp(_mlp_modules(params, "_processor", 2 * m), 3 * latent, latent)
+        mods = _mlp_modules(params, "_processor", 2 * m)
+        oe = put_mlp(mods, 3 * latent, latent)
+        put_tc_edge(mods, oe)
+        proc_edge[m] = oe
         proc_node[m] = put_mlp(_mlp_modules(params, "_processor", 2 * m + 1), 2 * latent, latent)
     dec = put_mlp(_mlp_modules(params, "_decoder", 0, layer_norm=False), latent, dim)
     blob = torch.from_numpy(np.concatenate(chunks)).to(device)
@@ -113,8 +140,12 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
                         num_types, dim, num_mp_steps)
 
 
-def gns_cfg(packed, n, e_cap, node_in, node_stride):
+EDGE_IMPL = {"tc": 0, "simt": 1}
+
+
+def gns_cfg(packed, n, e_cap, node_in, node_stride, edge_impl="tc"):
     c = _cabi.GnsCfg()
+    c.edge_impl = EDGE_IMPL[edge_impl]
     c.n, c.dim, c.num_mp_steps = n, packed.dim, packed.num_mp_steps
     c.node_in, c.node_stride = node_in, node_stride
     c.embed_size, c.num_particle_types = packed.embed_size, packed.num_types
@@ -184,6 +215,9 @@ class GNS:
         self._embedding_size = int(particle_type_embedding_size) if num_particle_types > 1 else 0
         self._packed = {}
         self._bufs = {}
+        # "tc": tcgen05 tensor-core message kernel (product path); "simt": fp32 CUDA-core
+        # kernel kept as the numerical cross-check of the split-precision scheme
+        self.edge_impl = "tc"
 
     # -- hk.transform_with_state surface ---------------------------------------------
     def init(self, key, sample):
@@ -248,7 +282,7 @@ class GNS:
         ptype = torch.as_tensor(particle_type).to(dev, torch.int32).contiguous()
         e_cap = idx.shape[1]
         b = self._buffers(n, e_cap, dev)
-        cfg = gns_cfg(pk, n, e_cap, node_feat.shape[1], node_feat.shape[1])
+        cfg = gns_cfg(pk, n, e_cap, node_feat.shape[1], node_feat.shape[1], self.edge_impl)
         out = torch.empty((n, self._output_size), dtype=torch.float32, device=dev)
         st = _cabi.stream()
         _cabi.check(lib.lb200_csr_build(_cabi.ptr(idx), n, e_cap, _cabi.ptr(b["rowptr"]), _cabi.ptr(b["perm"]),

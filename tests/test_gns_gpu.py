@@ -91,3 +91,15 @@ def test_forward_is_deterministic():
     got1, _, _, (c, ours, f_gpu, params, model) = _forward_both("rpf2d", "float32")
     out2, _ = model.apply(params, {}, (f_gpu, c["particle_type"]))
     assert np.array_equal(got1, out2["acc"].cpu().numpy()), "aggregation must be bitwise reproducible"
+
+
+def test_tensor_core_kernel_matches_cuda_core_kernel():
+    """The tcgen05 message kernel (fp16 hi/lo split, fp32 accumulate) against the fp32
+    CUDA-core kernel on the same inputs: both sit at float32 rounding level."""
+    got_tc, ref64, _, (c, ours, f_gpu, params, model) = _forward_both("rpf3d_8k", "float32")
+    assert model.edge_impl == "tc"
+    model.edge_impl = "simt"
+    out, _ = model.apply(params, {}, (f_gpu, c["particle_type"]))
+    got_simt = out["acc"].cpu().numpy()
+    assert rel_err(got_tc, got_simt) <= 5e-6
+    assert rel_err(got_tc, ref64) <= TOL and rel_err(got_simt, ref64) <= TOL

@@ -79,8 +79,10 @@ def test_engine_rollout_matches_oracle_loop(name, dtype):
     got = preds.cpu().numpy()
     # 3 + 1 steps: one host sync per chunk (plus one per re-allocation), not one per step
     assert engine.n_launch_calls == 2 + engine.n_reallocations
-    dx = c["metadata"]["dx"]
-    assert np.abs(got - ref[0]).max() <= 1e-6 * dx, "positions drift from the oracle loop"
+    # accelerations agree to ~1e-6 relative; positions additionally carry their own rounding
+    # (a few ulp of the box size in the position dtype)
+    tol = 1e-6 * c["metadata"]["dx"] + 8 * np.finfo(npd).eps * float(np.max(c["box"]))
+    assert np.abs(got - ref[0]).max() <= tol, "positions drift from the oracle loop"
     kin = np.isin(c["particle_type"], [1, 2, -1])
     if kin.any():  # kinematic particles follow the ground truth exactly (rollout.py:64-69)
         assert np.array_equal(got[:, kin], c["positions"][kin, 6:6 + n_steps].transpose(1, 0, 2))
