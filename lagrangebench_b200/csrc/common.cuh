@@ -23,7 +23,7 @@ namespace lb {
 constexpr int kLatent = LB200_LATENT;
 // Receiver-sorted edges per message tile / nodes per node tile.  The edge kernel and the
 // node kernel agree on the carry protocol through these two constants only.
-constexpr int kEdgeTile = 64;
+constexpr int kEdgeTile = 32;
 constexpr int kNodeTile = 64;
 
 // cumulative number of kernels launched by the library (lb200_launch_count)

@@ -28,7 +28,7 @@ constexpr int kTM = 64;         // rows per tile (== kEdgeTile == kNodeTile)
 constexpr int kWChunk = 32;     // weight rows per cp.async stage
 constexpr int kLdA = kLatent + 4;
 constexpr int kEncK = LB200_MAX_NODE_IN;  // node-encoder input width, zero padded
-static_assert(kEdgeTile == kTM && kNodeTile == kTM, "tile constants");
+static_assert(kTM % kEdgeTile == 0 && kNodeTile == kTM, "tile constants");
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -373,25 +373,32 @@ __global__ void __launch_bounds__(kThreads, 2) edge_mp_kernel(EdgeMpArgs a) {
   }
   store_tile_global(acc, a.e, slot0, rows, kLatent, 0);
   __syncthreads();
-  // deterministic segmented sum over receivers: one thread per column walks the tile's rows
+  // deterministic segmented sum over receivers: one thread per column walks the tile's rows,
+  // one carry sub-tile (kEdgeTile edges) at a time
   if (threadIdx.x < kLatent) {
     const int c = threadIdx.x;
-    const bool first_cont = ridx[kTM] == ridx[0];
-    const bool last_cont = ridx[kTM + 1] == ridx[rows - 1];
-    float sum = 0.f;
-    int seg_start = 0;
-    for (int r = 0; r < rows; ++r) {
-      sum += A2[r * kLdA + c];
-      const bool end = (r == rows - 1) || (ridx[r + 1] != ridx[r]);
-      if (end) {
-        if (seg_start == 0 && first_cont)
-          a.carry_first[(int64_t)blockIdx.x * kLatent + c] = sum;
-        else if (r == rows - 1 && last_cont)
-          a.carry_last[(int64_t)blockIdx.x * kLatent + c] = sum;
-        else
-          a.agg[(int64_t)ridx[r] * kLatent + c] = sum;
-        sum = 0.f;
-        seg_start = r + 1;
+    for (int r0 = 0; r0 < rows; r0 += kEdgeTile) {
+      const int r1 = min(rows, r0 + kEdgeTile);
+      const int before = r0 == 0 ? ridx[kTM] : ridx[r0 - 1];
+      const int after = r1 == rows ? ridx[kTM + 1] : ridx[r1];
+      const bool first_cont = before == ridx[r0];
+      const bool last_cont = after == ridx[r1 - 1];
+      const int64_t sub = (int64_t)blockIdx.x * (kTM / kEdgeTile) + r0 / kEdgeTile;
+      float sum = 0.f;
+      int seg_start = r0;
+      for (int r = r0; r < r1; ++r) {
+        sum += A2[r * kLdA + c];
+        const bool end = (r == r1 - 1) || (ridx[r + 1] != ridx[r]);
+        if (end) {
+          if (seg_start == r0 && first_cont)
+            a.carry_first[sub * kLatent + c] = sum;
+          else if (r == r1 - 1 && last_cont)
+            a.carry_last[sub * kLatent + c] = sum;
+          else
+            a.agg[(int64_t)ridx[r] * kLatent + c] = sum;
+          sum = 0.f;
+          seg_start = r + 1;
+        }
       }
     }
   }
@@ -547,14 +554,15 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const int n = c->n, e_cap = c->e_cap;
-  const int nt = cdiv(e_cap, kEdgeTile);
+  const int nt = cdiv(e_cap, kTM);             // CUDA-core edge tiles
+  const int n_sub = cdiv(e_cap, kEdgeTile);    // carry sub-tiles
   Arena ar(scratch_dev, scratch_bytes);
   float* h = ar.take<float>((int64_t)n * kLatent);
   float* P = ar.take<float>((int64_t)n * 2 * kLatent);
   float* agg = ar.take<float>((int64_t)n * kLatent);
   float* e = ar.take<float>((int64_t)e_cap * kLatent);
-  float* cf = ar.take<float>((int64_t)(nt + 1) * kLatent);
-  float* cl = ar.take<float>((int64_t)(nt + 1) * kLatent);
+  float* cf = ar.take<float>((int64_t)(n_sub + 1) * kLatent);
+  float* cl = ar.take<float>((int64_t)(n_sub + 1) * kLatent);
   if (!ar.ok()) return LB200_EINVAL;
   const float* w = weights_dev;
 

@@ -1,7 +1,9 @@
 // Message passing, edge side, on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
 //
 // Replaces update_edge_fn + segment_sum of the jraph.GraphNetwork block
-// (lagrangebench/models/gns.py:86-101,117-122) for one tile of 128 receiver-sorted edges:
+// (lagrangebench/models/gns.py:86-101,117-122) for tiles of 64 receiver-sorted edges (two
+// independent 128-thread workers per persistent CTA, so one worker's epilogue overlaps the
+// other's MMAs and memory latency):
 //
 //   hidden = relu(e @ W1e + P_s[snd] + P_r[rcv])        (P = per-node projections, gns.cu)
 //   yc     = hidden @ W2c + b2c                          (W2c/b2c: LayerNorm mean folded in)
@@ -25,33 +27,36 @@
 // (row, k) at (k / 8) * LBO + row * 16 + (k % 8) * 2 bytes, 8-row groups 128 B apart (SBO).
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "gns_tc.cuh"
 
 namespace lb {
 
-constexpr int kTcThreads = 256;
-constexpr int kTcTile = 128;           // edges per CTA tile = 2 carry sub-tiles of kEdgeTile
+constexpr int kTcThreads = 512;        // two 256-thread workers per CTA; 16 warps hide the epilogue latency
+constexpr int kTcTile = 64;            // edges per worker tile (one N=64 MMA tile) = 2 carry sub-tiles
 constexpr uint32_t kLboA = 2048;       // weights: 128 rows * 16 B per 8-wide K slab
-constexpr uint32_t kLboB = 2064;       // edge tile: padded slab pitch -> conflict-free stores
+constexpr uint32_t kLboB = 2064;       // edge operand: padded slab pitch -> conflict-free stores
 constexpr uint32_t kSbo = 128;
 constexpr uint32_t kWBytes = 16 * kLboA;  // one 128x128 fp16 weight operand (32 KB)
-constexpr uint32_t kBBytes = 16 * kLboB;  // one 128x128 fp16 edge operand (33 KB)
-// instruction descriptor: D=F32 (bit 4), A=B=F16 (0), both K-major, N=128 (>>3 at bit 17), M=128 (>>4 at bit 24)
-constexpr uint32_t kIdesc = (1u << 4) | (16u << 17) | (8u << 24);
+constexpr uint32_t kBBytes = 16 * kLboB;  // one 128-row fp16 edge operand (33 KB): rows 0..63 worker 0, 64..127 worker 1
+// instruction descriptor: D=F32 (bit 4), A=B=F16 (0), both K-major, N=64 (>>3 at bit 17), M=128 (>>4 at bit 24)
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTcTile >> 3) << 17) | (8u << 24);
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
-static_assert(kTcTile == 2 * kEdgeTile, "carry protocol: two 64-edge sub-tiles per CTA tile");
+static_assert(kTcTile == 2 * kEdgeTile && kEdgeTile == 32, "a warp's 32-edge chunk is one carry sub-tile");
 
 // shared memory map (bytes)
 constexpr uint32_t kOffW = 0;                         // W1e_hi, W1e_lo, W2c_hi, W2c_lo
 constexpr uint32_t kOffB = kOffW + 4 * kWBytes;       // B_hi, B_lo
 constexpr uint32_t kOffVec = kOffB + 2 * kBBytes;     // b2c[128], scale[128], offset[128]
-constexpr uint32_t kOffIdx = kOffVec + 3 * 512;       // sidx[128], ridx_ext[130]
-constexpr uint32_t kOffRed = kOffIdx + (128 + 132) * 4;  // red[2 buf][2 halves][4][32]
-constexpr uint32_t kOffInv = kOffRed + 2 * 2 * 4 * 32 * 4;  // inv[8 warps][32]: 1/sqrt(var + eps) per edge
-constexpr uint32_t kOffEnd = kOffInv + 8 * 32 * 4;          // endmask[4]: bit = last edge of its receiver bucket
-constexpr uint32_t kOffBar = kOffEnd + 16;                  // mbarriers (2 x 8 B) + tmem base (4 B)
-constexpr uint32_t kSmemTc = kOffBar + 32;
+constexpr uint32_t kOffIdx = kOffVec + 3 * 512;       // per worker: sidx[64], rclamp[64], ridx_ext[68]
+constexpr uint32_t kIdxInts = 64 + 64 + 68;
+constexpr uint32_t kOffRed = kOffIdx + 2 * kIdxInts * 4;    // per worker: red[2 chunks][4 warps][32]
+constexpr uint32_t kOffInv = kOffRed + 2 * 2 * 4 * 32 * 4;  // inv[16 warps][32]: 1/sqrt(var + eps) per edge
+constexpr uint32_t kOffEnd = kOffInv + 16 * 32 * 4;         // per worker: endmask[2]
+constexpr uint32_t kOffBar = kOffEnd + 16;                  // mbarriers: weights, mma[2]; tmem base
+constexpr uint32_t kSmemTc = kOffBar + 48;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -178,34 +183,44 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32]) {
 __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
-  float* vec = reinterpret_cast<float*>(smem + kOffVec);
-  int* sidx = reinterpret_cast<int*>(smem + kOffIdx);
-  int* ridx = sidx + 128;  // ridx[0] = receiver before the tile, ridx[1 + i] = row i, ridx[1 + rows] = after
-  float* red = reinterpret_cast<float*>(smem + kOffRed);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 16);
-  const uint32_t bar_w = sbase + kOffBar, bar_mma = sbase + kOffBar + 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter of this warp; which 64 edge columns it owns
-  const int f = q * 32 + lane;               // output feature == TMEM lane of this thread
+  const int wk = warp >> 3;        // worker (0/1): 8 warps, one 64-edge MMA tile at a time
+  const int c = (warp >> 2) & 1;   // which 32-edge chunk (carry sub-tile) of the tile this warp finishes
+  const int q = warp & 3;          // TMEM lane quarter of this warp
+  const int wtid = tid & 255;      // thread index inside the worker
+  const int f = q * 32 + lane;     // output feature == TMEM lane of this thread
+  float* vec = reinterpret_cast<float*>(smem + kOffVec);
+  int* sidx = reinterpret_cast<int*>(smem + kOffIdx) + wk * kIdxInts;
+  int* rclamp = sidx + 64;   // receivers clamped to a valid row (gather addresses)
+  int* ridx = rclamp + 64;   // ridx[0] = receiver before the tile, ridx[1 + i] = edge i, ridx[1 + rows] = after
+  float* red = reinterpret_cast<float*>(smem + kOffRed) + wk * 256 + c * 128;
+  float* invs = reinterpret_cast<float*>(smem + kOffInv) + warp * 32;
+  uint32_t* endm = reinterpret_cast<uint32_t*>(smem + kOffEnd) + wk * 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 32);
+  const uint32_t bar_w = sbase + kOffBar, bar_mma = sbase + kOffBar + 8 + 8 * wk;
+  const uint32_t bar_worker = 1 + wk;          // named barrier: the worker's 256 threads
+  const uint32_t bar_chunk = 3 + wk * 2 + c;   // named barrier: the 4 warps sharing a 32-edge chunk
 
   const int E = a.rowptr[a.n];
   const int n_tiles = (E + kTcTile - 1) / kTcTile;
-  if ((int)blockIdx.x >= n_tiles) return;
+  if ((int)blockIdx.x * 2 >= n_tiles) return;
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_mma, 1);
+    mbar_init(sbase + kOffBar + 8, 1);
+    mbar_init(sbase + kOffBar + 16, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t acc_hh = tmem, acc_x = tmem + 128;
+  // TMEM columns: [0,64) acc_hh worker 0, [64,128) acc_hh worker 1, [128,192) acc_x worker 0, [192,256) acc_x worker 1
+  const uint32_t acc_hh = tmem + wk * kTcTile, acc_x = tmem + 128 + wk * kTcTile;
 
   // resident weights: 4 fp16 operands (128 KB) + centred bias, LayerNorm scale / offset
   if (tid == 0) {
@@ -217,52 +232,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
   const float b2c = vec[f], ln_scale = vec[128 + f], ln_offset = vec[256 + f];
 
   const uint32_t w1_hi = sbase + kOffW, w1_lo = w1_hi + kWBytes, w2_hi = w1_lo + kWBytes, w2_lo = w2_hi + kWBytes;
-  const uint32_t b_hi = sbase + kOffB, b_lo = b_hi + kBBytes;
-  unsigned char* b_hi_p = smem + kOffB;
+  // this worker's 64 operand rows inside every K slab
+  const uint32_t b_hi = sbase + kOffB + wk * (kTcTile * 16), b_lo = b_hi + kBBytes;
+  unsigned char* b_hi_p = smem + kOffB + wk * (kTcTile * 16);
   unsigned char* b_lo_p = b_hi_p + kBBytes;
-  const uint32_t t_lane = (uint32_t)(q * 32) << 16;
-  // this thread's element of operand row `e` (edge), k = f:
-  const uint32_t elem_off = (uint32_t)(f >> 3) * kLboB + (uint32_t)(f & 7) * 2;
+  const uint32_t t_addr = ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);  // lane quarter, chunk columns
+  // this thread's element (k = f) of operand row `e` (edge) of its chunk:
+  const uint32_t elem_off = (uint32_t)(f >> 3) * kLboB + (uint32_t)(f & 7) * 2 + (uint32_t)(c * 32) * 16;
   uint32_t phase = 0;
 
-  float* invs = reinterpret_cast<float*>(smem + kOffInv) + warp * 32;
-  uint32_t* endm = reinterpret_cast<uint32_t*>(smem + kOffEnd);
-
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x * 2 + wk; tile < n_tiles; tile += gridDim.x * 2) {
     const int64_t slot0 = (int64_t)tile * kTcTile;
     const int rows = min(kTcTile, E - (int)slot0);
-    __syncthreads();  // previous tile's epilogue is done with sidx / ridx / B operands
-    if (tid < kTcTile) {
-      const bool ok = tid < rows;
-      const int r_here = ok ? a.rcv[slot0 + tid] : -1;
-      const int r_next = (slot0 + tid + 1 < E) ? a.rcv[slot0 + tid + 1] : -3;
-      sidx[tid] = ok ? a.snd[slot0 + tid] : 0;
-      ridx[1 + tid] = ok ? r_here : (tid == rows ? -3 : -1);  // -3: "no edge after the tile"
-      // last edge of its receiver bucket inside this 64-edge carry sub-tile
-      const bool end = ok && (r_next != r_here || (tid & 63) == 63 || tid == rows - 1);
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");  // previous tile is done with idx / operands
+    if (wtid < kTcTile) {
+      const bool ok = wtid < rows;
+      const int r_here = ok ? a.rcv[slot0 + wtid] : -1;
+      const int r_next = (slot0 + wtid + 1 < E) ? a.rcv[slot0 + wtid + 1] : -3;
+      sidx[wtid] = ok ? a.snd[slot0 + wtid] : 0;
+      rclamp[wtid] = max(r_here, 0);
+      ridx[1 + wtid] = ok ? r_here : (wtid == rows ? -3 : -1);  // -3: "no edge after the tile"
+      // last edge of its receiver bucket inside its 32-edge carry sub-tile
+      const bool end = ok && (r_next != r_here || lane == 31 || wtid == rows - 1);
       const uint32_t m = __ballot_sync(0xffffffffu, end);
-      if (lane == 0) endm[warp] = m;
-      if (tid == kTcTile - 1 && ok) ridx[1 + kTcTile] = r_next;  // receiver just after a full tile
-    } else if (tid == kTcTile) {
+      if (lane == 0) endm[wtid >> 5] = m;
+      if (wtid == kTcTile - 1 && ok) ridx[1 + kTcTile] = r_next;  // receiver just after a full tile
+    } else if (wtid == kTcTile) {
       ridx[0] = slot0 > 0 ? a.rcv[slot0 - 1] : -2;
     }
-    // ---- phase A: edge latents -> fp16 hi/lo N-side operand (coalesced 512 B rows)
+    // ---- phase A: edge latents -> fp16 hi/lo N-side operand (coalesced 512 B rows), 8 rows per warp
     {
-      float4 v[16];
+      const int r0 = (warp & 7) * 8;
+      float4 v[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int r = warp * 16 + i;
-        v[i] = r < rows ? reinterpret_cast<const float4*>(a.e + (slot0 + r) * kLatent)[lane]
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int i = 0; i < 8; ++i)
+        v[i] = r0 + i < rows ? reinterpret_cast<const float4*>(a.e + (slot0 + r0 + i) * kLatent)[lane]
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int r = warp * 16 + i;
+      for (int i = 0; i < 8; ++i) {
         const __half2 h01 = __floats2half2_rn(v[i].x, v[i].y), h23 = __floats2half2_rn(v[i].z, v[i].w);
         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
         const __half2 l01 = __floats2half2_rn((v[i].x - f01.x) * kLoScale, (v[i].y - f01.y) * kLoScale);
         const __half2 l23 = __floats2half2_rn((v[i].z - f23.x) * kLoScale, (v[i].w - f23.y) * kLoScale);
-        const uint32_t off = (uint32_t)(lane >> 1) * kLboB + (uint32_t)r * 16 + (uint32_t)(lane & 1) * 8;
+        const uint32_t off = (uint32_t)(lane >> 1) * kLboB + (uint32_t)(r0 + i) * 16 + (uint32_t)(lane & 1) * 8;
         *reinterpret_cast<uint2*>(b_hi_p + off) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
         *reinterpret_cast<uint2*>(b_lo_p + off) =
@@ -271,117 +283,137 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
     }
     fence_async_smem();
     tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");
+    if (wtid == 0) {
       tc_fence_after();
       issue_gemm(w1_hi, w1_lo, b_hi, b_lo, acc_hh, acc_x);
       umma_commit(bar_mma);
     }
-    mbar_wait(bar_mma, phase);
-    phase ^= 1;
-    tc_fence_after();
-
-    // ---- epilogue 1: hidden = relu(acc + P_s[snd] + P_r[rcv]) -> fp16 hi/lo operand for layer 2
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int col0 = half * 64 + cc * 32;
-      float hh[32], xx[32];
-      tmem_ld_pair(acc_hh + t_lane + col0, acc_x + t_lane + col0, hh, xx);
+    // ---- epilogue 1: hidden = relu(acc + P_s[snd] + P_r[rcv]) -> fp16 hi/lo operand for layer 2.
+    //      The gathers depend only on the indices: the first batch is in flight while the MMAs run,
+    //      and batch b+1 is issued before batch b is consumed.
+    {
+      const int* sp = sidx + c * 32;
+      const int* rp = rclamp + c * 32;
+      float ps[2][8], pr[2][8];
+      auto gather = [&](int j0, float (&gs)[8], float (&gr)[8]) {
+        const int4 sa = *reinterpret_cast<const int4*>(sp + j0), sb = *reinterpret_cast<const int4*>(sp + j0 + 4);
+        const int4 ra = *reinterpret_cast<const int4*>(rp + j0), rb = *reinterpret_cast<const int4*>(rp + j0 + 4);
+        const int si[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+        const int ri[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
-      for (int j0 = 0; j0 < 32; j0 += 16) {
-        float ps[16], pr[16];
-#pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4) {
-          const int4 s4 = *reinterpret_cast<const int4*>(sidx + col0 + j0 + j4);
-          int r4[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) r4[t] = max(ridx[1 + col0 + j0 + j4 + t], 0);
-          ps[j4 + 0] = __ldg(a.P + (int64_t)s4.x * (2 * kLatent) + f);
-          ps[j4 + 1] = __ldg(a.P + (int64_t)s4.y * (2 * kLatent) + f);
-          ps[j4 + 2] = __ldg(a.P + (int64_t)s4.z * (2 * kLatent) + f);
-          ps[j4 + 3] = __ldg(a.P + (int64_t)s4.w * (2 * kLatent) + f);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) pr[j4 + t] = __ldg(a.P + (int64_t)r4[t] * (2 * kLatent) + kLatent + f);
+        for (int j = 0; j < 8; ++j) {
+          gs[j] = __ldg(a.P + (int64_t)si[j] * (2 * kLatent) + f);
+          gr[j] = __ldg(a.P + (int64_t)ri[j] * (2 * kLatent) + kLatent + f);
         }
+      };
+      gather(0, ps[0], pr[0]);
+      mbar_wait(bar_mma, phase);
+      phase ^= 1;
+      tc_fence_after();
+      float acc[32];
+      {
+        float hh[32], xx[32];
+        tmem_ld_pair(acc_hh + t_addr, acc_x + t_addr, hh, xx);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int e = col0 + j0 + j;
-          const float hval = fmaxf(fmaf(xx[j0 + j], kLoInv, hh[j0 + j]) + ps[j] + pr[j], 0.f);
+        for (int j = 0; j < 32; ++j) acc[j] = fmaf(xx[j], kLoInv, hh[j]);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (b + 1 < 4) gather((b + 1) * 8, ps[(b + 1) & 1], pr[(b + 1) & 1]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float hval = fmaxf(acc[b * 8 + j] + ps[b & 1][j] + pr[b & 1][j], 0.f);
           const __half hi = __float2half_rn(hval);
           const __half lo = __float2half_rn((hval - __half2float(hi)) * kLoScale);
-          *reinterpret_cast<__half*>(b_hi_p + elem_off + (uint32_t)e * 16) = hi;
-          *reinterpret_cast<__half*>(b_lo_p + elem_off + (uint32_t)e * 16) = lo;
+          *reinterpret_cast<__half*>(b_hi_p + elem_off + (uint32_t)(b * 8 + j) * 16) = hi;
+          *reinterpret_cast<__half*>(b_lo_p + elem_off + (uint32_t)(b * 8 + j) * 16) = lo;
         }
       }
     }
     fence_async_smem();
     tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");
+    if (wtid == 0) {
       tc_fence_after();
       issue_gemm(w2_hi, w2_lo, b_hi, b_lo, acc_hh, acc_x);
       umma_commit(bar_mma);
     }
-    mbar_wait(bar_mma, phase);
-    phase ^= 1;
-    tc_fence_after();
-
-    // ---- epilogue 2: LayerNorm (mean folded into the weights), residual, store, segmented sum
-    const int sub = (int)(slot0 / kEdgeTile) + half;          // 64-edge carry sub-tile of this warp
-    const int rows_h = min(max(rows - half * 64, 0), 64);     // valid edges in it
-    const bool first_cont = rows_h > 0 && ridx[half * 64] == ridx[1 + half * 64];
-    const bool last_cont = rows_h > 0 && ridx[1 + half * 64 + rows_h] == ridx[half * 64 + rows_h];
-    float* const cfirst = a.carry_first + (int64_t)sub * kLatent + f;
-    float* const clast = a.carry_last + (int64_t)sub * kLatent + f;
-    float seg_sum = 0.f;
-    bool seg_first = true;  // still inside the first bucket of the sub-tile
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int col0 = half * 64 + cc * 32;
+    // ---- epilogue 2: LayerNorm (mean folded into the weights), residual, store, segmented sum.
+    //      Each warp finishes its own 32-edge chunk == one carry sub-tile.  The residual rows are
+    //      requested before waiting for the MMAs.
+    {
+      const int col0 = c * 32;
       const int valid = min(max(rows - col0, 0), 32);  // edges of this chunk that exist
-      float eold[32];
       float* const erow = a.e + (slot0 + col0) * kLatent + f;
+      float eold[32];
+      if (valid == 32) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) eold[j] = j < valid ? erow[(int64_t)j * kLatent] : 0.f;
-      float yc[32], sq[32];
-      tmem_ld_pair(acc_hh + t_lane + col0, acc_x + t_lane + col0, yc, sq);
+        for (int j = 0; j < 32; ++j) eold[j] = erow[(int64_t)j * kLatent];
+      } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        yc[j] = fmaf(sq[j], kLoInv, yc[j]) + b2c;
-        sq[j] = yc[j] * yc[j];
+        for (int j = 0; j < 32; ++j) eold[j] = j < valid ? erow[(int64_t)j * kLatent] : 0.f;
       }
-      const float part = warp_transpose_reduce(sq);  // lane l: this warp's 32 features, edge col0 + l
-      float* rbuf = red + (cc & 1) * 256 + half * 128;
-      rbuf[q * 32 + lane] = part;
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // the 4 warps sharing these columns
+      mbar_wait(bar_mma, phase);
+      phase ^= 1;
+      tc_fence_after();
+      float yc[32];
+      float part;
       {
-        const float var = (rbuf[lane] + rbuf[32 + lane] + rbuf[64 + lane] + rbuf[96 + lane]) * (1.0f / kLatent);
+        float sq[32];
+        tmem_ld_pair(acc_hh + t_addr, acc_x + t_addr, yc, sq);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          yc[j] = fmaf(sq[j], kLoInv, yc[j]) + b2c;
+          sq[j] = yc[j] * yc[j];
+        }
+        part = warp_transpose_reduce(sq);  // lane l: this warp's 32 features, edge col0 + l
+      }
+      red[q * 32 + lane] = part;
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_chunk) : "memory");
+      {
+        const float var = (red[lane] + red[32 + lane] + red[64 + lane] + red[96 + lane]) * (1.0f / kLatent);
         invs[lane] = 1.0f / sqrtf(var + 1e-5f);  // once per edge per warp (same value in the 4 warps)
       }
       __syncwarp();
-      const uint32_t emask = endm[col0 >> 5];
+      if (valid > 0) {
+        const uint32_t emask = endm[c];
+        const bool first_cont = ridx[col0] == ridx[1 + col0];
+        const bool last_cont = ridx[1 + col0 + valid] == ridx[col0 + valid];
+        const int sub = tile * 2 + c;  // carry sub-tile index (slot / kEdgeTile)
+        float* const cfirst = a.carry_first + (int64_t)sub * kLatent + f;
+        float* const clast = a.carry_last + (int64_t)sub * kLatent + f;
+        float seg_sum = 0.f;
+        bool seg_first = true;  // still inside the first bucket of the sub-tile
+        auto finish = [&](auto full_tag) {
+          constexpr bool kFull = decltype(full_tag)::value;
 #pragma unroll
-      for (int j4 = 0; j4 < 32; j4 += 4) {
-        const float4 inv4 = *reinterpret_cast<const float4*>(invs + j4);
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            const float4 inv4 = *reinterpret_cast<const float4*>(invs + j4);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int j = j4 + t;
-          const float inv = t == 0 ? inv4.x : (t == 1 ? inv4.y : (t == 2 ? inv4.z : inv4.w));
-          const float msg = fmaf(ln_scale * inv, yc[j], ln_offset);  // e' : the message
-          if (j < valid) {
-            erow[(int64_t)j * kLatent] = msg + eold[j];  // residual (gns.py:120-122)
-            seg_sum += msg;
-            if ((emask >> j) & 1u) {  // bucket ends here (uniform across the CTA half)
-              const int el = cc * 32 + j;
-              float* dst = a.agg + (int64_t)ridx[1 + col0 + j] * kLatent + f;
-              if (el == rows_h - 1 && last_cont) dst = clast;
-              if (seg_first && first_cont) dst = cfirst;
-              *dst = seg_sum;
-              seg_sum = 0.f;
-              seg_first = false;
+            for (int t = 0; t < 4; ++t) {
+              const int j = j4 + t;
+              const float inv = t == 0 ? inv4.x : (t == 1 ? inv4.y : (t == 2 ? inv4.z : inv4.w));
+              const float msg = fmaf(ln_scale * inv, yc[j], ln_offset);  // e' : the message
+              if (kFull || j < valid) {
+                erow[(int64_t)j * kLatent] = msg + eold[j];  // residual (gns.py:120-122)
+                seg_sum += msg;
+                if ((emask >> j) & 1u) {  // bucket ends here (uniform across the 4 warps of the chunk)
+                  float* dst = a.agg + (int64_t)ridx[1 + col0 + j] * kLatent + f;
+                  if (j == valid - 1 && last_cont) dst = clast;
+                  if (seg_first && first_cont) dst = cfirst;
+                  *dst = seg_sum;
+                  seg_sum = 0.f;
+                  seg_first = false;
+                }
+              }
             }
           }
-        }
+        };
+        if (valid == 32)
+          finish(std::true_type{});
+        else
+          finish(std::false_type{});
       }
       __syncwarp();
     }
@@ -389,7 +421,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
   }
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
   }
 }
 
@@ -404,8 +436,8 @@ int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
     if (attr_rc == 0) attr_rc = (int)cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   if (attr_rc) return attr_rc;
-  const int n_tiles = cdiv(e_cap, kTcTile);
-  const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
+  const int n_pairs = cdiv(cdiv(e_cap, kTcTile), 2);  // two workers (tiles) per CTA
+  const int grid = n_pairs < g_num_sms ? n_pairs : g_num_sms;
   { edge_mp_tc_kernel<<<grid, kTcThreads, kSmemTc, s>>>(a); LB_LAUNCHED(1); }
   return 0;
 }
