@@ -143,6 +143,26 @@ __device__ __forceinline__ void tmem_ld_pair(uint32_t ta, uint32_t tb, float (&a
   }
 }
 
+// two accumulators x 16 columns (half the registers of tmem_ld_pair)
+__device__ __forceinline__ void tmem_ld_pair16(uint32_t ta, uint32_t tb, float (&a)[16], float (&b)[16]) {
+  uint32_t x[16], y[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(x[8]),
+        "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15]), "=r"(y[0]),
+        "=r"(y[1]), "=r"(y[2]), "=r"(y[3]), "=r"(y[4]), "=r"(y[5]), "=r"(y[6]), "=r"(y[7]), "=r"(y[8]), "=r"(y[9]),
+        "=r"(y[10]), "=r"(y[11]), "=r"(y[12]), "=r"(y[13]), "=r"(y[14]), "=r"(y[15])
+      : "r"(ta), "r"(tb)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    a[i] = __uint_as_float(x[i]);
+    b[i] = __uint_as_float(y[i]);
+  }
+}
+
 __device__ __forceinline__ void split_f16(float x, unsigned short& hi, unsigned short& lo) {
   const __half h = __float2half_rn(x);
   const __half l = __float2half_rn((x - __half2float(h)) * kLoScale);
@@ -241,9 +261,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
   const uint32_t elem_off = (uint32_t)(f >> 3) * kLboB + (uint32_t)(f & 7) * 2 + (uint32_t)(c * 32) * 16;
   uint32_t phase = 0;
 
-  for (int tile = blockIdx.x * 2 + wk; tile < n_tiles; tile += gridDim.x * 2) {
+  // this warp's 8 edge rows of a tile (coalesced 512 B rows); requested one tile ahead
+  const int r0 = (warp & 7) * 8;
+  float4 v[8];
+  auto request_rows = [&](int t) {
+    const int64_t s0 = (int64_t)t * kTcTile;
+    const int nr = min(kTcTile, E - (int)s0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      v[i] = r0 + i < nr ? reinterpret_cast<const float4*>(a.e + (s0 + r0 + i) * kLatent)[lane]
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  const int tile_stride = gridDim.x * 2;
+
+  for (int tile = blockIdx.x * 2 + wk; tile < n_tiles; tile += tile_stride) {
     const int64_t slot0 = (int64_t)tile * kTcTile;
     const int rows = min(kTcTile, E - (int)slot0);
+    request_rows(tile);
     asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");  // previous tile is done with idx / operands
     if (wtid < kTcTile) {
       const bool ok = wtid < rows;
@@ -260,14 +294,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
     } else if (wtid == kTcTile) {
       ridx[0] = slot0 > 0 ? a.rcv[slot0 - 1] : -2;
     }
-    // ---- phase A: edge latents -> fp16 hi/lo N-side operand (coalesced 512 B rows), 8 rows per warp
+    // ---- phase A: edge latents (already in registers) -> fp16 hi/lo N-side operand
     {
-      const int r0 = (warp & 7) * 8;
-      float4 v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        v[i] = r0 + i < rows ? reinterpret_cast<const float4*>(a.e + (slot0 + r0 + i) * kLatent)[lane]
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const __half2 h01 = __floats2half2_rn(v[i].x, v[i].y), h23 = __floats2half2_rn(v[i].z, v[i].w);
@@ -295,39 +323,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
     {
       const int* sp = sidx + c * 32;
       const int* rp = rclamp + c * 32;
-      float ps[2][8], pr[2][8];
-      auto gather = [&](int j0, float (&gs)[8], float (&gr)[8]) {
-        const int4 sa = *reinterpret_cast<const int4*>(sp + j0), sb = *reinterpret_cast<const int4*>(sp + j0 + 4);
-        const int4 ra = *reinterpret_cast<const int4*>(rp + j0), rb = *reinterpret_cast<const int4*>(rp + j0 + 4);
-        const int si[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-        const int ri[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+      float ps[32], pr[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          gs[j] = __ldg(a.P + (int64_t)si[j] * (2 * kLatent) + f);
-          gr[j] = __ldg(a.P + (int64_t)ri[j] * (2 * kLatent) + kLatent + f);
-        }
-      };
-      gather(0, ps[0], pr[0]);
+      for (int j0 = 0; j0 < 32; j0 += 4) {
+        const int4 s4 = *reinterpret_cast<const int4*>(sp + j0);
+        const int4 r4 = *reinterpret_cast<const int4*>(rp + j0);
+        ps[j0 + 0] = __ldg(a.P + (int64_t)s4.x * (2 * kLatent) + f);
+        ps[j0 + 1] = __ldg(a.P + (int64_t)s4.y * (2 * kLatent) + f);
+        ps[j0 + 2] = __ldg(a.P + (int64_t)s4.z * (2 * kLatent) + f);
+        ps[j0 + 3] = __ldg(a.P + (int64_t)s4.w * (2 * kLatent) + f);
+        pr[j0 + 0] = __ldg(a.P + (int64_t)r4.x * (2 * kLatent) + kLatent + f);
+        pr[j0 + 1] = __ldg(a.P + (int64_t)r4.y * (2 * kLatent) + kLatent + f);
+        pr[j0 + 2] = __ldg(a.P + (int64_t)r4.z * (2 * kLatent) + kLatent + f);
+        pr[j0 + 3] = __ldg(a.P + (int64_t)r4.w * (2 * kLatent) + kLatent + f);
+      }
       mbar_wait(bar_mma, phase);
       phase ^= 1;
       tc_fence_after();
-      float acc[32];
-      {
-        float hh[32], xx[32];
-        tmem_ld_pair(acc_hh + t_addr, acc_x + t_addr, hh, xx);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = fmaf(xx[j], kLoInv, hh[j]);
-      }
+      for (int h = 0; h < 2; ++h) {
+        float hh[16], xx[16];
+        tmem_ld_pair16(acc_hh + t_addr + h * 16, acc_x + t_addr + h * 16, hh, xx);
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        if (b + 1 < 4) gather((b + 1) * 8, ps[(b + 1) & 1], pr[(b + 1) & 1]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float hval = fmaxf(acc[b * 8 + j] + ps[b & 1][j] + pr[b & 1][j], 0.f);
+        for (int j = 0; j < 16; ++j) {
+          const int e = h * 16 + j;
+          const float hval = fmaxf(fmaf(xx[j], kLoInv, hh[j]) + ps[e] + pr[e], 0.f);
           const __half hi = __float2half_rn(hval);
           const __half lo = __float2half_rn((hval - __half2float(hi)) * kLoScale);
-          *reinterpret_cast<__half*>(b_hi_p + elem_off + (uint32_t)(b * 8 + j) * 16) = hi;
-          *reinterpret_cast<__half*>(b_lo_p + elem_off + (uint32_t)(b * 8 + j) * 16) = lo;
+          *reinterpret_cast<__half*>(b_hi_p + elem_off + (uint32_t)e * 16) = hi;
+          *reinterpret_cast<__half*>(b_lo_p + elem_off + (uint32_t)e * 16) = lo;
         }
       }
     }
