@@ -332,6 +332,118 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_sharded(args):
+    """ONE cloud sharded over the ranks (slab decomposition + halo exchange, domain.py):
+    strong scaling of the periodic RPF-3D clouds (BASELINE.json configs[4])."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from lagrangebench_b200 import _cabi
+    from lagrangebench_b200 import models as lbmodels
+    from lagrangebench_b200.domain import DistributedRollout
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _cabi.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, args.warmup
+    spec = build_workload(args.workload, 0, args.seed, "float32")
+    d = spec["metadata"]["dim"]
+    n_total = spec["positions"].shape[0]
+    params = lbmodels.init_params(node_in_of(spec), d, 128, MP_STEPS, 16, seed=args.seed)
+    tdt = torch.float64 if args.dtype == "float64" else torch.float32
+    dr = DistributedRollout(spec["box"], spec["metadata"], params, MP_STEPS, force=spec["force"], dtype=tdt,
+                            multiplier=spec["multiplier"]).scatter(spec["positions"], spec["particle_type"])
+    for _ in range(W):
+        dr.step()
+    barrier()
+    launches0 = lib.lb200_launch_count()
+    lib.lb200_profile(1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    halo_bytes = 0
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        dr.step()
+        halo_bytes += dr.halo_bytes
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.lb200_launch_count() - launches0
+    kms, kl = (C.c_double * 2)(), (C.c_int64 * 2)()
+    _cabi.check(lib.lb200_profile_read(kms, kl))
+    lib.lb200_profile(0)
+    n_own, n_edges = dr.window.shape[0], dr.edges_last
+    # end-to-end: every step also reads the rank's new positions back to pinned host memory
+    esz = 8 if args.dtype == "float64" else 4
+    h_out = torch.empty((int(n_own * 1.2) + 1024, d), dtype=tdt).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        dr.step()
+        cur = dr.window[:, -1]
+        h_out[:cur.shape[0]].copy_(cur, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+        cnt = torch.tensor([float(launches), float(dr.window.shape[0])], device=dev, dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        launches, owned_total = int(cnt[0].item()), int(cnt[1].item())
+    else:
+        owned_total = dr.window.shape[0]
+    if rank == 0:
+        assert owned_total == n_total, "particles lost in migration"
+        peaks, peak_kind = measured_peaks()
+        edge_ms_avg = kms[0] / max(kl[0], 1)
+        alg_bytes = EDGE_BYTES * n_edges + NODE_BYTES * n_own
+        achieved = alg_bytes / (edge_ms_avg * 1e-3) / 1e9 if edge_ms_avg > 0 else 0.0
+        line = {
+            "metric": METRIC.replace("LDC-3D", args.workload), "value": n_total * K / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "particles": n_total, "particles_rank0": n_own,
+                       "edges_rank0": n_edges, "ghosts_rank0": dr.n_ghost_left + dr.n_ghost_right,
+                       "mp_steps": MP_STEPS, "latent": 128, "positions": args.dtype,
+                       "multi_gpu": f"slab decomposition along axis {dr.axis}, halo exchange of P per MP step (NCCL)",
+                       "halo_bytes_per_step_rank0": halo_bytes // max(K, 1),
+                       "l2": "inputs larger than L2 (edge latents %.0f MB per rank)" % (n_edges * 512 / 1e6)},
+            "roofline": {"bound": "hbm", "kernel": "edge_mp_tc_kernel (rank 0)", "achieved": achieved,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": None, "peak_source": peak_kind, "avg_launch_ms": edge_ms_avg,
+                         "launches": int(kl[0]), "share_of_step": kms[0] / ms,
+                         "node_kernel_share_of_step": kms[1] / ms},
+            "e2e": {"value": n_total * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": n_total * d * esz},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -344,10 +456,15 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=12000, help="particles in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded", action="store_true",
+                    help="shard ONE periodic cloud over the GPUs (slab decomposition, strong scaling) "
+                         "instead of one replica per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.sharded:
+        run_sharded(args)
     else:
         run_ours(args)
 

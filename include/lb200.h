@@ -47,7 +47,8 @@ typedef struct {
   int32_t n;               /* particles */
   int32_t dim;             /* 2 or 3 */
   int32_t pos_f64;         /* 0: float positions, 1: double positions */
-  int32_t periodic;        /* case.py:104-108: periodic in all dims, or free */
+  int32_t periodic;        /* bit k set: dimension k is periodic.  The reference is all-or-none
+                              (case.py:104-108); a slab of a decomposed domain is open along its cut axis */
   double box[3];
   double r_cutoff;
   int32_t use_cells;       /* out of lb200_grid_init: 1 cell list, 0 all-pairs */
@@ -162,10 +163,22 @@ typedef struct {
   const lb200_mlp_off* proc_node; /* host array [num_mp_steps] */
   int32_t edge_impl;        /* 0: tcgen05 tensor-core message kernel (product path);
                                1: fp32 CUDA-core kernel (kept as the numerical cross-check) */
+  /* Domain decomposition (0 / NULL on a single GPU): rows [0, n_owned) of the node arrays are
+   * this rank's particles, rows [n_owned, n) are ghosts whose projections P arrive from the
+   * neighbouring ranks.  Node kernels run over owned rows, edge kernels over edges whose
+   * receiver is owned.  halo_fn(halo_ctx, m) is called on the host after the node projections
+   * feeding message-passing step m have been enqueued (m = 0 .. num_mp_steps-1): it must enqueue,
+   * on the same stream, the exchange that fills the ghost rows of P (lb200_gns_scratch_layout). */
+  int32_t n_owned;
+  void (*halo_fn)(void* ctx, int32_t mp_step);
+  void* halo_ctx;
 } lb200_gns_cfg;
 
 /* device scratch the forward needs, in bytes (node latents, projections, edge latents ...) */
 int64_t lb200_gns_scratch_bytes(int32_t n, int32_t e_cap);
+/* byte offsets inside that scratch of h [n][128], P [n][256], agg [n][128], e [e_cap][128] */
+int lb200_gns_scratch_layout(int32_t n, int32_t e_cap, int64_t* off_h, int64_t* off_p, int64_t* off_agg,
+                             int64_t* off_e);
 
 /*
  *   node_feat, edge_feat  as produced by lb200_features (edge_feat in LIST order)

@@ -46,7 +46,10 @@ class GnsCfg(C.Structure):
                 ("node_stride", C.c_int32), ("embed_size", C.c_int32), ("num_particle_types", C.c_int32),
                 ("e_cap", C.c_int32), ("embedding", C.c_int64), ("enc_node", MlpOff), ("enc_edge", MlpOff),
                 ("dec", MlpOff), ("proc_edge", C.POINTER(MlpOff)), ("proc_node", C.POINTER(MlpOff)),
-                ("edge_impl", C.c_int32)]
+                ("edge_impl", C.c_int32), ("n_owned", C.c_int32), ("halo_fn", C.c_void_p), ("halo_ctx", C.c_void_p)]
+
+
+HALO_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int32)
 
 
 class IntegrateCfg(C.Structure):
@@ -72,6 +75,7 @@ _SIGNATURES = {
     "lb200_node_feature_width": (_I32, [C.POINTER(FeatureCfg)]),
     "lb200_features": (C.c_int, [C.POINTER(FeatureCfg), _VP, _VP, _VP, _I32, _VP, _VP, _VP]),
     "lb200_gns_scratch_bytes": (_I64, [_I32, _I32]),
+    "lb200_gns_scratch_layout": (C.c_int, [_I32, _I32, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "lb200_gns_forward": (C.c_int, [C.POINTER(GnsCfg), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP]),
     "lb200_integrate": (C.c_int, [C.POINTER(IntegrateCfg), _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "lb200_rollout_scratch_bytes": (_I64, [C.POINTER(RolloutCfg)]),

@@ -40,6 +40,13 @@ class PiecewiseForce:
         return torch.where((r[..., self.axis] > self.threshold)[..., None], hi, lo)
 
 
+def periodic_mask(periodic, dim):
+    """bool (the reference's all-or-none) or an explicit per-dimension bit mask -> bit mask."""
+    if isinstance(periodic, bool):
+        return (1 << dim) - 1 if periodic else 0
+    return int(periodic)
+
+
 class FeatureDict(dict):
     """The reference's ``FeatureDict`` (``features.py:10``) plus a handle on the packed
     device buffers the arrays are views of, so the model does not re-pack them."""
@@ -84,7 +91,8 @@ class _NeighborFn:
         self.box = [float(b) for b in box]
         self.dim = len(self.box)
         self.r_cutoff = float(r_cutoff)
-        self.periodic = bool(periodic)
+        # bit k: dimension k is periodic; the reference is all-or-none (case.py:104-108)
+        self.periodic = periodic_mask(periodic, self.dim)
         self.multiplier = float(multiplier)
         self.tdtype = tdtype
 
@@ -235,7 +243,7 @@ def case_builder(box, metadata, input_seq_length, cfg_neighbors=None, cfg_model=
     def feature_cfg(n):
         fc = _cabi.FeatureCfg()
         fc.n, fc.dim, fc.t_window = n, dim, isl
-        fc.pos_f64, fc.periodic = int(tdtype == torch.float64), int(periodic)
+        fc.pos_f64, fc.periodic = int(tdtype == torch.float64), periodic_mask(periodic, dim)
         fc.box = _cabi.vec3(box, 1.0)
         fc.r_cutoff = radius
         fc.vel_mean = _cabi.vec3(stats["velocity"]["mean"])
@@ -256,7 +264,7 @@ def case_builder(box, metadata, input_seq_length, cfg_neighbors=None, cfg_model=
     def integrate_cfg(n, t_window, out_mode):
         ic = _cabi.IntegrateCfg()
         ic.n, ic.dim, ic.t_window = n, dim, t_window
-        ic.pos_f64, ic.periodic, ic.out_mode = int(tdtype == torch.float64), int(periodic), out_mode
+        ic.pos_f64, ic.periodic, ic.out_mode = int(tdtype == torch.float64), periodic_mask(periodic, dim), out_mode
         ic.box = _cabi.vec3(box, 1.0)
         key = "velocity" if out_mode == 1 else "acceleration"
         ic.mean = _cabi.vec3(stats[key]["mean"])

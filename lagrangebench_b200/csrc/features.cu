@@ -19,7 +19,6 @@ __global__ void node_feature_kernel(FeatDev c, const T* __restrict__ window, con
                                     float* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
-  const bool per = c.periodic != 0;
   T side[DIM], half[DIM], vm[DIM], vs[DIM];
 #pragma unroll
   for (int k = 0; k < DIM; ++k) {
@@ -40,7 +39,7 @@ __global__ void node_feature_kernel(FeatDev c, const T* __restrict__ window, con
 #pragma unroll
     for (int k = 0; k < DIM; ++k) {
       cur[k] = w[(t + 1) * DIM + k];
-      T v = disp1(cur[k], prev[k], side[k], half[k], per);
+      T v = disp1(cur[k], prev[k], side[k], half[k], ((c.periodic >> k) & 1) != 0);
       T nv = div_rn(sub_rn(v, vm[k]), vs[k]);
       o[t * DIM + k] = (float)nv;
       ss = k == 0 ? mul_rn(nv, nv) : add_rn(ss, mul_rn(nv, nv));
@@ -81,7 +80,6 @@ __global__ void edge_feature_kernel(FeatDev c, const T* __restrict__ window, con
                                     int e_cap, float4* __restrict__ out) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= e_cap) return;
-  const bool per = c.periodic != 0;
   int r = min(idx[e], c.n - 1), s = min(idx[e_cap + e], c.n - 1);  // JAX gathers clamp the pad index
   r = max(r, 0);
   s = max(s, 0);
@@ -93,7 +91,7 @@ __global__ void edge_feature_kernel(FeatDev c, const T* __restrict__ window, con
 #pragma unroll
   for (int k = 0; k < DIM; ++k) {
     T side = (T)c.box[k];
-    T d = disp1(pr[k], ps[k], side, mul_rn(side, T(0.5)), per);
+    T d = disp1(pr[k], ps[k], side, mul_rn(side, T(0.5)), ((c.periodic >> k) & 1) != 0);
     T nd = div_rn(d, radius);
     f[k] = (float)nd;
     ss = k == 0 ? mul_rn(nd, nd) : add_rn(ss, mul_rn(nd, nd));
@@ -114,7 +112,6 @@ __global__ void integrate_kernel(IntegDev c, const float* __restrict__ net_out, 
   if (skip != nullptr && *skip != 0) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
-  const bool per = c.periodic != 0;
   T* w = window + (int64_t)i * c.tw * DIM;
   T np[DIM];
   int pt = ptype[i];
@@ -123,6 +120,7 @@ __global__ void integrate_kernel(IntegDev c, const float* __restrict__ net_out, 
   for (int k = 0; k < DIM; ++k) {
     T side = (T)c.box[k];
     T half = mul_rn(side, T(0.5));
+    const bool per = ((c.periodic >> k) & 1) != 0;
     T last = w[(c.tw - 1) * DIM + k];
     T x = (T)net_out[(int64_t)i * DIM + k];
     T res;
@@ -173,8 +171,8 @@ extern "C" int32_t lb200_node_feature_width(const lb200_feature_cfg* c) {
 extern "C" int lb200_features(const lb200_feature_cfg* c, const void* window_dev, const float* force_dev,
                               const int32_t* idx_dev, int32_t e_cap, float* node_feat_dev, float* edge_feat_dev,
                               void* stream) {
-  if (!c || !window_dev || (c->dim != 2 && c->dim != 3) || c->t_window < 2) return LB200_EINVAL;
-  if (c->node_stride < lb200_node_feature_width(c)) return LB200_EINVAL;
+  if (!c || !window_dev || (c->dim != 2 && c->dim != 3) || c->t_window < 1) return LB200_EINVAL;
+  if (node_feat_dev && (c->t_window < 2 || c->node_stride < lb200_node_feature_width(c))) return LB200_EINVAL;
   if (c->force_mode == 2 && !force_dev) return LB200_EINVAL;
   FeatDev d;
   d.n = c->n;

@@ -541,6 +541,20 @@ extern "C" int64_t lb200_gns_scratch_bytes(int32_t n, int32_t e_cap) {
   return b + 4096;
 }
 
+extern "C" int lb200_gns_scratch_layout(int32_t n, int32_t e_cap, int64_t* off_h, int64_t* off_p, int64_t* off_agg,
+                                        int64_t* off_e) {
+  Arena ar(nullptr, 0);
+  float* h = ar.take<float>((int64_t)n * kLatent);
+  float* P = ar.take<float>((int64_t)n * 2 * kLatent);
+  float* agg = ar.take<float>((int64_t)n * kLatent);
+  float* e = ar.take<float>((int64_t)e_cap * kLatent);
+  if (off_h) *off_h = (char*)h - (char*)nullptr;
+  if (off_p) *off_p = (char*)P - (char*)nullptr;
+  if (off_agg) *off_agg = (char*)agg - (char*)nullptr;
+  if (off_e) *off_e = (char*)e - (char*)nullptr;
+  return 0;
+}
+
 extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_dev, const float* node_feat_dev,
                                  const float* edge_feat_dev, const int32_t* ptype_dev, const int32_t* rowptr_dev,
                                  const int32_t* perm_dev, const int32_t* snd_dev, const int32_t* rcv_dev,
@@ -554,6 +568,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const int n = c->n, e_cap = c->e_cap;
+  const int n_own = c->n_owned > 0 ? c->n_owned : n;  // rows [n_own, n) are ghosts (halo exchange)
   const int nt = cdiv(e_cap, kTM);             // CUDA-core edge tiles
   const int n_sub = cdiv(e_cap, kEdgeTile);    // carry sub-tiles
   Arena ar(scratch_dev, scratch_bytes);
@@ -567,7 +582,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   const float* w = weights_dev;
 
   NodeEncArgs ne;
-  ne.n = n;
+  ne.n = n_own;
   ne.node_in = c->node_in;
   ne.node_stride = c->node_stride;
   ne.embed = c->embed_size;
@@ -579,10 +594,10 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   ne.nxt = mlp_ptrs(w, c->proc_edge[0]);
   ne.h = h;
   ne.P = P;
-  { node_encoder_kernel<<<cdiv(n, kTM), kThreads, kSmemNodeEnc, s>>>(ne); LB_LAUNCHED(1); }
+  { node_encoder_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeEnc, s>>>(ne); LB_LAUNCHED(1); }
 
   EdgeEncArgs ee;
-  ee.n = n;
+  ee.n = n_own;
   ee.rowptr = rowptr_dev;
   ee.perm = perm_dev;
   ee.edge_feat = reinterpret_cast<const float4*>(edge_feat_dev);
@@ -591,11 +606,12 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   { edge_encoder_kernel<<<nt, kThreads, kSmemEdgeEnc, s>>>(ee); LB_LAUNCHED(1); }
 
   for (int m = 0; m < c->num_mp_steps; ++m) {
+    if (c->halo_fn) c->halo_fn(c->halo_ctx, m);  // ghost rows of P for this step (enqueued on `s`)
     const lb200_mlp_off& eo = c->proc_edge[m];
     prof_begin(0, s);
     if (c->edge_impl == 0 && eo.tc_w >= 0 && eo.tc_vec >= 0) {
       EdgeTcArgs et;
-      et.n = n;
+      et.n = n_own;
       et.rowptr = rowptr_dev;
       et.snd = snd_dev;
       et.rcv = rcv_dev;
@@ -610,7 +626,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       if (rc) return rc;
     } else {
       EdgeMpArgs em;
-      em.n = n;
+      em.n = n_own;
       em.rowptr = rowptr_dev;
       em.snd = snd_dev;
       em.rcv = rcv_dev;
@@ -625,7 +641,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     prof_end(0, s);
 
     NodeMpArgs nm;
-    nm.n = n;
+    nm.n = n_own;
     nm.dim = c->dim;
     nm.last = m == c->num_mp_steps - 1;
     nm.rowptr = rowptr_dev;
@@ -638,7 +654,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     nm.P = P;
     nm.out = out_dev;
     prof_begin(1, s);
-    { node_mp_kernel<<<cdiv(n, kTM), kThreads, kSmemNodeMp, s>>>(nm); LB_LAUNCHED(1); }
+    { node_mp_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeMp, s>>>(nm); LB_LAUNCHED(1); }
     prof_end(1, s);
   }
   LB_LAUNCH_CHECK();

@@ -121,11 +121,11 @@ struct GridDev {
 template <typename T>
 struct Geo {  // per-thread typed copy of the geometry
   T side[3], half[3], cs[3], cutoff_sq;
-  bool periodic;
+  bool periodic[3];  // bit k of the mask: dimension k wraps
   __device__ Geo(const GridDev& g) {
-    periodic = g.periodic != 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
+      periodic[k] = ((g.periodic >> k) & 1) != 0;
       side[k] = (T)g.box[k];
       half[k] = mul_rn(side[k], T(0.5));
       cs[k] = (T)g.cell_size[k];
@@ -212,11 +212,11 @@ __global__ void gather_sorted_kernel(const T* __restrict__ pos, const int32_t* _
 template <typename T, int DIM>
 __device__ __forceinline__ bool within(const T* pi, const T* pj, const Geo<T>& geo) {
   // metric_sq(position[i], position[j]) = sum(disp(pos_i, pos_j)**2), left to right
-  T d0 = disp1(pi[0], pj[0], geo.side[0], geo.half[0], geo.periodic);
+  T d0 = disp1(pi[0], pj[0], geo.side[0], geo.half[0], geo.periodic[0]);
   T acc = mul_rn(d0, d0);
 #pragma unroll
   for (int k = 1; k < DIM; ++k) {
-    T d = disp1(pi[k], pj[k], geo.side[k], geo.half[k], geo.periodic);
+    T d = disp1(pi[k], pj[k], geo.side[k], geo.half[k], geo.periodic[k]);
     acc = add_rn(acc, mul_rn(d, d));
   }
   return acc < geo.cutoff_sq;
@@ -493,7 +493,7 @@ extern "C" int lb200_grid_init(lb200_grid* g, int32_t n, int32_t dim, int32_t po
   g->n = n;
   g->dim = dim;
   g->pos_f64 = pos_f64 ? 1 : 0;
-  g->periodic = periodic ? 1 : 0;
+  g->periodic = periodic;  // bit k: dimension k is periodic (the reference uses all-or-none, case.py:104)
   g->r_cutoff = r_cutoff;
   g->n_cand_cells = dim == 2 ? 9 : 27;
   // jax-md: box = f32(box); use the cell list iff all(cutoff < box / 3)
