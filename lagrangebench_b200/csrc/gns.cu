@@ -640,21 +640,41 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     }
     prof_end(0, s);
 
-    NodeMpArgs nm;
-    nm.n = n_own;
-    nm.dim = c->dim;
-    nm.last = m == c->num_mp_steps - 1;
-    nm.rowptr = rowptr_dev;
-    nm.agg = agg;
-    nm.carry_first = cf;
-    nm.carry_last = cl;
-    nm.mlp = mlp_ptrs(w, c->proc_node[m]);
-    nm.nxt = nm.last ? mlp_ptrs(w, c->dec) : mlp_ptrs(w, c->proc_edge[m + 1]);
-    nm.h = h;
-    nm.P = P;
-    nm.out = out_dev;
+    const lb200_mlp_off& no = c->proc_node[m];
+    const bool last = m == c->num_mp_steps - 1;
     prof_begin(1, s);
-    { node_mp_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeMp, s>>>(nm); LB_LAUNCHED(1); }
+    if (c->edge_impl == 0 && no.tc_w >= 0 && no.tc_vec >= 0) {
+      NodeTcArgs nt_args;
+      nt_args.n = n_own;
+      nt_args.last = last;
+      nt_args.dim = c->dim;
+      nt_args.rowptr = rowptr_dev;
+      nt_args.agg = agg;
+      nt_args.carry_first = cf;
+      nt_args.carry_last = cl;
+      nt_args.w_tc = w + no.tc_w;
+      nt_args.vec_tc = w + no.tc_vec;
+      nt_args.h = h;
+      nt_args.P = P;
+      nt_args.out = out_dev;
+      rc = launch_node_mp_tc(nt_args, s);
+      if (rc) return rc;
+    } else {
+      NodeMpArgs nm;
+      nm.n = n_own;
+      nm.dim = c->dim;
+      nm.last = last;
+      nm.rowptr = rowptr_dev;
+      nm.agg = agg;
+      nm.carry_first = cf;
+      nm.carry_last = cl;
+      nm.mlp = mlp_ptrs(w, no);
+      nm.nxt = last ? mlp_ptrs(w, c->dec) : mlp_ptrs(w, c->proc_edge[m + 1]);
+      nm.h = h;
+      nm.P = P;
+      nm.out = out_dev;
+      { node_mp_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeMp, s>>>(nm); LB_LAUNCHED(1); }
+    }
     prof_end(1, s);
   }
   LB_LAUNCH_CHECK();

@@ -69,14 +69,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo) {
   return d;                                           // layout_type 0 = no swizzle
 }
 
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate,
+                                         uint32_t idesc = kIdesc) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -172,16 +173,19 @@ __device__ __forceinline__ void split_f16(float x, unsigned short& hi, unsigned 
 
 // 3-pass split-precision GEMM: acc_hh = A_hi B_hi ; acc_x = A_hi B_lo + A_lo B_hi   (K = 128)
 __device__ __forceinline__ void issue_gemm(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                           uint32_t acc_hh, uint32_t acc_x) {
+                                           uint32_t acc_hh, uint32_t acc_x, uint32_t idesc = kIdesc,
+                                           bool accumulate = false) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    umma_f16(acc_hh, umma_desc(a_hi + j * 2 * kLboA, kLboA), umma_desc(b_hi + j * 2 * kLboB, kLboB), j > 0);
+    umma_f16(acc_hh, umma_desc(a_hi + j * 2 * kLboA, kLboA), umma_desc(b_hi + j * 2 * kLboB, kLboB),
+             (j > 0 || accumulate) ? 1u : 0u, idesc);
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    umma_f16(acc_x, umma_desc(a_hi + j * 2 * kLboA, kLboA), umma_desc(b_lo + j * 2 * kLboB, kLboB), j > 0);
+    umma_f16(acc_x, umma_desc(a_hi + j * 2 * kLboA, kLboA), umma_desc(b_lo + j * 2 * kLboB, kLboB),
+             (j > 0 || accumulate) ? 1u : 0u, idesc);
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    umma_f16(acc_x, umma_desc(a_lo + j * 2 * kLboA, kLboA), umma_desc(b_hi + j * 2 * kLboB, kLboB), 1);
+    umma_f16(acc_x, umma_desc(a_lo + j * 2 * kLboA, kLboA), umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
 }
 
 // lane l ends with the sum over the warp's 32 lanes of v[l]   (31 shuffles, fixed order)
@@ -449,6 +453,289 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
   }
 }
 
+// =====================================================================================
+// Node update on the tensor cores (replaces update_node_fn + residual of gns.py:103-122 and
+// the projection of the next step's first edge layer / the decoder of gns.py:126-133).
+//
+// One persistent CTA (512 threads) per 128-node tile; GEMMs transposed as in the edge kernel
+// (TMEM lane = feature, column = node).  The node tile stays resident in shared memory as
+// hi/lo fp16 operands while the five 128x128 weight operands of the step (64 KB each, hi|lo)
+// are streamed through one shared-memory buffer by cp.async.bulk:
+//   W1[0:128] (acts on h), W1[128:256] (acts on the aggregate), W2c (LayerNorm mean folded in),
+//   then either the two halves of the next step's edge W1 (-> P) or the decoder's first layer.
+constexpr int kNtThreads = 512;
+constexpr int kNtTile = 128;
+constexpr uint32_t kIdescN128 = (1u << 4) | ((uint32_t)(kNtTile >> 3) << 17) | (8u << 24);
+constexpr uint32_t kNOffW = 0;                          // streamed weight operand: hi | lo
+constexpr uint32_t kNOffBh = kNOffW + 2 * kWBytes;      // h (later h_new) operand: hi | lo
+constexpr uint32_t kNOffBa = kNOffBh + 2 * kBBytes;     // aggregate (later hidden) operand: hi | lo
+constexpr uint32_t kNOffVec = kNOffBa + 2 * kBBytes;    // b1 | b2c | ln_scale | ln_offset | b_next | wd1[128*3] | bd1[4]
+constexpr uint32_t kNVecFloats = 5 * 128 + 3 * 128 + 4;
+constexpr uint32_t kNOffRed = kNOffVec + ((kNVecFloats * 4 + 15) / 16) * 16;  // red[4 groups][4 warps][32] x 3
+constexpr uint32_t kNOffInv = kNOffRed + 3 * 4 * 4 * 32 * 4;                   // inv[16 warps][32]
+constexpr uint32_t kNOffBar = kNOffInv + 16 * 32 * 4;
+constexpr uint32_t kSmemNodeTc = kNOffBar + 48;
+
+__global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3;    // TMEM lane quarter
+  const int g = warp >> 2;   // 32-node column group of the tile this warp finishes
+  const int f = q * 32 + lane;
+  float* vec = reinterpret_cast<float*>(smem + kNOffVec);
+  float* red = reinterpret_cast<float*>(smem + kNOffRed) + g * 128;
+  float* invs = reinterpret_cast<float*>(smem + kNOffInv) + warp * 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kNOffBar + 32);
+  const uint32_t bar_w = sbase + kNOffBar, bar_mma = sbase + kNOffBar + 8, bar_mid = sbase + kNOffBar + 16;
+  const uint32_t bar_group = 1 + g;
+  const int n_tiles = (a.n + kNtTile - 1) / kNtTile;
+  if ((int)blockIdx.x >= n_tiles) return;
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    mbar_init(bar_mid, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < (int)kNVecFloats; i += kNtThreads) vec[i] = a.vec_tc[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t acc_hh = tmem, acc_x = tmem + 128;
+  const float b1 = vec[f], b2c = vec[128 + f], ln_scale = vec[256 + f], ln_offset = vec[384 + f], b_next = vec[512 + f];
+
+  const uint32_t w_hi = sbase + kNOffW, w_lo = w_hi + kWBytes;
+  const uint32_t bh_hi = sbase + kNOffBh, bh_lo = bh_hi + kBBytes;
+  const uint32_t ba_hi = sbase + kNOffBa, ba_lo = ba_hi + kBBytes;
+  unsigned char* bh_hi_p = smem + kNOffBh;
+  unsigned char* bh_lo_p = bh_hi_p + kBBytes;
+  unsigned char* ba_hi_p = smem + kNOffBa;
+  unsigned char* ba_lo_p = ba_hi_p + kBBytes;
+  const uint32_t t_addr = ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32);
+  const uint32_t elem_off = (uint32_t)(f >> 3) * kLboB + (uint32_t)(f & 7) * 2 + (uint32_t)(g * 32) * 16;
+  const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(a.w_tc);
+  uint32_t ph_w = 0, ph_mma = 0, ph_mid = 0;  // ph_w / ph_mid are only used by thread 0
+
+  auto load_w = [&](int k) {  // thread 0: stream weight operand k (hi|lo, 64 KB) into the buffer
+    mbar_expect_tx(bar_w, 2 * kWBytes);
+    bulk_g2s(w_hi, wsrc + (size_t)k * 2 * kWBytes, 2 * kWBytes, bar_w);
+  };
+  auto wait_w = [&]() {
+    mbar_wait(bar_w, ph_w);
+    ph_w ^= 1;
+  };
+  auto wait_all = [&]() {  // every thread: the MMAs committed to bar_mma are done
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tc_fence_after();
+  };
+  // split a float and store it as this thread's element (k = f) of operand row `col` (its column group)
+  auto put_elem = [&](unsigned char* hi_p, unsigned char* lo_p, int col, float v) {
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
+    *reinterpret_cast<__half*>(hi_p + elem_off + (uint32_t)col * 16) = hi;
+    *reinterpret_cast<__half*>(lo_p + elem_off + (uint32_t)col * 16) = lo;
+  };
+  auto put_row4 = [&](unsigned char* hi_p, unsigned char* lo_p, int r, const float4& v) {
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn((v.x - f01.x) * kLoScale, (v.y - f01.y) * kLoScale);
+    const __half2 l23 = __floats2half2_rn((v.z - f23.x) * kLoScale, (v.w - f23.y) * kLoScale);
+    const uint32_t off = (uint32_t)(lane >> 1) * kLboB + (uint32_t)r * 16 + (uint32_t)(lane & 1) * 8;
+    *reinterpret_cast<uint2*>(hi_p + off) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    *reinterpret_cast<uint2*>(lo_p + off) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+  };
+
+  if (tid == 0) load_w(0);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = (int64_t)tile * kNtTile;
+    const int rows = min(kNtTile, a.n - (int)row0);
+    const int valid = min(max(rows - g * 32, 0), 32);  // nodes of this warp's column group that exist
+    // ---- phase 0: h and the aggregate (bucket carries resolved) -> hi/lo operands, 8 rows per warp
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = warp * 8 + i;
+      float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), av = hv;
+      if (r < rows) {
+        const int64_t v = row0 + r;
+        hv = reinterpret_cast<const float4*>(a.h + v * kLatent)[lane];
+        const int e0 = a.rowptr[v], e1 = a.rowptr[v + 1];
+        if (e1 > e0) {
+          const int ta = e0 / kEdgeTile, tb = (e1 - 1) / kEdgeTile;
+          if (ta == tb) {
+            av = reinterpret_cast<const float4*>(a.agg + v * kLatent)[lane];
+          } else {  // bucket straddles carry sub-tiles: partial sums in slot order
+            av = reinterpret_cast<const float4*>(a.carry_last + (int64_t)ta * kLatent)[lane];
+            for (int t = ta + 1; t <= tb; ++t) {
+              const float4 p = reinterpret_cast<const float4*>(a.carry_first + (int64_t)t * kLatent)[lane];
+              av.x += p.x; av.y += p.y; av.z += p.z; av.w += p.w;
+            }
+          }
+        }
+      }
+      put_row4(bh_hi_p, bh_lo_p, r, hv);
+      put_row4(ba_hi_p, ba_lo_p, r, av);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 1: acc = W1h^T h + W1a^T agg   (two streamed operands)
+    if (tid == 0) {
+      tc_fence_after();
+      wait_w();
+      issue_gemm(w_hi, w_lo, bh_hi, bh_lo, acc_hh, acc_x, kIdescN128, false);
+      umma_commit(bar_mid);
+      mbar_wait(bar_mid, ph_mid);
+      ph_mid ^= 1;
+      load_w(1);
+      wait_w();
+      tc_fence_after();
+      issue_gemm(w_hi, w_lo, ba_hi, ba_lo, acc_hh, acc_x, kIdescN128, true);
+      umma_commit(bar_mma);
+    }
+    wait_all();
+    if (tid == 0) load_w(2);  // W2c streams in while the hidden layer is written
+    // hidden = relu(acc + b1) -> operand (over the aggregate, which is no longer needed)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float hh[16], xx[16];
+      tmem_ld_pair16(acc_hh + t_addr + hf * 16, acc_x + t_addr + hf * 16, hh, xx);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) put_elem(ba_hi_p, ba_lo_p, hf * 16 + j, fmaxf(fmaf(xx[j], kLoInv, hh[j]) + b1, 0.f));
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 2 (+ LayerNorm, residual)
+    if (tid == 0) {
+      tc_fence_after();
+      wait_w();
+      issue_gemm(w_hi, w_lo, ba_hi, ba_lo, acc_hh, acc_x, kIdescN128, false);
+      umma_commit(bar_mma);
+    }
+    float* const hrow = a.h + (row0 + g * 32) * kLatent + f;
+    float hold[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) hold[j] = j < valid ? hrow[(int64_t)j * kLatent] : 0.f;
+    wait_all();
+    if (tid == 0) load_w(3);
+    {
+      float yc[32];
+      float part;
+      {
+        float sq[32];
+        tmem_ld_pair(acc_hh + t_addr, acc_x + t_addr, yc, sq);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          yc[j] = fmaf(sq[j], kLoInv, yc[j]) + b2c;
+          sq[j] = yc[j] * yc[j];
+        }
+        part = warp_transpose_reduce(sq);
+      }
+      red[q * 32 + lane] = part;
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_group) : "memory");
+      {
+        const float var = (red[lane] + red[32 + lane] + red[64 + lane] + red[96 + lane]) * (1.0f / kLatent);
+        invs[lane] = 1.0f / sqrtf(var + 1e-5f);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        const float4 inv4 = *reinterpret_cast<const float4*>(invs + j4);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int j = j4 + t;
+          const float inv = t == 0 ? inv4.x : (t == 1 ? inv4.y : (t == 2 ? inv4.z : inv4.w));
+          const float hnew = fmaf(ln_scale * inv, yc[j], ln_offset) + hold[j];  // residual (gns.py:120-122)
+          if (!a.last && j < valid) hrow[(int64_t)j * kLatent] = hnew;
+          put_elem(bh_hi_p, bh_lo_p, j, j < valid ? hnew : 0.f);
+        }
+      }
+      __syncwarp();
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- next step's sender projection P[:, 0:128], or the decoder's hidden layer
+    if (tid == 0) {
+      tc_fence_after();
+      wait_w();
+      issue_gemm(w_hi, w_lo, bh_hi, bh_lo, acc_hh, acc_x, kIdescN128, false);
+      umma_commit(bar_mma);
+    }
+    wait_all();
+    if (!a.last) {
+      if (tid == 0) load_w(4);
+      float* const prow = a.P + (row0 + g * 32) * (2 * kLatent) + f;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float hh[16], xx[16];
+        tmem_ld_pair16(acc_hh + t_addr + hf * 16, acc_x + t_addr + hf * 16, hh, xx);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (hf * 16 + j < valid) prow[(int64_t)(hf * 16 + j) * (2 * kLatent)] = fmaf(xx[j], kLoInv, hh[j]);
+      }
+      tc_fence_before();
+      __syncthreads();  // every warp has drained the accumulators
+      // ---- receiver projection P[:, 128:256] = h W1r + b1(next)
+      if (tid == 0) {
+        tc_fence_after();
+        wait_w();
+        issue_gemm(w_hi, w_lo, bh_hi, bh_lo, acc_hh, acc_x, kIdescN128, false);
+        umma_commit(bar_mma);
+      }
+      wait_all();
+      if (tid == 0 && tile + (int)gridDim.x < n_tiles) load_w(0);  // next tile's first operand
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float hh[16], xx[16];
+        tmem_ld_pair16(acc_hh + t_addr + hf * 16, acc_x + t_addr + hf * 16, hh, xx);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (hf * 16 + j < valid)
+            prow[(int64_t)(hf * 16 + j) * (2 * kLatent) + kLatent] = fmaf(xx[j], kLoInv, hh[j]) + b_next;
+      }
+    } else {
+      if (tid == 0 && tile + (int)gridDim.x < n_tiles) load_w(0);
+      // decoder (gns.py:126-133): out = relu(h Wd0 + bd0) Wd1 + bd1; the reduction over the 128
+      // features runs across threads (31-shuffle transpose-reduce, then the 4 warps of the group)
+      float hid[32];
+      {
+        float xx[32];
+        tmem_ld_pair(acc_hh + t_addr, acc_x + t_addr, hid, xx);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) hid[j] = fmaxf(fmaf(xx[j], kLoInv, hid[j]) + b_next, 0.f);
+      }
+      for (int k = 0; k < a.dim; ++k) {
+        const float wk = vec[640 + f * 3 + k];
+        float t[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] = hid[j] * wk;
+        red[(1 + (k & 1)) * 512 + q * 32 + lane] = warp_transpose_reduce(t);  // red block 1/2 alternate over k
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_group) : "memory");
+        if (q == 0 && lane < valid) {
+          const float* rb = red + (1 + (k & 1)) * 512;
+          a.out[(row0 + g * 32 + lane) * a.dim + k] = rb[lane] + rb[32 + lane] + rb[64 + lane] + rb[96 + lane] + vec[640 + 384 + k];
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // operands and accumulators are free for the next tile
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+  }
+}
+
 static int g_num_sms = 0;
 
 int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
@@ -463,6 +750,22 @@ int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
   const int n_pairs = cdiv(cdiv(e_cap, kTcTile), 2);  // two workers (tiles) per CTA
   const int grid = n_pairs < g_num_sms ? n_pairs : g_num_sms;
   { edge_mp_tc_kernel<<<grid, kTcThreads, kSmemTc, s>>>(a); LB_LAUNCHED(1); }
+  return 0;
+}
+
+int launch_node_mp_tc(const NodeTcArgs& a, cudaStream_t s) {
+  static int attr_rc = -1;
+  static int sms = 0;
+  if (attr_rc < 0) {
+    attr_rc = (int)cudaFuncSetAttribute(node_mp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNodeTc);
+    int dev = 0;
+    if (attr_rc == 0) attr_rc = (int)cudaGetDevice(&dev);
+    if (attr_rc == 0) attr_rc = (int)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (attr_rc) return attr_rc;
+  const int n_tiles = cdiv(a.n, kNtTile);
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  { node_mp_tc_kernel<<<grid, kNtThreads, kSmemNodeTc, s>>>(a); LB_LAUNCHED(1); }
   return 0;
 }
 

@@ -16,4 +16,17 @@ struct EdgeTcArgs {
 
 int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s);
 
+struct NodeTcArgs {
+  int n;     // owned nodes
+  int last;  // last message-passing step: decoder instead of the next step's projections
+  int dim;
+  const int32_t* rowptr;
+  const float *agg, *carry_first, *carry_last;
+  const void* w_tc;     // 5 (4 when last) streamed operands, each hi|lo = 64 KB, UMMA K-major layout
+  const float* vec_tc;  // b1 | b2c | ln_scale | ln_offset | b_next | wd1[128][3] | bd1[4]
+  float *h, *P, *out;
+};
+
+int launch_node_mp_tc(const NodeTcArgs& a, cudaStream_t s);
+
 }  // namespace lb

@@ -94,6 +94,36 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
         o.tc_w = put(halves.view(np.float32))
         o.tc_vec = put(np.concatenate([b2c, np.asarray(ln["scale"], np.float32), np.asarray(ln["offset"], np.float32)]))
 
+    def put_tc_node(mods, nxt_l0, o, last):
+        """Tensor-core operands of a processor node MLP: five (four when ``last``) streamed
+        128x128 operands hi|lo -- W1[0:128]^T, W1[128:256]^T, W2c^T, then the two halves of the
+        next edge MLP's first layer (-> P) or the decoder's first layer -- and the vector block
+        b1 | b2c | ln_scale | ln_offset | b_next | wd1[128][3] | bd1[4] (csrc/gns_tc.cu)."""
+        l0, l1, ln = mods
+        w1 = np.asarray(l0["w"], dtype=np.float32)
+        w2 = np.asarray(l1["w"], dtype=np.float64)
+        b2 = np.asarray(l1["b"], dtype=np.float64)
+        w2c_t = (w2 - w2.mean(axis=1, keepdims=True)).astype(np.float32).T
+        b2c = (b2 - b2.mean()).astype(np.float32)
+        wn = np.asarray(nxt_l0["w"], dtype=np.float32)
+        mats = [w1[:latent].T, w1[latent:2 * latent].T, w2c_t, wn[:latent].T]
+        if not last:
+            mats.append(wn[latent:2 * latent].T)
+        halves = []
+        for m in mats:
+            hi, lo = umma_operand(m)
+            halves += [hi, lo]
+        o.tc_w = put(np.concatenate(halves).view(np.float32))
+        wd1 = np.zeros((latent, 3), np.float32)
+        bd1 = np.zeros(4, np.float32)
+        if last:
+            dl1 = _mlp_modules(params, "_decoder", 0, layer_norm=False)[1]
+            wd1[:, :dim] = np.asarray(dl1["w"], np.float32)
+            bd1[:dim] = np.asarray(dl1["b"], np.float32)
+        o.tc_vec = put(np.concatenate([np.asarray(l0["b"], np.float32), b2c, np.asarray(ln["scale"], np.float32),
+                                       np.asarray(ln["offset"], np.float32), np.asarray(nxt_l0["b"], np.float32),
+                                       wd1.reshape(-1), bd1]))
+
     def put_mlp(mods, in_rows, out_cols, rows_pad=None):
         l0, l1, ln = mods
         w0, w1 = np.asarray(l0["w"]), np.asarray(l1["w"])
@@ -133,7 +163,13 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
         oe = put_mlp(mods, 3 * latent, latent)
         put_tc_edge(mods, oe)
         proc_edge[m] = oe
-        proc_node[m] = put_mlp(_mlp_modules(params, "_processor", 2 * m + 1), 2 * latent, latent)
+        nmods = _mlp_modules(params, "_processor", 2 * m + 1)
+        on = put_mlp(nmods, 2 * latent, latent)
+        last = m == num_mp_steps - 1
+        nxt = (_mlp_modules(params, "_decoder", 0, layer_norm=False) if last
+               else _mlp_modules(params, "_processor", 2 * m + 2))[0]
+        put_tc_node(nmods, nxt, on, last)
+        proc_node[m] = on
     dec = put_mlp(_mlp_modules(params, "_decoder", 0, layer_norm=False), latent, dim)
     blob = torch.from_numpy(np.concatenate(chunks)).to(device)
     return PackedParams(blob, embedding, enc_node, enc_edge, dec, proc_edge, proc_node, node_in_total, embed_size,
