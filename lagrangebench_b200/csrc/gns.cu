@@ -596,14 +596,36 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   ne.P = P;
   { node_encoder_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeEnc, s>>>(ne); LB_LAUNCHED(1); }
 
-  EdgeEncArgs ee;
-  ee.n = n_own;
-  ee.rowptr = rowptr_dev;
-  ee.perm = perm_dev;
-  ee.edge_feat = reinterpret_cast<const float4*>(edge_feat_dev);
-  ee.enc = mlp_ptrs(w, c->enc_edge);
-  ee.e = e;
-  { edge_encoder_kernel<<<nt, kThreads, kSmemEdgeEnc, s>>>(ee); LB_LAUNCHED(1); }
+  if (c->edge_impl == 0 && c->enc_edge.tc_w >= 0 && c->enc_edge.tc_vec >= 0 &&
+      c->enc_edge.b0 == c->enc_edge.w0 + 4 * kLatent) {
+    EdgeTcArgs et;
+    et.n = n_own;
+    et.rowptr = rowptr_dev;
+    et.snd = snd_dev;
+    et.rcv = rcv_dev;
+    et.P = nullptr;
+    et.w_tc = w + c->enc_edge.tc_w;
+    et.vec_tc = w + c->enc_edge.tc_vec;
+    et.e = e;
+    et.agg = nullptr;
+    et.carry_first = nullptr;
+    et.carry_last = nullptr;
+    et.encoder = 1;
+    et.edge_feat = reinterpret_cast<const float4*>(edge_feat_dev);
+    et.perm = perm_dev;
+    et.enc_vec = w + c->enc_edge.w0;
+    rc = launch_edge_mp_tc(et, e_cap, s);
+    if (rc) return rc;
+  } else {
+    EdgeEncArgs ee;
+    ee.n = n_own;
+    ee.rowptr = rowptr_dev;
+    ee.perm = perm_dev;
+    ee.edge_feat = reinterpret_cast<const float4*>(edge_feat_dev);
+    ee.enc = mlp_ptrs(w, c->enc_edge);
+    ee.e = e;
+    { edge_encoder_kernel<<<nt, kThreads, kSmemEdgeEnc, s>>>(ee); LB_LAUNCHED(1); }
+  }
 
   for (int m = 0; m < c->num_mp_steps; ++m) {
     if (c->halo_fn) c->halo_fn(c->halo_ctx, m);  // ghost rows of P for this step (enqueued on `s`)
@@ -622,6 +644,10 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       et.agg = agg;
       et.carry_first = cf;
       et.carry_last = cl;
+      et.encoder = 0;
+      et.edge_feat = nullptr;
+      et.perm = nullptr;
+      et.enc_vec = nullptr;
       rc = launch_edge_mp_tc(et, e_cap, s);
       if (rc) return rc;
     } else {

@@ -204,6 +204,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32]) {
   return v[0];
 }
 
+template <bool kEnc>
 __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -248,12 +249,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
 
   // resident weights: 4 fp16 operands (128 KB) + centred bias, LayerNorm scale / offset
   if (tid == 0) {
-    mbar_expect_tx(bar_w, 4 * kWBytes + 3 * 512);
-    bulk_g2s(sbase + kOffW, a.w_tc, 4 * kWBytes, bar_w);
+    if (kEnc) {  // only the second-layer operand pair, into the W2 slots
+      mbar_expect_tx(bar_w, 2 * kWBytes + 3 * 512);
+      bulk_g2s(sbase + kOffW + 2 * kWBytes, a.w_tc, 2 * kWBytes, bar_w);
+    } else {
+      mbar_expect_tx(bar_w, 4 * kWBytes + 3 * 512);
+      bulk_g2s(sbase + kOffW, a.w_tc, 4 * kWBytes, bar_w);
+    }
     bulk_g2s(sbase + kOffVec, a.vec_tc, 3 * 512, bar_w);
   }
   mbar_wait(bar_w, 0);
   const float b2c = vec[f], ln_scale = vec[128 + f], ln_offset = vec[256 + f];
+  float ew0 = 0.f, ew1 = 0.f, ew2 = 0.f, ew3 = 0.f, eb0 = 0.f;  // encoder first layer, this thread's feature
+  if (kEnc) {
+    ew0 = a.enc_vec[f];
+    ew1 = a.enc_vec[128 + f];
+    ew2 = a.enc_vec[256 + f];
+    ew3 = a.enc_vec[384 + f];
+    eb0 = a.enc_vec[512 + f];
+  }
 
   const uint32_t w1_hi = sbase + kOffW, w1_lo = w1_hi + kWBytes, w2_hi = w1_lo + kWBytes, w2_lo = w2_hi + kWBytes;
   // this worker's 64 operand rows inside every K slab
@@ -281,13 +295,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
   for (int tile = blockIdx.x * 2 + wk; tile < n_tiles; tile += tile_stride) {
     const int64_t slot0 = (int64_t)tile * kTcTile;
     const int rows = min(kTcTile, E - (int)slot0);
-    request_rows(tile);
+    if (!kEnc) request_rows(tile);
     asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");  // previous tile is done with idx / operands
     if (wtid < kTcTile) {
       const bool ok = wtid < rows;
       const int r_here = ok ? a.rcv[slot0 + wtid] : -1;
       const int r_next = (slot0 + wtid + 1 < E) ? a.rcv[slot0 + wtid + 1] : -3;
-      sidx[wtid] = ok ? a.snd[slot0 + wtid] : 0;
+      sidx[wtid] = ok ? (kEnc ? a.perm[slot0 + wtid] : a.snd[slot0 + wtid]) : 0;
       rclamp[wtid] = max(r_here, 0);
       ridx[1 + wtid] = ok ? r_here : (wtid == rows ? -3 : -1);  // -3: "no edge after the tile"
       // last edge of its receiver bucket inside its 32-edge carry sub-tile
@@ -298,6 +312,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
     } else if (wtid == kTcTile) {
       ridx[0] = slot0 > 0 ? a.rcv[slot0 - 1] : -2;
     }
+    if constexpr (kEnc) {
+      // ---- encoder: first layer (K = dim + 1 <= 4) on CUDA cores straight into the layer-2 operand
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");  // sidx (= list positions) visible
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        const float4 ft = a.edge_feat[sidx[c * 32 + j]];
+        float v = ft.x * ew0;
+        v = fmaf(ft.y, ew1, v);
+        v = fmaf(ft.z, ew2, v);
+        v = fmaf(ft.w, ew3, v);
+        const float hval = fmaxf(v + eb0, 0.f);
+        const __half hi = __float2half_rn(hval);
+        const __half lo = __float2half_rn((hval - __half2float(hi)) * kLoScale);
+        *reinterpret_cast<__half*>(b_hi_p + elem_off + (uint32_t)j * 16) = hi;
+        *reinterpret_cast<__half*>(b_lo_p + elem_off + (uint32_t)j * 16) = lo;
+      }
+    } else {
     // ---- phase A: edge latents (already in registers) -> fp16 hi/lo N-side operand
     {
 #pragma unroll
@@ -359,6 +390,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
         }
       }
     }
+    }
     fence_async_smem();
     tc_fence_before();
     asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");
@@ -375,7 +407,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
       const int valid = min(max(rows - col0, 0), 32);  // edges of this chunk that exist
       float* const erow = a.e + (slot0 + col0) * kLatent + f;
       float eold[32];
-      if (valid == 32) {
+      if (kEnc) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) eold[j] = 0.f;
+      } else if (valid == 32) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) eold[j] = erow[(int64_t)j * kLatent];
       } else {
@@ -426,7 +461,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
               if (kFull || j < valid) {
                 erow[(int64_t)j * kLatent] = msg + eold[j];  // residual (gns.py:120-122)
                 seg_sum += msg;
-                if ((emask >> j) & 1u) {  // bucket ends here (uniform across the 4 warps of the chunk)
+                if (!kEnc && ((emask >> j) & 1u)) {  // bucket ends here (uniform across the chunk's 4 warps)
                   float* dst = a.agg + (int64_t)ridx[1 + col0 + j] * kLatent + f;
                   if (j == valid - 1 && last_cont) dst = clast;
                   if (seg_first && first_cont) dst = cfirst;
@@ -741,7 +776,9 @@ static int g_num_sms = 0;
 int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
   static int attr_rc = -1;
   if (attr_rc < 0) {
-    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc);
+    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc);
+    if (attr_rc == 0)
+      attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc);
     int dev = 0;
     if (attr_rc == 0) attr_rc = (int)cudaGetDevice(&dev);
     if (attr_rc == 0) attr_rc = (int)cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -749,7 +786,12 @@ int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
   if (attr_rc) return attr_rc;
   const int n_pairs = cdiv(cdiv(e_cap, kTcTile), 2);  // two workers (tiles) per CTA
   const int grid = n_pairs < g_num_sms ? n_pairs : g_num_sms;
-  { edge_mp_tc_kernel<<<grid, kTcThreads, kSmemTc, s>>>(a); LB_LAUNCHED(1); }
+  if (a.encoder) {
+    edge_mp_tc_kernel<true><<<grid, kTcThreads, kSmemTc, s>>>(a);
+  } else {
+    edge_mp_tc_kernel<false><<<grid, kTcThreads, kSmemTc, s>>>(a);
+  }
+  LB_LAUNCHED(1);
   return 0;
 }
 

@@ -12,6 +12,13 @@ struct EdgeTcArgs {
   const void* w_tc;     // W1e^T hi, lo, W2c^T hi, lo: four 128x128 fp16 operands in UMMA K-major layout
   const float* vec_tc;  // b2c[128] | ln_scale[128] | ln_offset[128]
   float *e, *agg, *carry_first, *carry_last;
+  // encoder mode (gns.py:65-81, edge MLP): e = LN(relu(feat W0 + b0) W1c + b1c); no gather, no
+  // residual, no aggregation.  w_tc then holds only W1c^T hi|lo, vec_tc = b1c | scale | offset,
+  // enc_vec = W0[4][128] | b0[128], edge_feat in LIST order addressed through perm.
+  int encoder;
+  const float4* edge_feat;
+  const int32_t* perm;
+  const float* enc_vec;
 };
 
 int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s);

@@ -94,6 +94,16 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
         o.tc_w = put(halves.view(np.float32))
         o.tc_vec = put(np.concatenate([b2c, np.asarray(ln["scale"], np.float32), np.asarray(ln["offset"], np.float32)]))
 
+    def put_tc_encoder(mods, o):
+        """Tensor-core operands of the edge encoder's second layer: W1c^T hi|lo, b1c|scale|offset."""
+        _, l1, ln = mods
+        w = np.asarray(l1["w"], dtype=np.float64)
+        b = np.asarray(l1["b"], dtype=np.float64)
+        hi, lo = umma_operand((w - w.mean(axis=1, keepdims=True)).astype(np.float32).T)
+        o.tc_w = put(np.concatenate([hi, lo]).view(np.float32))
+        o.tc_vec = put(np.concatenate([(b - b.mean()).astype(np.float32), np.asarray(ln["scale"], np.float32),
+                                       np.asarray(ln["offset"], np.float32)]))
+
     def put_tc_node(mods, nxt_l0, o, last):
         """Tensor-core operands of a processor node MLP: five (four when ``last``) streamed
         128x128 operands hi|lo -- W1[0:128]^T, W1[128:256]^T, W2c^T, then the two halves of the
@@ -156,6 +166,8 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
         raise ValueError(f"edge encoder expects {edge_in} inputs, dim+1 = {dim + 1}")
     enc_node = put_mlp(enc_node_mods, node_in_total, latent, rows_pad=_cabi.MAX_NODE_IN)
     enc_edge = put_mlp(enc_edge_mods, edge_in, latent, rows_pad=4)
+    assert enc_edge.b0 == enc_edge.w0 + 4 * latent  # W0[4][128] | b0[128] contiguous (encoder kernel)
+    put_tc_encoder(enc_edge_mods, enc_edge)
     proc_edge = (_cabi.MlpOff * num_mp_steps)()
     proc_node = (_cabi.MlpOff * num_mp_steps)()
     for m in range(num_mp_steps):
