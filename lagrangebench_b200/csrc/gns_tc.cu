@@ -55,7 +55,8 @@ constexpr uint32_t kIdxInts = 64 + 64 + 68;
 constexpr uint32_t kOffRed = kOffIdx + 2 * kIdxInts * 4;    // per worker: red[2 chunks][4 warps][32]
 constexpr uint32_t kOffInv = kOffRed + 2 * 2 * 4 * 32 * 4;  // inv[16 warps][32]: 1/sqrt(var + eps) per edge
 constexpr uint32_t kOffEnd = kOffInv + 16 * 32 * 4;         // per worker: endmask[2]
-constexpr uint32_t kOffBar = kOffEnd + 16;                  // mbarriers: weights, mma[2]; tmem base
+constexpr uint32_t kOffFeat = kOffEnd + 16;                 // per worker: feat[64] float4 (encoder inputs)
+constexpr uint32_t kOffBar = kOffFeat + 2 * 64 * 16;        // mbarriers: weights, mma[2]; tmem base
 constexpr uint32_t kSmemTc = kOffBar + 48;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -314,10 +315,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
     }
     if constexpr (kEnc) {
       // ---- encoder: first layer (K = dim + 1 <= 4) on CUDA cores straight into the layer-2 operand
-      asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");  // sidx (= list positions) visible
-#pragma unroll 4
+      float4* feat_s = reinterpret_cast<float4*>(smem + kOffFeat) + wk * 64;
+      if (wtid < kTcTile)  // the tile's edge features, gathered once through perm (list order -> slot order)
+        feat_s[wtid] = wtid < rows ? a.edge_feat[a.perm[slot0 + wtid]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");
+#pragma unroll 8
       for (int j = 0; j < 32; ++j) {
-        const float4 ft = a.edge_feat[sidx[c * 32 + j]];
+        const float4 ft = feat_s[c * 32 + j];
         float v = ft.x * ew0;
         v = fmaf(ft.y, ew1, v);
         v = fmaf(ft.z, ew2, v);
