@@ -82,6 +82,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(workload, kernel="edge_mp_tc_kernel"):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    of this workload (profiles/ncu_traffic.json), or None when no capture exists for it."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            table = json.load(f)
+        ent = table.get(workload, {}).get(kernel)
+        return None if ent is None else ent["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def build_workload(name, n_future, seed, dtype_name):
     from lagrangebench_b200 import synthetic
 
@@ -309,9 +322,10 @@ def run_ours(args):
                        if n_edges * 512 > 126e6 else "working set below L2 (edge latents %.0f MB): latency-bound"
                        % (n_edges * 512 / 1e6),
                        "reallocations_in_timed_region": engine.n_reallocations - realloc0},
-            "roofline": {"bound": "hbm", "kernel": "edge_mp_kernel (fused gather + edge MLP + LayerNorm + residual "
-                         "+ segmented sum)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+            "roofline": {"bound": "hbm", "kernel": "edge_mp_tc_kernel (tcgen05: fused gather + edge MLP + LayerNorm "
+                         "+ residual + segmented sum)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(args.workload),
+                         "algorithmic_bytes": alg_bytes, "peak_source": peak_kind,
                          "avg_launch_ms": edge_ms_avg, "launches": int(kl[0]),
                          "share_of_step": kms[0] / ms, "node_kernel_share_of_step": kms[1] / ms,
                          "fp32_tflops": flops_launch / (edge_ms_avg * 1e-3) / 1e12 if edge_ms_avg > 0 else 0.0},
