@@ -270,6 +270,17 @@ def run_ours(args):
     lib.lb200_profile(0)
     n_edges = nbrs.n_edges
     assert torch.isfinite(preds).all(), "rollout diverged"
+    # informational: the same K steps with per-kernel events off, so that lb200_rollout_steps replays
+    # them from a CUDA graph (the API path); reported in config, not as `value`
+    window_g = torch.as_tensor(spec["positions"][:, :6]).to(dev, tdt).contiguous()
+    _, nb_g = engine.run(window_g, ptype, targets_all[:W], W)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    engine.run(window_g, ptype, targets_all[W:W + K], K, nb_g)
+    g1.record()
+    barrier()
+    ms_graph = g0.elapsed_time(g1)
 
     # end-to-end leg: the same steps through the public per-step API with HOST buffers --
     # every step uploads that step's kinematic-target frame from pinned memory and reads the
@@ -321,7 +332,8 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (edge latents %.0f MB)" % (n_edges * 512 / 1e6)
                        if n_edges * 512 > 126e6 else "working set below L2 (edge latents %.0f MB): latency-bound"
                        % (n_edges * 512 / 1e6),
-                       "reallocations_in_timed_region": engine.n_reallocations - realloc0},
+                       "reallocations_in_timed_region": engine.n_reallocations - realloc0,
+                       "ms_per_step_cuda_graph_replay": ms_graph / K},
             "roofline": {"bound": "hbm", "kernel": "edge_mp_tc_kernel (tcgen05: fused gather + edge MLP + LayerNorm "
                          "+ residual + segmented sum)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(args.workload),

@@ -30,6 +30,13 @@ constexpr int kNodeTile = 64;
 extern int64_t g_launches;
 #define LB_LAUNCHED(k) (::lb::g_launches += (k))
 
+bool prof_enabled();
+
+// integrate with the frame of `target` / `pred` selected by a device-side step counter
+int integrate_indexed(const lb200_integrate_cfg* c, const float* out_dev, void* window_dev, const int32_t* ptype_dev,
+                      const void* target_dev, void* pred_out_dev, const int32_t* skip_flag_dev,
+                      const int32_t* step_counter_dev, cudaStream_t s);
+
 // optional CUDA-event timing of a kernel class on its launch stream (lb200_profile)
 void prof_begin(int cls, cudaStream_t s);
 void prof_end(int cls, cudaStream_t s);

@@ -108,10 +108,16 @@ struct IntegDev {
 template <typename T, int DIM>
 __global__ void integrate_kernel(IntegDev c, const float* __restrict__ net_out, T* __restrict__ window,
                                  const int32_t* __restrict__ ptype, const T* __restrict__ target,
-                                 T* __restrict__ pred, const int32_t* __restrict__ skip) {
+                                 T* __restrict__ pred, const int32_t* __restrict__ skip,
+                                 const int32_t* __restrict__ step_counter) {
   if (skip != nullptr && *skip != 0) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
+  if (step_counter != nullptr) {  // device-resident loop: frame index = steps completed so far
+    const int64_t frame = (int64_t)(*step_counter) * c.n * DIM;
+    if (target != nullptr) target += frame;
+    if (pred != nullptr) pred += frame;
+  }
   T* w = window + (int64_t)i * c.tw * DIM;
   T np[DIM];
   int pt = ptype[i];
@@ -203,9 +209,10 @@ extern "C" int lb200_features(const lb200_feature_cfg* c, const void* window_dev
                      : features_t<float, 3>(d, window_dev, force_dev, idx_dev, e_cap, node_feat_dev, edge_feat_dev, s);
 }
 
-extern "C" int lb200_integrate(const lb200_integrate_cfg* c, const float* out_dev, void* window_dev,
-                               const int32_t* ptype_dev, const void* target_dev, void* pred_out_dev,
-                               const int32_t* skip_flag_dev, void* stream) {
+namespace lb {
+int integrate_indexed(const lb200_integrate_cfg* c, const float* out_dev, void* window_dev, const int32_t* ptype_dev,
+                      const void* target_dev, void* pred_out_dev, const int32_t* skip_flag_dev,
+                      const int32_t* step_counter_dev, cudaStream_t s) {
   if (!c || !out_dev || !window_dev || !ptype_dev || (c->dim != 2 && c->dim != 3) || c->t_window < 2)
     return LB200_EINVAL;
   IntegDev d;
@@ -219,12 +226,11 @@ extern "C" int lb200_integrate(const lb200_integrate_cfg* c, const float* out_de
     d.mean[k] = c->mean[k];
     d.std[k] = c->std[k];
   }
-  cudaStream_t s = (cudaStream_t)stream;
   int grid = cdiv(c->n, 128);
 #define LB_INTEG(T, D)                                                                                       \
   do {                                                                                                       \
     integrate_kernel<T, D><<<grid, 128, 0, s>>>(d, out_dev, (T*)window_dev, ptype_dev, (const T*)target_dev, \
-                                                (T*)pred_out_dev, skip_flag_dev);                            \
+                                                (T*)pred_out_dev, skip_flag_dev, step_counter_dev);          \
     LB_LAUNCHED(1);                                                                                          \
   } while (0)
   if (c->pos_f64) {
@@ -235,4 +241,12 @@ extern "C" int lb200_integrate(const lb200_integrate_cfg* c, const float* out_de
 #undef LB_INTEG
   LB_LAUNCH_CHECK();
   return 0;
+}
+}  // namespace lb
+
+extern "C" int lb200_integrate(const lb200_integrate_cfg* c, const float* out_dev, void* window_dev,
+                               const int32_t* ptype_dev, const void* target_dev, void* pred_out_dev,
+                               const int32_t* skip_flag_dev, void* stream) {
+  return lb::integrate_indexed(c, out_dev, window_dev, ptype_dev, target_dev, pred_out_dev, skip_flag_dev, nullptr,
+                               (cudaStream_t)stream);
 }

@@ -2,6 +2,8 @@
 // (lagrangebench/evaluate/rollout.py:125-169) for several consecutive steps, enqueued on one
 // stream with no host round trip.  The reference's blocking overflow read (rollout.py:135)
 // becomes a sticky device flag that turns the remaining integrate steps into no-ops.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -19,6 +21,8 @@ struct ProfState {
   cudaEvent_t pending_start = nullptr;
 };
 static ProfState g_prof;
+
+bool prof_enabled() { return g_prof.on; }
 
 void prof_begin(int cls, cudaStream_t s) {
   if (!g_prof.on) return;
@@ -147,7 +151,9 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
   const int n = c->grid.n, dim = c->grid.dim, tw = c->feat.t_window;
   const int64_t esz = c->grid.pos_f64 ? 8 : 4;
   { rollout_init_kernel<<<1, 1, 0, s>>>(b.stats, status_dev); LB_LAUNCHED(1); }
-  for (int t = 0; t < n_steps; ++t) {
+  // One step; targets / predictions are indexed on the device by status[0] (steps completed in this
+  // call), so the very same launches serve every step -- and can be replayed from a CUDA graph.
+  auto one_step = [&]() -> int {
     if (c->grid.pos_f64)
       { extract_last_kernel<double><<<cdiv(n * dim, 256), 256, 0, s>>>((const double*)window_dev, n, tw, dim, (double*)b.pos); LB_LAUNCHED(1); }
     else
@@ -162,11 +168,44 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
     rc = lb200_gns_forward(&c->gns, weights_dev, b.node_feat, b.edge_feat, ptype_dev, b.rowptr, b.perm, b.snd, b.rcv,
                            b.out, b.gns_scratch, b.gns_bytes, stream);
     if (rc) return rc;
-    const char* tgt = targets_dev ? (const char*)targets_dev + (int64_t)t * n * dim * esz : nullptr;
-    char* prd = preds_dev ? (char*)preds_dev + (int64_t)t * n * dim * esz : nullptr;
-    rc = lb200_integrate(&c->integ, b.out, window_dev, ptype_dev, tgt, prd, b.stats + 2, stream);
+    rc = integrate_indexed(&c->integ, b.out, window_dev, ptype_dev, targets_dev, preds_dev, b.stats + 2, status_dev, s);
     if (rc) return rc;
     { rollout_step_done_kernel<<<1, 1, 0, s>>>(b.stats, status_dev); LB_LAUNCHED(1); }
+    return 0;
+  };
+  int t = 0;
+  if (n_steps > 0) {  // the first step runs eagerly (it also performs every one-time kernel attribute setup)
+    int rc = one_step();
+    if (rc) return rc;
+    t = 1;
+  }
+  // Launch-bound inner loop (about 100 launches per step): replay the remaining steps from a CUDA graph.
+  // Not on the legacy default stream (capture is unsupported there) and not while per-kernel events are on.
+  const bool want_graph = n_steps - t >= 2 && s != nullptr && s != cudaStreamLegacy && !prof_enabled() &&
+                          getenv("LB200_NO_GRAPH") == nullptr;
+  if (want_graph && cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+    const int64_t launches0 = g_launches;
+    int rc = one_step();
+    const int64_t per_step = g_launches - launches0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (rc == 0 && e == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+      g_launches = launches0;  // the captured launches did not execute
+      for (; t < n_steps; ++t) {
+        if (cudaGraphLaunch(exec, s) != cudaSuccess) break;
+        g_launches += per_step;
+      }
+    } else {
+      g_launches = launches0;
+      cudaGetLastError();  // capture failed: clear the error and finish eagerly
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+  }
+  for (; t < n_steps; ++t) {
+    int rc = one_step();
+    if (rc) return rc;
   }
   LB_LAUNCH_CHECK();
   return 0;

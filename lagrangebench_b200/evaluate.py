@@ -96,6 +96,7 @@ class RolloutEngine:
         self.steps_per_sync = int(steps_per_sync)
         self._cfg = None
         self._scratch = None
+        self._stream = None  # non-default stream: lets lb200_rollout_steps replay steps from a CUDA graph
         self.n_reallocations = 0
         self.n_launch_calls = 0
 
@@ -135,14 +136,20 @@ class RolloutEngine:
             targets = targets.to(dev, window.dtype).contiguous()
             assert targets.shape == (n_steps, n, dim)
         status = torch.zeros(4, dtype=torch.int32, device=dev)
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev)
+        caller = torch.cuda.current_stream(dev)
         done = 0
         while done < n_steps:
             chunk = min(self.steps_per_sync, n_steps - done)
             tgt = _cabi.ptr(targets[done:done + chunk]) if targets is not None else None
-            _cabi.check(lib.lb200_rollout_steps(
-                C.byref(self._cfg), chunk, _cabi.ptr(self.packed.blob), _cabi.ptr(window), _cabi.ptr(ptype), None,
-                tgt, _cabi.ptr(preds[done:done + chunk]), _cabi.ptr(neighbors.idx), _cabi.ptr(status),
-                _cabi.ptr(self._scratch), self._scratch.numel(), _cabi.stream()))
+            self._stream.wait_stream(caller)
+            with torch.cuda.stream(self._stream):
+                _cabi.check(lib.lb200_rollout_steps(
+                    C.byref(self._cfg), chunk, _cabi.ptr(self.packed.blob), _cabi.ptr(window), _cabi.ptr(ptype), None,
+                    tgt, _cabi.ptr(preds[done:done + chunk]), _cabi.ptr(neighbors.idx), _cabi.ptr(status),
+                    _cabi.ptr(self._scratch), self._scratch.numel(), _cabi.stream()))
+            caller.wait_stream(self._stream)
             self.n_launch_calls += 1
             completed, overflow, _, _ = status.tolist()  # the one host sync per chunk
             done += completed
