@@ -296,7 +296,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
   for (int tile = blockIdx.x * 2 + wk; tile < n_tiles; tile += tile_stride) {
     const int64_t slot0 = (int64_t)tile * kTcTile;
     const int rows = min(kTcTile, E - (int)slot0);
-    if (!kEnc) request_rows(tile);
+    if (!kEnc) {
+      request_rows(tile);
+      // pull the next tile's rows into L2 now: its demand loads then skip the HBM round trip
+      const int nt = tile + tile_stride;
+      if (nt < n_tiles) {
+        const float* nrow = a.e + ((int64_t)nt * kTcTile + r0) * kLatent + lane * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + (int64_t)i * kLatent));
+      }
+    }
     asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");  // previous tile is done with idx / operands
     if (wtid < kTcTile) {
       const bool ok = wtid < rows;
