@@ -70,8 +70,25 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo) {
   return d;                                           // layout_type 0 = no swizzle
 }
 
+// One lane of a converged warp (elect.sync); operands computed by the whole warp stay warp-uniform,
+// which lets the compiler feed tcgen05.mma from uniform registers without a per-instruction
+// ELECT / R2UR "waterfall" loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Call from ALL lanes of one warp: a single elected lane issues the MMA.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate,
                                          uint32_t idesc = kIdesc) {
+  if (elect_one())
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -82,7 +99,8 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       : "memory");
 }
 
-__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {  // call from ALL lanes of the issuing warp
+  if (elect_one())
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
 
@@ -209,7 +227,8 @@ template <bool kEnc>
 __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const int wk = warp >> 3;        // worker (0/1): 8 warps, one 64-edge MMA tile at a time
   const int c = (warp >> 2) & 1;   // which 32-edge chunk (carry sub-tile) of the tile this warp finishes
   const int q = warp & 3;          // TMEM lane quarter of this warp
@@ -361,7 +380,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
     fence_async_smem();
     tc_fence_before();
     asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");
-    if (wtid == 0) {
+    if ((warp & 7) == 0) {  // the worker's first warp issues (one elected lane per instruction)
       tc_fence_after();
       issue_gemm(w1_hi, w1_lo, b_hi, b_lo, acc_hh, acc_x);
       umma_commit(bar_mma);
@@ -408,7 +427,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
     fence_async_smem();
     tc_fence_before();
     asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");
-    if (wtid == 0) {
+    if ((warp & 7) == 0) {
       tc_fence_after();
       issue_gemm(w2_hi, w2_lo, b_hi, b_lo, acc_hh, acc_x);
       umma_commit(bar_mma);
@@ -528,7 +547,8 @@ constexpr uint32_t kSmemNodeTc = kNOffBar + 48;
 __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const int q = warp & 3;    // TMEM lane quarter
   const int g = warp >> 2;   // 32-node column group of the tile this warp finishes
   const int f = q * 32 + lane;
@@ -569,11 +589,13 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
   const uint32_t t_addr = ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32);
   const uint32_t elem_off = (uint32_t)(f >> 3) * kLboB + (uint32_t)(f & 7) * 2 + (uint32_t)(g * 32) * 16;
   const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(a.w_tc);
-  uint32_t ph_w = 0, ph_mma = 0, ph_mid = 0;  // ph_w / ph_mid are only used by thread 0
+  uint32_t ph_w = 0, ph_mma = 0, ph_mid = 0;  // ph_w / ph_mid are only used by warp 0
 
-  auto load_w = [&](int k) {  // thread 0: stream weight operand k (hi|lo, 64 KB) into the buffer
-    mbar_expect_tx(bar_w, 2 * kWBytes);
-    bulk_g2s(w_hi, wsrc + (size_t)k * 2 * kWBytes, 2 * kWBytes, bar_w);
+  auto load_w = [&](int k) {  // warp 0 (one elected lane): stream weight operand k (hi|lo, 64 KB) into the buffer
+    if (elect_one()) {
+      mbar_expect_tx(bar_w, 2 * kWBytes);
+      bulk_g2s(w_hi, wsrc + (size_t)k * 2 * kWBytes, 2 * kWBytes, bar_w);
+    }
   };
   auto wait_w = [&]() {
     mbar_wait(bar_w, ph_w);
@@ -603,7 +625,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
         make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
   };
 
-  if (tid == 0) load_w(0);
+  if (warp == 0) load_w(0);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = (int64_t)tile * kNtTile;
     const int rows = min(kNtTile, a.n - (int)row0);
@@ -637,7 +659,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
     tc_fence_before();
     __syncthreads();
     // ---- layer 1: acc = W1h^T h + W1a^T agg   (two streamed operands)
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       wait_w();
       issue_gemm(w_hi, w_lo, bh_hi, bh_lo, acc_hh, acc_x, kIdescN128, false);
@@ -651,7 +673,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
       umma_commit(bar_mma);
     }
     wait_all();
-    if (tid == 0) load_w(2);  // W2c streams in while the hidden layer is written
+    if (warp == 0) load_w(2);  // W2c streams in while the hidden layer is written
     // hidden = relu(acc + b1) -> operand (over the aggregate, which is no longer needed)
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
@@ -664,7 +686,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
     tc_fence_before();
     __syncthreads();
     // ---- layer 2 (+ LayerNorm, residual)
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       wait_w();
       issue_gemm(w_hi, w_lo, ba_hi, ba_lo, acc_hh, acc_x, kIdescN128, false);
@@ -675,7 +697,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
 #pragma unroll
     for (int j = 0; j < 32; ++j) hold[j] = j < valid ? hrow[(int64_t)j * kLatent] : 0.f;
     wait_all();
-    if (tid == 0) load_w(3);
+    if (warp == 0) load_w(3);
     {
       float yc[32];
       float part;
@@ -714,7 +736,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
     tc_fence_before();
     __syncthreads();
     // ---- next step's sender projection P[:, 0:128], or the decoder's hidden layer
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       wait_w();
       issue_gemm(w_hi, w_lo, bh_hi, bh_lo, acc_hh, acc_x, kIdescN128, false);
@@ -722,7 +744,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
     }
     wait_all();
     if (!a.last) {
-      if (tid == 0) load_w(4);
+      if (warp == 0) load_w(4);
       float* const prow = a.P + (row0 + g * 32) * (2 * kLatent) + f;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -735,14 +757,14 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
       tc_fence_before();
       __syncthreads();  // every warp has drained the accumulators
       // ---- receiver projection P[:, 128:256] = h W1r + b1(next)
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after();
         wait_w();
         issue_gemm(w_hi, w_lo, bh_hi, bh_lo, acc_hh, acc_x, kIdescN128, false);
         umma_commit(bar_mma);
       }
       wait_all();
-      if (tid == 0 && tile + (int)gridDim.x < n_tiles) load_w(0);  // next tile's first operand
+      if (warp == 0 && tile + (int)gridDim.x < n_tiles) load_w(0);  // next tile's first operand
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         float hh[16], xx[16];
@@ -753,7 +775,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
             prow[(int64_t)(hf * 16 + j) * (2 * kLatent) + kLatent] = fmaf(xx[j], kLoInv, hh[j]) + b_next;
       }
     } else {
-      if (tid == 0 && tile + (int)gridDim.x < n_tiles) load_w(0);
+      if (warp == 0 && tile + (int)gridDim.x < n_tiles) load_w(0);
       // decoder (gns.py:126-133): out = relu(h Wd0 + bd0) Wd1 + bd1; the reduction over the 128
       // features runs across threads (31-shuffle transpose-reduce, then the 4 warps of the group)
       float hid[32];
