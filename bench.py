@@ -114,9 +114,20 @@ def node_in_of(case_spec):
 
 # --------------------------------------------------------------------------------------
 # oracle legs (cpu_baseline / --impl reference).  The ONLY place bench.py executes oracle/.
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs should use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:  # noqa: BLE001
+        pass
+
+
 def oracle_steps(spec, n_steps, warmup, seed, dtype_name):
     """Time the oracle port of the path: per step neighbor update + features + float32 GNS
     forward + integrate, NumPy on all host cores.  Returns (seconds for n_steps, N, E)."""
+    use_all_host_threads()
     from oracle import case as ocase
     from oracle import gns as ogns
     from oracle import rollout as orollout
