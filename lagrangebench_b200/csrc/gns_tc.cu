@@ -34,8 +34,11 @@
 
 namespace lb {
 
-constexpr int kTcThreads = 512;        // two 256-thread workers per CTA; 16 warps hide the epilogue latency
-constexpr int kTcTile = 64;            // edges per worker tile (one N=64 MMA tile) = 2 carry sub-tiles
+constexpr int kTcThreads = 512;        // kWorkers independent workers per CTA; 16 warps hide the epilogue latency
+constexpr int kWorkers = 4;            // 4 x 128 threads (32-edge tiles) or 2 x 256 threads (64-edge tiles)
+constexpr int kTcTile = 128 / kWorkers;  // edges per worker tile (one MMA tile, N = kTcTile)
+constexpr int kChunks = kTcTile / 32;    // 32-edge chunks (carry sub-tiles) per tile, one per group of 4 warps
+constexpr int kWThreads = kTcThreads / kWorkers;
 constexpr uint32_t kLboA = 2048;       // weights: 128 rows * 16 B per 8-wide K slab
 constexpr uint32_t kLboB = 2064;       // edge operand: padded slab pitch -> conflict-free stores
 constexpr uint32_t kSbo = 128;
@@ -44,20 +47,20 @@ constexpr uint32_t kBBytes = 16 * kLboB;  // one 128-row fp16 edge operand (33 K
 // instruction descriptor: D=F32 (bit 4), A=B=F16 (0), both K-major, N=64 (>>3 at bit 17), M=128 (>>4 at bit 24)
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTcTile >> 3) << 17) | (8u << 24);
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
-static_assert(kTcTile == 2 * kEdgeTile && kEdgeTile == 32, "a warp's 32-edge chunk is one carry sub-tile");
+static_assert(kTcTile == kChunks * kEdgeTile && kEdgeTile == 32, "a warp's 32-edge chunk is one carry sub-tile");
 
 // shared memory map (bytes)
 constexpr uint32_t kOffW = 0;                         // W1e_hi, W1e_lo, W2c_hi, W2c_lo
 constexpr uint32_t kOffB = kOffW + 4 * kWBytes;       // B_hi, B_lo
 constexpr uint32_t kOffVec = kOffB + 2 * kBBytes;     // b2c[128], scale[128], offset[128]
-constexpr uint32_t kOffIdx = kOffVec + 3 * 512;       // per worker: sidx[64], rclamp[64], ridx_ext[68]
-constexpr uint32_t kIdxInts = 64 + 64 + 68;
-constexpr uint32_t kOffRed = kOffIdx + 2 * kIdxInts * 4;    // per worker: red[2 chunks][4 warps][32]
-constexpr uint32_t kOffInv = kOffRed + 2 * 2 * 4 * 32 * 4;  // inv[16 warps][32]: 1/sqrt(var + eps) per edge
-constexpr uint32_t kOffEnd = kOffInv + 16 * 32 * 4;         // per worker: endmask[2]
-constexpr uint32_t kOffFeat = kOffEnd + 16;                 // per worker: feat[64] float4 (encoder inputs)
-constexpr uint32_t kOffBar = kOffFeat + 2 * 64 * 16;        // mbarriers: weights, mma[2]; tmem base
-constexpr uint32_t kSmemTc = kOffBar + 48;
+constexpr uint32_t kOffIdx = kOffVec + 3 * 512;       // per worker: sidx[T], rclamp[T], ridx_ext[T + 4]
+constexpr uint32_t kIdxInts = 3 * kTcTile + 4;
+constexpr uint32_t kOffRed = kOffIdx + kWorkers * kIdxInts * 4;  // per 32-edge chunk: red[4 warps][32]
+constexpr uint32_t kOffInv = kOffRed + 4 * 4 * 32 * 4;           // inv[16 warps][32]: 1/sqrt(var + eps) per edge
+constexpr uint32_t kOffEnd = kOffInv + 16 * 32 * 4;              // per chunk: endmask
+constexpr uint32_t kOffFeat = kOffEnd + 16;                      // per worker: feat[T] float4 (encoder inputs)
+constexpr uint32_t kOffBar = kOffFeat + 128 * 16;                // mbarriers: weights, mma[kWorkers]; tmem base
+constexpr uint32_t kSmemTc = kOffBar + 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -229,31 +232,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
-  const int wk = warp >> 3;        // worker (0/1): 8 warps, one 64-edge MMA tile at a time
-  const int c = (warp >> 2) & 1;   // which 32-edge chunk (carry sub-tile) of the tile this warp finishes
-  const int q = warp & 3;          // TMEM lane quarter of this warp
-  const int wtid = tid & 255;      // thread index inside the worker
-  const int f = q * 32 + lane;     // output feature == TMEM lane of this thread
+  const int wk = warp / (4 * kChunks);   // worker: 4 * kChunks warps, one kTcTile-edge MMA tile at a time
+  const int c = (warp >> 2) % kChunks;   // which 32-edge chunk (carry sub-tile) of the tile this warp finishes
+  const int q = warp & 3;                // TMEM lane quarter of this warp
+  const int wwarp = warp % (4 * kChunks);  // warp index inside the worker
+  const int wtid = tid % kWThreads;      // thread index inside the worker
+  const int f = q * 32 + lane;           // output feature == TMEM lane of this thread
   float* vec = reinterpret_cast<float*>(smem + kOffVec);
   int* sidx = reinterpret_cast<int*>(smem + kOffIdx) + wk * kIdxInts;
-  int* rclamp = sidx + 64;   // receivers clamped to a valid row (gather addresses)
-  int* ridx = rclamp + 64;   // ridx[0] = receiver before the tile, ridx[1 + i] = edge i, ridx[1 + rows] = after
-  float* red = reinterpret_cast<float*>(smem + kOffRed) + wk * 256 + c * 128;
+  int* rclamp = sidx + kTcTile;   // receivers clamped to a valid row (gather addresses)
+  int* ridx = rclamp + kTcTile;   // ridx[0] = receiver before the tile, ridx[1 + i] = edge i, ridx[1 + rows] = after
+  float* red = reinterpret_cast<float*>(smem + kOffRed) + (wk * kChunks + c) * 128;
   float* invs = reinterpret_cast<float*>(smem + kOffInv) + warp * 32;
-  uint32_t* endm = reinterpret_cast<uint32_t*>(smem + kOffEnd) + wk * 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 32);
+  uint32_t* endm = reinterpret_cast<uint32_t*>(smem + kOffEnd) + wk * kChunks;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 48);
   const uint32_t bar_w = sbase + kOffBar, bar_mma = sbase + kOffBar + 8 + 8 * wk;
-  const uint32_t bar_worker = 1 + wk;          // named barrier: the worker's 256 threads
-  const uint32_t bar_chunk = 3 + wk * 2 + c;   // named barrier: the 4 warps sharing a 32-edge chunk
+  const uint32_t bar_worker = 1 + wk;                       // named barrier: the worker's threads
+  const uint32_t bar_chunk = 1 + kWorkers + wk * kChunks + c;  // named barrier: the 4 warps sharing a 32-edge chunk
 
   const int E = a.rowptr[a.n];
   const int n_tiles = (E + kTcTile - 1) / kTcTile;
-  if ((int)blockIdx.x * 2 >= n_tiles) return;
+  if ((int)blockIdx.x * kWorkers >= n_tiles) return;
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
-    mbar_init(sbase + kOffBar + 8, 1);
-    mbar_init(sbase + kOffBar + 16, 1);
+    for (int w = 0; w < kWorkers; ++w) mbar_init(sbase + kOffBar + 8 + 8 * w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // TMEM columns: [0,64) acc_hh worker 0, [64,128) acc_hh worker 1, [128,192) acc_x worker 0, [192,256) acc_x worker 1
+  // TMEM columns: [0,128) acc_hh (kTcTile per worker), [128,256) acc_x
   const uint32_t acc_hh = tmem + wk * kTcTile, acc_x = tmem + 128 + wk * kTcTile;
 
   // resident weights: 4 fp16 operands (128 KB) + centred bias, LayerNorm scale / offset
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
   }
 
   const uint32_t w1_hi = sbase + kOffW, w1_lo = w1_hi + kWBytes, w2_hi = w1_lo + kWBytes, w2_lo = w2_hi + kWBytes;
-  // this worker's 64 operand rows inside every K slab
+  // this worker's kTcTile operand rows inside every K slab
   const uint32_t b_hi = sbase + kOffB + wk * (kTcTile * 16), b_lo = b_hi + kBBytes;
   unsigned char* b_hi_p = smem + kOffB + wk * (kTcTile * 16);
   unsigned char* b_lo_p = b_hi_p + kBBytes;
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
   uint32_t phase = 0;
 
   // this warp's 8 edge rows of a tile (coalesced 512 B rows); requested one tile ahead
-  const int r0 = (warp & 7) * 8;
+  const int r0 = wwarp * 8;
   float4 v[8];
   auto request_rows = [&](int t) {
     const int64_t s0 = (int64_t)t * kTcTile;
@@ -310,9 +313,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
       v[i] = r0 + i < nr ? reinterpret_cast<const float4*>(a.e + (s0 + r0 + i) * kLatent)[lane]
                          : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  const int tile_stride = gridDim.x * 2;
+  const int tile_stride = gridDim.x * kWorkers;
 
-  for (int tile = blockIdx.x * 2 + wk; tile < n_tiles; tile += tile_stride) {
+  for (int tile = blockIdx.x * kWorkers + wk; tile < n_tiles; tile += tile_stride) {
     const int64_t slot0 = (int64_t)tile * kTcTile;
     const int rows = min(kTcTile, E - (int)slot0);
     if (!kEnc) {
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + (int64_t)i * kLatent));
       }
     }
-    asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");  // previous tile is done with idx / operands
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(kWThreads) : "memory");  // previous tile is done with idx / operands
     if (wtid < kTcTile) {
       const bool ok = wtid < rows;
       const int r_here = ok ? a.rcv[slot0 + wtid] : -1;
@@ -337,17 +340,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
       // last edge of its receiver bucket inside its 32-edge carry sub-tile
       const bool end = ok && (r_next != r_here || lane == 31 || wtid == rows - 1);
       const uint32_t m = __ballot_sync(0xffffffffu, end);
-      if (lane == 0) endm[wtid >> 5] = m;
+      if (lane == 0) endm[wtid >> 5] = m;  // one mask per 32-edge chunk
       if (wtid == kTcTile - 1 && ok) ridx[1 + kTcTile] = r_next;  // receiver just after a full tile
     } else if (wtid == kTcTile) {
       ridx[0] = slot0 > 0 ? a.rcv[slot0 - 1] : -2;
     }
     if constexpr (kEnc) {
       // ---- encoder: first layer (K = dim + 1 <= 4) on CUDA cores straight into the layer-2 operand
-      float4* feat_s = reinterpret_cast<float4*>(smem + kOffFeat) + wk * 64;
+      float4* feat_s = reinterpret_cast<float4*>(smem + kOffFeat) + wk * kTcTile;
       if (wtid < kTcTile)  // the tile's edge features, gathered once through perm (list order -> slot order)
         feat_s[wtid] = wtid < rows ? a.edge_feat[a.perm[slot0 + wtid]] : make_float4(0.f, 0.f, 0.f, 0.f);
-      asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(kWThreads) : "memory");
 #pragma unroll 8
       for (int j = 0; j < 32; ++j) {
         const float4 ft = feat_s[c * 32 + j];
@@ -379,8 +382,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
     }
     fence_async_smem();
     tc_fence_before();
-    asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");
-    if ((warp & 7) == 0) {  // the worker's first warp issues (one elected lane per instruction)
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(kWThreads) : "memory");
+    if (wwarp == 0) {  // the worker's first warp issues (one elected lane per instruction)
       tc_fence_after();
       issue_gemm(w1_hi, w1_lo, b_hi, b_lo, acc_hh, acc_x);
       umma_commit(bar_mma);
@@ -426,8 +429,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
     }
     fence_async_smem();
     tc_fence_before();
-    asm volatile("bar.sync %0, 256;" ::"r"(bar_worker) : "memory");
-    if ((warp & 7) == 0) {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(kWThreads) : "memory");
+    if (wwarp == 0) {
       tc_fence_after();
       issue_gemm(w2_hi, w2_lo, b_hi, b_lo, acc_hh, acc_x);
       umma_commit(bar_mma);
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
         const uint32_t emask = endm[c];
         const bool first_cont = ridx[col0] == ridx[1 + col0];
         const bool last_cont = ridx[1 + col0 + valid] == ridx[col0 + valid];
-        const int sub = tile * 2 + c;  // carry sub-tile index (slot / kEdgeTile)
+        const int sub = tile * kChunks + c;  // carry sub-tile index (slot / kEdgeTile)
         float* const cfirst = a.carry_first + (int64_t)sub * kLatent + f;
         float* const clast = a.carry_last + (int64_t)sub * kLatent + f;
         float seg_sum = 0.f;
@@ -820,8 +823,8 @@ int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
     if (attr_rc == 0) attr_rc = (int)cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   if (attr_rc) return attr_rc;
-  const int n_pairs = cdiv(cdiv(e_cap, kTcTile), 2);  // two workers (tiles) per CTA
-  const int grid = n_pairs < g_num_sms ? n_pairs : g_num_sms;
+  const int n_groups = cdiv(cdiv(e_cap, kTcTile), kWorkers);  // kWorkers tiles in flight per CTA
+  const int grid = n_groups < g_num_sms ? n_groups : g_num_sms;
   if (a.encoder) {
     edge_mp_tc_kernel<true><<<grid, kTcThreads, kSmemTc, s>>>(a);
   } else {
