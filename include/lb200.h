@@ -161,8 +161,10 @@ typedef struct {
   lb200_mlp_off enc_node, enc_edge, dec;
   const lb200_mlp_off* proc_edge; /* host array [num_mp_steps] */
   const lb200_mlp_off* proc_node; /* host array [num_mp_steps] */
-  int32_t edge_impl;        /* 0: tcgen05 tensor-core message kernel (product path);
-                               1: fp32 CUDA-core kernel (kept as the numerical cross-check) */
+  int32_t edge_impl;        /* 0: tcgen05 tensor-core message kernel (product path: weights in TMEM,
+                                  pipelined tiles);
+                               1: fp32 CUDA-core kernel (kept as the numerical cross-check);
+                               2: first tensor-core kernel (weights in shared memory) */
   /* Domain decomposition (0 / NULL on a single GPU): rows [0, n_owned) of the node arrays are
    * this rank's particles, rows [n_owned, n) are ghosts whose projections P arrive from the
    * neighbouring ranks.  Node kernels run over owned rows, edge kernels over edges whose
@@ -252,6 +254,11 @@ int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, const float
  *   time (ms) and launch count of [0] the edge (message+aggregate) kernel and [1] the
  *   node-update kernel since the last reset.
  */
+/* Hardware self-test of the tcgen05 features the message kernel relies on (A operand read from
+ * tensor memory, scale-input-d accumulate): writes three floats to out3_dev -- max |D_ts - D_ss|,
+ * max |D_scaled - expected|, max |D_ss| (must be non-zero); the first two must be exactly 0. */
+int lb200_tc_selftest(float* out3_dev, void* stream);
+
 int64_t lb200_launch_count(void);
 int lb200_profile(int32_t enable);
 int lb200_profile_read(double* ms_out2, int64_t* launches_out2);

@@ -80,6 +80,7 @@ _SIGNATURES = {
     "lb200_integrate": (C.c_int, [C.POINTER(IntegrateCfg), _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "lb200_rollout_scratch_bytes": (_I64, [C.POINTER(RolloutCfg)]),
     "lb200_rollout_steps": (C.c_int, [C.POINTER(RolloutCfg), _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP]),
+    "lb200_tc_selftest": (C.c_int, [_VP, _VP]),
     "lb200_launch_count": (_I64, []),
     "lb200_profile": (C.c_int, [_I32]),
     "lb200_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -18,6 +18,8 @@
 //   agg  [N][128]      aggregated messages of receivers whose bucket lies inside one tile;
 //   carry_first/last [tiles][128]  partial sums of buckets that straddle a tile boundary,
 //                      combined (in tile order) by the node kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gns_tc.cuh"
 
@@ -493,6 +495,18 @@ __global__ void __launch_bounds__(kThreads, 2) node_mp_kernel(NodeMpArgs a) {
   }
 }
 
+// Which tensor-core message kernel runs: cfg.edge_impl 0 = default (v2, gns_tc2.cu), 2 = v1 (gns_tc.cu).
+// LB200_EDGE_TC=1|2 overrides the default (A/B measurements).
+static int edge_tc_version(int edge_impl) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("LB200_EDGE_TC");
+    env = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+  }
+  if (edge_impl == 2) return 1;
+  return env ? env : 2;
+}
+
 static MlpW mlp_ptrs(const float* w, const lb200_mlp_off& o) {
   MlpW m;
   m.w0 = w + o.w0;
@@ -596,7 +610,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   ne.P = P;
   { node_encoder_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeEnc, s>>>(ne); LB_LAUNCHED(1); }
 
-  if (c->edge_impl == 0 && c->enc_edge.tc_w >= 0 && c->enc_edge.tc_vec >= 0 &&
+  if (c->edge_impl != 1 && c->enc_edge.tc_w >= 0 && c->enc_edge.tc_vec >= 0 &&
       c->enc_edge.b0 == c->enc_edge.w0 + 4 * kLatent) {
     EdgeTcArgs et;
     et.n = n_own;
@@ -631,7 +645,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     if (c->halo_fn) c->halo_fn(c->halo_ctx, m);  // ghost rows of P for this step (enqueued on `s`)
     const lb200_mlp_off& eo = c->proc_edge[m];
     prof_begin(0, s);
-    if (c->edge_impl == 0 && eo.tc_w >= 0 && eo.tc_vec >= 0) {
+    if (c->edge_impl != 1 && eo.tc_w >= 0 && eo.tc_vec >= 0) {
       EdgeTcArgs et;
       et.n = n_own;
       et.rowptr = rowptr_dev;
@@ -648,7 +662,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       et.edge_feat = nullptr;
       et.perm = nullptr;
       et.enc_vec = nullptr;
-      rc = launch_edge_mp_tc(et, e_cap, s);
+      rc = edge_tc_version(c->edge_impl) == 2 ? launch_edge_mp_tc2(et, e_cap, s) : launch_edge_mp_tc(et, e_cap, s);
       if (rc) return rc;
     } else {
       EdgeMpArgs em;
@@ -669,7 +683,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     const lb200_mlp_off& no = c->proc_node[m];
     const bool last = m == c->num_mp_steps - 1;
     prof_begin(1, s);
-    if (c->edge_impl == 0 && no.tc_w >= 0 && no.tc_vec >= 0) {
+    if (c->edge_impl != 1 && no.tc_w >= 0 && no.tc_vec >= 0) {
       NodeTcArgs nt_args;
       nt_args.n = n_own;
       nt_args.last = last;

@@ -22,6 +22,8 @@ struct EdgeTcArgs {
 };
 
 int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s);
+// v2 (gns_tc2.cu): weights resident in TMEM, two-tile software pipeline per worker; processor steps only
+int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s);
 
 struct NodeTcArgs {
   int n;     // owned nodes

@@ -1,0 +1,552 @@
+// Message kernel v2 (tcgen05 + TMEM), sm_100a: the processor's edge update + segmented sum of
+// lagrangebench/models/gns.py:86-101,117-122 with
+//   * the four 128x128 fp16 weight operands (W1e hi|lo, W2c hi|lo) resident in TENSOR MEMORY for
+//     the whole persistent CTA (tcgen05.mma with the A operand in TMEM, 256 columns), which frees
+//     128 KB of shared memory for
+//   * double-buffered edge operands and accumulators, so that each 128-thread worker runs a
+//     two-tile software pipeline:  E1(k) | A(k+1) | E2(k)  -- every GEMM overlaps the phase that
+//     follows its issue instead of being waited for;
+//   * ONE accumulator per GEMM: the cross terms A_hi B_lo' + A_lo' B_hi (lo' = lo * 2^11) are
+//     accumulated first, and the first A_hi B_hi instruction rescales them with
+//     scale-input-d = 11 (D = A B + D * 2^-11), so the epilogues read half the TMEM columns;
+//   * the next tile's indices prefetched into registers one phase ahead.
+// Math, operand layouts and the carry protocol are those of v1 (gns_tc.cu).
+//
+//   hidden = relu(e @ W1e + P_s[snd] + P_r[rcv])        (P = per-node projections)
+//   yc     = hidden @ W2c + b2c                          (LayerNorm mean folded into W2c / b2c)
+//   e'     = scale * yc * rsqrt(mean(yc^2) + 1e-5) + offset
+//   e     <- e' + e ;  agg[rcv] = sum over the receiver's edges of e'  (ascending slot order)
+#include "tc_common.cuh"
+
+namespace lb {
+
+constexpr int k2Threads = 512;
+constexpr int k2Workers = 4;
+constexpr int k2Tile = 32;  // edges per worker tile == one carry sub-tile (kEdgeTile)
+constexpr int k2WThreads = k2Threads / k2Workers;
+static_assert(k2Tile == kEdgeTile, "a tile is one carry sub-tile");
+// instruction descriptor: D=F32, A=B=F16, K-major, N=32, M=128
+constexpr uint32_t k2Idesc = (1u << 4) | ((uint32_t)(k2Tile >> 3) << 17) | (8u << 24);
+
+// TMEM columns: [0,256) weights (64 columns per 128x128 fp16 operand), [256,512) accumulators
+constexpr uint32_t k2ColW1Hi = 0, k2ColW1Lo = 64, k2ColW2Hi = 128, k2ColW2Lo = 192, k2ColAcc = 256;
+
+// shared memory map (bytes)
+constexpr uint32_t k2OffB = 0;                                      // [buf 2][hi | lo], kBBytes each
+constexpr uint32_t k2OffVec = k2OffB + 4 * kBBytes;                 // b2c[128], scale[128], offset[128]
+constexpr uint32_t k2IdxInts = 32 + 32 + 36;                        // sidx[32], rclamp[32], ridx[34 (+2)]
+constexpr uint32_t k2OffIdx = k2OffVec + 3 * 512;                   // [worker][buf][k2IdxInts]
+constexpr uint32_t k2OffRed = k2OffIdx + k2Workers * 2 * k2IdxInts * 4;  // [worker][4 warps][32]
+constexpr uint32_t k2OffInv = k2OffRed + k2Workers * 128 * 4;       // [16 warps][32]
+constexpr uint32_t k2OffEnd = k2OffInv + 16 * 32 * 4;               // [worker][buf] end masks
+constexpr uint32_t k2OffBar = k2OffEnd + 32;                        // mbarriers g1[4], g2[4]; tmem base
+constexpr uint32_t k2Smem = k2OffBar + 8 * 8 + 16;
+
+// D[tmem] (+)= A[tmem] * B[smem desc]; call from ALL lanes of one warp
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate,
+                                        uint32_t idesc) {
+  if (elect_one())
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// D = A * B + D * 2^-11 (scale-input-d)
+__device__ __forceinline__ void umma_ts_rescale11(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
+  if (elect_one()) {
+    const uint32_t zero = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%4, %4, %4, %4}, p, 11;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(zero)
+        : "memory");
+  }
+}
+
+// SS twin of the rescaling instruction (self-test only)
+__device__ __forceinline__ void umma_ss_rescale11(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if (elect_one()) {
+    const uint32_t zero = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%4, %4, %4, %4}, p, 11;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(zero)
+        : "memory");
+  }
+}
+
+// split-precision GEMM (K = 128) into ONE accumulator:
+//   acc = (A_hi B_lo' + A_lo' B_hi) * 2^-11 + A_hi B_hi        (lo' = lo * 2^11)
+__device__ __forceinline__ void issue_gemm_ts(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t acc) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    umma_ts(acc, a_hi + j * 8, umma_desc(b_lo + j * 2 * kLboB, kLboB), j > 0 ? 1u : 0u, k2Idesc);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) umma_ts(acc, a_lo + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, k2Idesc);
+  umma_ts_rescale11(acc, a_hi, umma_desc(b_hi, kLboB), k2Idesc);
+#pragma unroll
+  for (int j = 1; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, k2Idesc);
+}
+
+// 16 columns of this warp's 32 TMEM lanes -> registers (thread == lane)
+__device__ __forceinline__ void tmem_ld16(uint32_t ta, float (&a)[16]) {
+  uint32_t x[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(x[8]),
+        "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15])
+      : "r"(ta)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(x[i]);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t ta, float (&a)[32]) {
+  uint32_t x[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(x[8]),
+        "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15]), "=r"(x[16]),
+        "=r"(x[17]), "=r"(x[18]), "=r"(x[19]), "=r"(x[20]), "=r"(x[21]), "=r"(x[22]), "=r"(x[23]), "=r"(x[24]),
+        "=r"(x[25]), "=r"(x[26]), "=r"(x[27]), "=r"(x[28]), "=r"(x[29]), "=r"(x[30]), "=r"(x[31])
+      : "r"(ta)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(x[i]);
+}
+
+// registers -> 16 columns of this warp's 32 TMEM lanes (thread == lane)
+__device__ __forceinline__ void tmem_st16(uint32_t ta, const uint32_t (&x)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(ta),
+      "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(x[8]), "r"(x[9]),
+      "r"(x[10]), "r"(x[11]), "r"(x[12]), "r"(x[13]), "r"(x[14]), "r"(x[15])
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// One 128x128 fp16 operand, stored in global memory in the UMMA K-major layout [k/8][m][k%8]
+// (models.py: umma_operand), -> 64 TMEM columns: lane m holds row m, column c holds k = 2c, 2c+1.
+// Called by a warp for its own lane quarter; `lane_row` = the thread's row m.
+__device__ __forceinline__ void weight_to_tmem(const uint4* op, int lane_row, uint32_t taddr) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t x[16];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const uint4 v = __ldg(op + (g * 4 + s) * 128 + lane_row);
+      x[s * 4 + 0] = v.x;
+      x[s * 4 + 1] = v.y;
+      x[s * 4 + 2] = v.z;
+      x[s * 4 + 3] = v.w;
+    }
+    tmem_st16(taddr + g * 16, x);
+  }
+}
+
+__global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
+  const int wk = warp >> 2;              // worker: 4 warps, a two-tile software pipeline
+  const int q = warp & 3;                // TMEM lane quarter of this warp == warp index inside the worker
+  const int wtid = tid & (k2WThreads - 1);
+  const int f = q * 32 + lane;           // output feature == TMEM lane of this thread
+  float* vec = reinterpret_cast<float*>(smem + k2OffVec);
+  int* idx_base = reinterpret_cast<int*>(smem + k2OffIdx) + wk * 2 * k2IdxInts;
+  float* red = reinterpret_cast<float*>(smem + k2OffRed) + wk * 128;
+  float* invs = reinterpret_cast<float*>(smem + k2OffInv) + warp * 32;
+  uint32_t* endm = reinterpret_cast<uint32_t*>(smem + k2OffEnd) + wk * 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + k2OffBar + 64);
+  const uint32_t bar_g1 = sbase + k2OffBar + 8 * wk, bar_g2 = sbase + k2OffBar + 32 + 8 * wk;
+  const uint32_t bar_worker = 1 + wk;            // named barriers: the worker's 128 threads
+  const uint32_t bar_ln = 1 + k2Workers + wk;
+
+  const int E = a.rowptr[a.n];
+  const int n_tiles = (E + k2Tile - 1) / k2Tile;
+  if ((int)blockIdx.x * k2Workers >= n_tiles) return;
+
+  if (tid == 0) {
+    for (int w = 0; w < 2 * k2Workers; ++w) mbar_init(sbase + k2OffBar + 8 * w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < 3 * 128; i += k2Threads) vec[i] = a.vec_tc[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // resident weights -> TMEM: warp group g (4 warps, one per lane quarter) loads operand g
+  weight_to_tmem(reinterpret_cast<const uint4*>(a.w_tc) + wk * 2048, f, tmem + ((uint32_t)(q * 32) << 16) + wk * 64);
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const float b2c = vec[f], ln_scale = vec[128 + f], ln_offset = vec[256 + f];
+  const uint32_t w1_hi = tmem + k2ColW1Hi, w1_lo = tmem + k2ColW1Lo, w2_hi = tmem + k2ColW2Hi, w2_lo = tmem + k2ColW2Lo;
+  const uint32_t acc0 = tmem + k2ColAcc + wk * 64;                       // + buf * 32
+  const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+  // this worker's 32 operand rows inside every K slab; buffer b at + b * 2 * kBBytes, lo at + kBBytes
+  const uint32_t b_off = k2OffB + wk * (k2Tile * 16);
+  // this thread's element (k = f) of operand row `e` (edge):
+  const uint32_t elem_off = b_off + (uint32_t)(f >> 3) * kLboB + (uint32_t)(f & 7) * 2;
+  const int r0 = q * 8;  // this warp's 8 edge rows in phase A
+  const int tile_stride = gridDim.x * k2Workers;
+  uint32_t ph1 = 0, ph2 = 0;
+  int pre_a = 0, pre_b = 0;  // next tile's indices: warp 0: rcv[i], rcv[i + 1]; warp 1: snd[i]; warp 2 lane 0: rcv[-1]
+
+  auto prefetch_idx = [&](int tile) {
+    if (tile >= n_tiles) return;
+    const int64_t s = (int64_t)tile * k2Tile + lane;
+    if (q == 0) {
+      pre_a = s < E ? __ldg(a.rcv + s) : -1;
+      pre_b = s + 1 < E ? __ldg(a.rcv + s + 1) : -3;
+    } else if (q == 1) {
+      pre_a = s < E ? __ldg(a.snd + s) : 0;
+    } else if (q == 2) {
+      pre_a = (lane == 0 && s > 0) ? __ldg(a.rcv + s - 1) : -2;
+    }
+  };
+
+  // ---- phase A(tile -> buffer b): indices -> smem, edge latents -> fp16 hi/lo operand, issue GEMM 1
+  auto phase_a = [&](int tile, int b) {
+    const int64_t slot0 = (int64_t)tile * k2Tile;
+    const int rows = min(k2Tile, E - (int)slot0);
+    int* sidx = idx_base + b * k2IdxInts;
+    int* rclamp = sidx + 32;
+    int* ridx = rclamp + 32;  // ridx[0] = receiver before the tile, ridx[1 + i] = edge i, ridx[1 + rows] = after
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      v[i] = r0 + i < rows ? reinterpret_cast<const float4*>(a.e + (slot0 + r0 + i) * kLatent)[lane]
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    {  // pull the rows of the tile after this one into L2
+      const int nt = tile + tile_stride;
+      if (nt < n_tiles) {
+        const float* nrow = a.e + ((int64_t)nt * k2Tile + r0) * kLatent + lane * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + (int64_t)i * kLatent));
+      }
+    }
+    if (q == 0) {
+      const bool ok = lane < rows;
+      const int r_here = pre_a, r_next = pre_b;
+      rclamp[lane] = max(r_here, 0);
+      ridx[1 + lane] = ok ? r_here : (lane == rows ? -3 : -1);  // -3: "no edge after the tile"
+      // last edge of its receiver bucket inside the tile (== carry sub-tile)
+      const bool end = ok && (r_next != r_here || lane == 31 || lane == rows - 1);
+      const uint32_t m = __ballot_sync(0xffffffffu, end);
+      if (lane == 0) endm[b] = m;
+      if (lane == 31 && ok) ridx[1 + 32] = r_next;  // receiver just after a full tile
+    } else if (q == 1) {
+      sidx[lane] = pre_a;
+    } else if (q == 2) {
+      if (lane == 0) ridx[0] = pre_a;
+    }
+    prefetch_idx(tile + tile_stride);
+    unsigned char* hi_p = smem + k2OffB + b * 2 * kBBytes + wk * (k2Tile * 16);
+    unsigned char* lo_p = hi_p + kBBytes;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __half2 h01 = __floats2half2_rn(v[i].x, v[i].y), h23 = __floats2half2_rn(v[i].z, v[i].w);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn((v[i].x - f01.x) * kLoScale, (v[i].y - f01.y) * kLoScale);
+      const __half2 l23 = __floats2half2_rn((v[i].z - f23.x) * kLoScale, (v[i].w - f23.y) * kLoScale);
+      const uint32_t off = (uint32_t)(lane >> 1) * kLboB + (uint32_t)(r0 + i) * 16 + (uint32_t)(lane & 1) * 8;
+      *reinterpret_cast<uint2*>(hi_p + off) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+      *reinterpret_cast<uint2*>(lo_p + off) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
+    fence_async_smem();
+    tc_fence_before();
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(k2WThreads) : "memory");
+    if (q == 0) {  // the worker's first warp issues (one elected lane per instruction)
+      tc_fence_after();
+      const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
+      issue_gemm_ts(w1_hi, w1_lo, bh, bh + kBBytes, acc0 + b * 32);
+      umma_commit(bar_g1);
+    }
+  };
+
+  // ---- E1(tile in buffer b): hidden = relu(acc + P_s[snd] + P_r[rcv]) -> operand, issue GEMM 2
+  auto phase_e1 = [&](int b) {
+    const int* sp = idx_base + b * k2IdxInts;
+    const int* rp = sp + 32;
+    float ps[32], pr[32];
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += 4) {
+      const int4 s4 = *reinterpret_cast<const int4*>(sp + j0);
+      const int4 r4 = *reinterpret_cast<const int4*>(rp + j0);
+      ps[j0 + 0] = __ldg(a.P + (int64_t)s4.x * (2 * kLatent) + f);
+      ps[j0 + 1] = __ldg(a.P + (int64_t)s4.y * (2 * kLatent) + f);
+      ps[j0 + 2] = __ldg(a.P + (int64_t)s4.z * (2 * kLatent) + f);
+      ps[j0 + 3] = __ldg(a.P + (int64_t)s4.w * (2 * kLatent) + f);
+      pr[j0 + 0] = __ldg(a.P + (int64_t)r4.x * (2 * kLatent) + kLatent + f);
+      pr[j0 + 1] = __ldg(a.P + (int64_t)r4.y * (2 * kLatent) + kLatent + f);
+      pr[j0 + 2] = __ldg(a.P + (int64_t)r4.z * (2 * kLatent) + kLatent + f);
+      pr[j0 + 3] = __ldg(a.P + (int64_t)r4.w * (2 * kLatent) + kLatent + f);
+    }
+    mbar_wait(bar_g1, ph1);
+    ph1 ^= 1;
+    tc_fence_after();
+    unsigned char* hi_p = smem + elem_off + b * 2 * kBBytes;
+    unsigned char* lo_p = hi_p + kBBytes;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float acc[16];
+      tmem_ld16(acc0 + b * 32 + lane_sel + h * 16, acc);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int e = h * 16 + j;
+        const float hval = fmaxf(acc[j] + ps[e] + pr[e], 0.f);
+        const __half hi = __float2half_rn(hval);
+        const __half lo = __float2half_rn((hval - __half2float(hi)) * kLoScale);
+        *reinterpret_cast<__half*>(hi_p + (uint32_t)e * 16) = hi;
+        *reinterpret_cast<__half*>(lo_p + (uint32_t)e * 16) = lo;
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(k2WThreads) : "memory");
+    if (q == 0) {
+      tc_fence_after();
+      const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
+      issue_gemm_ts(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32);
+      umma_commit(bar_g2);
+    }
+  };
+
+  // ---- E2(tile in buffer b): LayerNorm (mean folded into the weights), residual, store, segmented sum
+  auto phase_e2 = [&](int tile, int b) {
+    const int64_t slot0 = (int64_t)tile * k2Tile;
+    const int valid = min(k2Tile, E - (int)slot0);  // edges of this tile that exist (>= 1)
+    const int* ridx = idx_base + b * k2IdxInts + 64;
+    float* const erow = a.e + slot0 * kLatent + f;
+    float eold[32];
+    if (valid == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) eold[j] = erow[(int64_t)j * kLatent];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) eold[j] = j < valid ? erow[(int64_t)j * kLatent] : 0.f;
+    }
+    mbar_wait(bar_g2, ph2);
+    ph2 ^= 1;
+    tc_fence_after();
+    float yc[32];
+    float part;
+    {
+      float sq[32];
+      tmem_ld32(acc0 + b * 32 + lane_sel, yc);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        yc[j] += b2c;
+        sq[j] = yc[j] * yc[j];
+      }
+      part = warp_transpose_reduce(sq);  // lane l: this warp's 32 features, edge l
+    }
+    red[q * 32 + lane] = part;
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_ln), "n"(k2WThreads) : "memory");
+    {
+      const float var = (red[lane] + red[32 + lane] + red[64 + lane] + red[96 + lane]) * (1.0f / kLatent);
+      invs[lane] = 1.0f / sqrtf(var + 1e-5f);  // once per edge per warp (same value in the 4 warps)
+    }
+    __syncwarp();
+    const uint32_t emask = endm[b];
+    const bool first_cont = ridx[0] == ridx[1];
+    const bool last_cont = ridx[1 + valid] == ridx[valid];
+    float* const cfirst = a.carry_first + (int64_t)tile * kLatent + f;
+    float* const clast = a.carry_last + (int64_t)tile * kLatent + f;
+    float seg_sum = 0.f;
+    bool seg_first = true;  // still inside the first bucket of the sub-tile
+    auto finish = [&](auto full_tag) {
+      constexpr bool kFull = decltype(full_tag)::value;
+#pragma unroll
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        const float4 inv4 = *reinterpret_cast<const float4*>(invs + j4);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int j = j4 + t;
+          const float inv = t == 0 ? inv4.x : (t == 1 ? inv4.y : (t == 2 ? inv4.z : inv4.w));
+          const float msg = fmaf(ln_scale * inv, yc[j], ln_offset);  // e' : the message
+          if (kFull || j < valid) {
+            erow[(int64_t)j * kLatent] = msg + eold[j];  // residual (gns.py:120-122)
+            seg_sum += msg;
+            if ((emask >> j) & 1u) {  // bucket ends here (uniform across the worker)
+              float* dst = a.agg + (int64_t)ridx[1 + j] * kLatent + f;
+              if (j == valid - 1 && last_cont) dst = clast;
+              if (seg_first && first_cont) dst = cfirst;
+              *dst = seg_sum;
+              seg_sum = 0.f;
+              seg_first = false;
+            }
+          }
+        }
+      }
+    };
+    if (valid == 32)
+      finish(std::true_type{});
+    else
+      finish(std::false_type{});
+    tc_fence_before();
+  };
+
+  // two-tile software pipeline per worker:  A(k0) ; { E1(k) ; A(k+1) ; E2(k) }
+  const int k0 = blockIdx.x * k2Workers + wk;
+  if (k0 < n_tiles) {
+    prefetch_idx(k0);
+    phase_a(k0, 0);
+  }
+  int buf = 0;
+  for (int tile = k0; tile < n_tiles; tile += tile_stride) {
+    phase_e1(buf);
+    if (tile + tile_stride < n_tiles) phase_a(tile + tile_stride, buf ^ 1);
+    phase_e2(tile, buf);
+    buf ^= 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
+  static int attr_rc = -1;
+  static int sms = 0;
+  if (attr_rc < 0) {
+    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem);
+    int dev = 0;
+    if (attr_rc == 0) attr_rc = (int)cudaGetDevice(&dev);
+    if (attr_rc == 0) attr_rc = (int)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (attr_rc) return attr_rc;
+  const int n_groups = cdiv(cdiv(e_cap, k2Tile), k2Workers);
+  const int grid = n_groups < sms ? n_groups : sms;
+  edge_mp_tc2_kernel<<<grid, k2Threads, k2Smem, s>>>(a);
+  LB_LAUNCHED(1);
+  return 0;
+}
+
+// =====================================================================================
+// Hardware self-test of the two tcgen05 features v2 relies on (one CTA, 128 threads):
+//   out[0] = max |D_ts - D_ss|   A operand read from TMEM (row m in lane m, column c = k 2c, 2c+1)
+//                                 vs the same A read from shared memory
+//   out[1] = max |D_scaled - (A B + (A B) 2^-11)|   scale-input-d = 11
+//   out[2] = max |D_ss|          (sanity: non-zero)
+__global__ void __launch_bounds__(128, 1) tc_selftest_kernel(float* out) {
+  __shared__ __align__(128) unsigned char sm_a[128 * 32];   // A: 128 rows x K 16 fp16, K-major core matrices
+  __shared__ __align__(128) unsigned char sm_b[32 * 32];    // B: 32 rows x K 16
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t slot;
+  __shared__ float red[3][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t mb = smem_u32(&bar);
+  if (tid == 0) {
+    mbar_init(mb, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // A[m][k] = ((m * 7 + k * 3) % 17 - 8) / 8 ; B[n][k] = ((n * 5 + k) % 13 - 6) / 4   (exact in fp16)
+  uint32_t arow[8];
+  for (int k = 0; k < 16; ++k) {
+    const float av = (float)((tid * 7 + k * 3) % 17 - 8) * 0.125f;
+    const unsigned short ah = __half_as_ushort(__float2half_rn(av));
+    *reinterpret_cast<unsigned short*>(sm_a + (k >> 3) * 2048 + tid * 16 + (k & 7) * 2) = ah;
+    if (k & 1)
+      arow[k >> 1] |= (uint32_t)ah << 16;
+    else
+      arow[k >> 1] = ah;
+    if (tid < 32) {
+      const float bv = (float)((tid * 5 + k) % 13 - 6) * 0.25f;
+      *reinterpret_cast<__half*>(sm_b + (k >> 3) * 512 + tid * 16 + (k & 7) * 2) = __float2half_rn(bv);
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+  // A -> TMEM columns [96, 104)
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(tmem + lane_sel + 96),
+               "r"(arow[0]), "r"(arow[1]), "r"(arow[2]), "r"(arow[3]), "r"(arow[4]), "r"(arow[5]), "r"(arow[6]),
+               "r"(arow[7])
+               : "memory");
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    const uint64_t ad = umma_desc(smem_u32(sm_a), 2048), bd = umma_desc(smem_u32(sm_b), 512);
+    umma_f16(tmem + 0, ad, bd, 0u, k2Idesc);            // D_ss  (columns 0..31)
+    umma_ts(tmem + 32, tmem + 96, bd, 0u, k2Idesc);     // D_ts  (columns 32..63)
+    umma_f16(tmem + 64, ad, bd, 0u, k2Idesc);           // D_scaled = A B, then A B + D 2^-11
+    umma_ss_rescale11(tmem + 64, ad, bd, k2Idesc);
+    umma_commit(mb);
+  }
+  mbar_wait(mb, 0);
+  tc_fence_after();
+  float dss[32], dts[32], dsc[32];
+  tmem_ld32(tmem + lane_sel + 0, dss);
+  tmem_ld32(tmem + lane_sel + 32, dts);
+  tmem_ld32(tmem + lane_sel + 64, dsc);
+  float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+  for (int j = 0; j < 32; ++j) {
+    e0 = fmaxf(e0, fabsf(dts[j] - dss[j]));
+    e1 = fmaxf(e1, fabsf(dsc[j] - (dss[j] + dss[j] * (1.0f / 2048.0f))));
+    e2 = fmaxf(e2, fabsf(dss[j]));
+  }
+  for (int off = 16; off >= 1; off >>= 1) {
+    e0 = fmaxf(e0, __shfl_xor_sync(0xffffffffu, e0, off));
+    e1 = fmaxf(e1, __shfl_xor_sync(0xffffffffu, e1, off));
+    e2 = fmaxf(e2, __shfl_xor_sync(0xffffffffu, e2, off));
+  }
+  if (lane == 0) {
+    red[0][warp] = e0;
+    red[1][warp] = e1;
+    red[2][warp] = e2;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) out[i] = fmaxf(fmaxf(red[i][0], red[i][1]), fmaxf(red[i][2], red[i][3]));
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+  }
+}
+
+}  // namespace lb
+
+extern "C" int lb200_tc_selftest(float* out3_dev, void* stream) {
+  if (!out3_dev) return LB200_EINVAL;
+  lb::tc_selftest_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(out3_dev);
+  LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,206 @@
+// tcgen05 / TMEM / mbarrier / bulk-copy helpers and the operand-layout constants shared by the
+// tensor-core kernels (gns_tc.cu: message kernel v1, edge encoder, node update; gns_tc2.cu: the
+// pipelined message kernel with TMEM-resident weights).  sm_100a only.
+#pragma once
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+#include "gns_tc.cuh"
+
+namespace lb {
+
+constexpr int kTcThreads = 512;        // kWorkers independent workers per CTA; 16 warps hide the epilogue latency
+constexpr int kWorkers = 4;            // 4 x 128 threads (32-edge tiles) or 2 x 256 threads (64-edge tiles)
+constexpr int kTcTile = 128 / kWorkers;  // edges per worker tile (one MMA tile, N = kTcTile)
+constexpr int kChunks = kTcTile / 32;    // 32-edge chunks (carry sub-tiles) per tile, one per group of 4 warps
+constexpr int kWThreads = kTcThreads / kWorkers;
+constexpr uint32_t kLboA = 2048;       // weights: 128 rows * 16 B per 8-wide K slab
+constexpr uint32_t kLboB = 2064;       // edge operand: padded slab pitch -> conflict-free stores
+constexpr uint32_t kSbo = 128;
+constexpr uint32_t kWBytes = 16 * kLboA;  // one 128x128 fp16 weight operand (32 KB)
+constexpr uint32_t kBBytes = 16 * kLboB;  // one 128-row fp16 edge operand (33 KB): rows 0..63 worker 0, 64..127 worker 1
+// instruction descriptor: D=F32 (bit 4), A=B=F16 (0), both K-major, N=64 (>>3 at bit 17), M=128 (>>4 at bit 24)
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTcTile >> 3) << 17) | (8u << 24);
+constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
+static_assert(kTcTile == kChunks * kEdgeTile && kEdgeTile == 32, "a warp's 32-edge chunk is one carry sub-tile");
+
+// shared memory map (bytes)
+constexpr uint32_t kOffW = 0;                         // W1e_hi, W1e_lo, W2c_hi, W2c_lo
+constexpr uint32_t kOffB = kOffW + 4 * kWBytes;       // B_hi, B_lo
+constexpr uint32_t kOffVec = kOffB + 2 * kBBytes;     // b2c[128], scale[128], offset[128]
+constexpr uint32_t kOffIdx = kOffVec + 3 * 512;       // per worker: sidx[T], rclamp[T], ridx_ext[T + 4]
+constexpr uint32_t kIdxInts = 3 * kTcTile + 4;
+constexpr uint32_t kOffRed = kOffIdx + kWorkers * kIdxInts * 4;  // per 32-edge chunk: red[4 warps][32]
+constexpr uint32_t kOffInv = kOffRed + 4 * 4 * 32 * 4;           // inv[16 warps][32]: 1/sqrt(var + eps) per edge
+constexpr uint32_t kOffEnd = kOffInv + 16 * 32 * 4;              // per chunk: endmask
+constexpr uint32_t kOffFeat = kOffEnd + 16;                      // per worker: feat[T] float4 (encoder inputs)
+constexpr uint32_t kOffBar = kOffFeat + 128 * 16;                // mbarriers: weights, mma[kWorkers]; tmem base
+constexpr uint32_t kSmemTc = kOffBar + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);           // start address  [0,14)
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;        // leading byte offset (K-adjacent core matrices)
+  d |= (uint64_t)((kSbo >> 4) & 0x3FFFu) << 32;       // stride byte offset (8-row groups)
+  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+  return d;                                           // layout_type 0 = no swizzle
+}
+
+// One lane of a converged warp (elect.sync); operands computed by the whole warp stay warp-uniform,
+// which lets the compiler feed tcgen05.mma from uniform registers without a per-instruction
+// ELECT / R2UR "waterfall" loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Call from ALL lanes of one warp: a single elected lane issues the MMA.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate,
+                                         uint32_t idesc = kIdesc) {
+  if (elect_one())
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {  // call from ALL lanes of the issuing warp
+  if (elect_one())
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// two accumulators x 32 columns of this warp's 32 TMEM lanes -> registers (thread == lane)
+__device__ __forceinline__ void tmem_ld_pair(uint32_t ta, uint32_t tb, float (&a)[32], float (&b)[32]) {
+  uint32_t x[32], y[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%64];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%65];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(x[8]),
+        "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15]), "=r"(x[16]),
+        "=r"(x[17]), "=r"(x[18]), "=r"(x[19]), "=r"(x[20]), "=r"(x[21]), "=r"(x[22]), "=r"(x[23]), "=r"(x[24]),
+        "=r"(x[25]), "=r"(x[26]), "=r"(x[27]), "=r"(x[28]), "=r"(x[29]), "=r"(x[30]), "=r"(x[31]), "=r"(y[0]),
+        "=r"(y[1]), "=r"(y[2]), "=r"(y[3]), "=r"(y[4]), "=r"(y[5]), "=r"(y[6]), "=r"(y[7]), "=r"(y[8]), "=r"(y[9]),
+        "=r"(y[10]), "=r"(y[11]), "=r"(y[12]), "=r"(y[13]), "=r"(y[14]), "=r"(y[15]), "=r"(y[16]), "=r"(y[17]),
+        "=r"(y[18]), "=r"(y[19]), "=r"(y[20]), "=r"(y[21]), "=r"(y[22]), "=r"(y[23]), "=r"(y[24]), "=r"(y[25]),
+        "=r"(y[26]), "=r"(y[27]), "=r"(y[28]), "=r"(y[29]), "=r"(y[30]), "=r"(y[31])
+      : "r"(ta), "r"(tb)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    a[i] = __uint_as_float(x[i]);
+    b[i] = __uint_as_float(y[i]);
+  }
+}
+
+// two accumulators x 16 columns (half the registers of tmem_ld_pair)
+__device__ __forceinline__ void tmem_ld_pair16(uint32_t ta, uint32_t tb, float (&a)[16], float (&b)[16]) {
+  uint32_t x[16], y[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(x[8]),
+        "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15]), "=r"(y[0]),
+        "=r"(y[1]), "=r"(y[2]), "=r"(y[3]), "=r"(y[4]), "=r"(y[5]), "=r"(y[6]), "=r"(y[7]), "=r"(y[8]), "=r"(y[9]),
+        "=r"(y[10]), "=r"(y[11]), "=r"(y[12]), "=r"(y[13]), "=r"(y[14]), "=r"(y[15])
+      : "r"(ta), "r"(tb)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    a[i] = __uint_as_float(x[i]);
+    b[i] = __uint_as_float(y[i]);
+  }
+}
+
+__device__ __forceinline__ void split_f16(float x, unsigned short& hi, unsigned short& lo) {
+  const __half h = __float2half_rn(x);
+  const __half l = __float2half_rn((x - __half2float(h)) * kLoScale);
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(l);
+}
+
+// 3-pass split-precision GEMM: acc_hh = A_hi B_hi ; acc_x = A_hi B_lo + A_lo B_hi   (K = 128)
+__device__ __forceinline__ void issue_gemm(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                           uint32_t acc_hh, uint32_t acc_x, uint32_t idesc = kIdesc,
+                                           bool accumulate = false) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    umma_f16(acc_hh, umma_desc(a_hi + j * 2 * kLboA, kLboA), umma_desc(b_hi + j * 2 * kLboB, kLboB),
+             (j > 0 || accumulate) ? 1u : 0u, idesc);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    umma_f16(acc_x, umma_desc(a_hi + j * 2 * kLboA, kLboA), umma_desc(b_lo + j * 2 * kLboB, kLboB),
+             (j > 0 || accumulate) ? 1u : 0u, idesc);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    umma_f16(acc_x, umma_desc(a_lo + j * 2 * kLboA, kLboA), umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
+}
+
+// lane l ends with the sum over the warp's 32 lanes of v[l]   (31 shuffles, fixed order)
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+}  // namespace lb

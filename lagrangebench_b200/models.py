@@ -188,7 +188,7 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
                         num_types, dim, num_mp_steps)
 
 
-EDGE_IMPL = {"tc": 0, "simt": 1}
+EDGE_IMPL = {"tc": 0, "simt": 1, "tc1": 2}
 
 
 def gns_cfg(packed, n, e_cap, node_in, node_stride, edge_impl="tc"):

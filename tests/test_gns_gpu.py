@@ -103,3 +103,33 @@ def test_tensor_core_kernel_matches_cuda_core_kernel():
     got_simt = out["acc"].cpu().numpy()
     assert rel_err(got_tc, got_simt) <= 5e-6
     assert rel_err(got_tc, ref64) <= TOL and rel_err(got_simt, ref64) <= TOL
+
+
+def test_tcgen05_selftest_tmem_operand_and_rescaled_accumulate():
+    """The two hardware features the pipelined message kernel relies on: the A operand read
+    from tensor memory must equal the same operand read from shared memory, and
+    scale-input-d = 11 must compute A B + D * 2^-11 exactly."""
+    from lagrangebench_b200 import _cabi
+
+    lib = _cabi.load()
+    out = torch.full((3,), -1.0, device="cuda")
+    _cabi.check(lib.lb200_tc_selftest(_cabi.ptr(out), _cabi.stream()))
+    torch.cuda.synchronize()
+    ts_vs_ss, scaled, mag = out.cpu().tolist()
+    print(f"tc selftest: |D_ts - D_ss| {ts_vs_ss:.3e}  |D_scaled - expected| {scaled:.3e}  max|D| {mag:.3f}")
+    assert mag > 1.0
+    assert ts_vs_ss == 0.0
+    assert scaled <= 1e-6 * mag
+
+
+def test_pipelined_message_kernel_matches_first_tensor_core_kernel():
+    """v2 (weights in TMEM, one rescaled accumulator, two-tile pipeline) against v1 (weights in
+    shared memory, two accumulators): same split-precision scheme, same summation order of
+    the segmented sum -- they may differ in the last float32 bits of the GEMMs only."""
+    got_v2, ref64, _, (c, ours, f_gpu, params, model) = _forward_both("ldc3d", "float64")
+    model.edge_impl = "tc1"
+    out, _ = model.apply(params, {}, (f_gpu, c["particle_type"]))
+    got_v1 = out["acc"].cpu().numpy()
+    print(f"v2 vs v1 {rel_err(got_v2, got_v1):.2e}; v2 vs f64 {rel_err(got_v2, ref64):.2e}; v1 vs f64 {rel_err(got_v1, ref64):.2e}")
+    assert rel_err(got_v2, got_v1) <= 5e-6
+    assert rel_err(got_v2, ref64) <= TOL
