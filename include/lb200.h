@@ -254,10 +254,12 @@ int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, const float
  *   time (ms) and launch count of [0] the edge (message+aggregate) kernel and [1] the
  *   node-update kernel since the last reset.
  */
-/* Hardware self-test of the tcgen05 features the message kernel relies on (A operand read from
- * tensor memory, scale-input-d accumulate): writes three floats to out3_dev -- max |D_ts - D_ss|,
- * max |D_scaled - expected|, max |D_ss| (must be non-zero); the first two must be exactly 0. */
-int lb200_tc_selftest(float* out3_dev, void* stream);
+/* Hardware self-test of the tcgen05 features the message kernel relies on: writes five floats to
+ * out5_dev -- [0] max |D_ts - D_ss| (A operand read from tensor memory vs shared memory),
+ * [1] max |D_scaled - expected| (scale-input-d accumulate), [2] max |D_ss| (must be non-zero),
+ * [3] max |D_mn - D_ss| (B operand in the MN-major core-matrix layout), [4] max |D_sub 2^18 - D_ss|
+ * (fp16 subnormal inputs are not flushed); [0], [1], [3], [4] must be exactly 0. */
+int lb200_tc_selftest(float* out5_dev, void* stream);
 
 int64_t lb200_launch_count(void);
 int lb200_profile(int32_t enable);

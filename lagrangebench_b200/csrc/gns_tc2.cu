@@ -16,17 +16,21 @@
 //   yc     = hidden @ W2c + b2c                          (LayerNorm mean folded into W2c / b2c)
 //   e'     = scale * yc * rsqrt(mean(yc^2) + 1e-5) + offset
 //   e     <- e' + e ;  agg[rcv] = sum over the receiver's edges of e'  (ascending slot order)
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace lb {
 
 constexpr int k2Threads = 512;
 constexpr int k2Workers = 4;
+constexpr int k2DefaultVariant = 3;  // see launch_edge_mp_tc2
 constexpr int k2Tile = 32;  // edges per worker tile == one carry sub-tile (kEdgeTile)
 constexpr int k2WThreads = k2Threads / k2Workers;
 static_assert(k2Tile == kEdgeTile, "a tile is one carry sub-tile");
 // instruction descriptor: D=F32, A=B=F16, K-major, N=32, M=128
 constexpr uint32_t k2Idesc = (1u << 4) | ((uint32_t)(k2Tile >> 3) << 17) | (8u << 24);
+constexpr uint32_t k2IdescBMn = k2Idesc | (1u << 16);  // B operand MN-major (edge-contiguous core matrices)
 
 // TMEM columns: [0,256) weights (64 columns per 128x128 fp16 operand), [256,512) accumulators
 constexpr uint32_t k2ColW1Hi = 0, k2ColW1Lo = 64, k2ColW2Hi = 128, k2ColW2Lo = 192, k2ColAcc = 256;
@@ -35,12 +39,13 @@ constexpr uint32_t k2ColW1Hi = 0, k2ColW1Lo = 64, k2ColW2Hi = 128, k2ColW2Lo = 1
 constexpr uint32_t k2OffB = 0;                                      // [buf 2][hi | lo], kBBytes each
 constexpr uint32_t k2OffVec = k2OffB + 4 * kBBytes;                 // b2c[128], scale[128], offset[128]
 constexpr uint32_t k2IdxInts = 32 + 32 + 36;                        // sidx[32], rclamp[32], ridx[34 (+2)]
-constexpr uint32_t k2OffIdx = k2OffVec + 3 * 512;                   // [worker][buf][k2IdxInts]
-constexpr uint32_t k2OffRed = k2OffIdx + k2Workers * 2 * k2IdxInts * 4;  // [worker][4 warps][32]
-constexpr uint32_t k2OffInv = k2OffRed + k2Workers * 128 * 4;       // [16 warps][32]
-constexpr uint32_t k2OffEnd = k2OffInv + 16 * 32 * 4;               // [worker][buf] end masks
-constexpr uint32_t k2OffBar = k2OffEnd + 32;                        // mbarriers g1[4], g2[4]; tmem base
-constexpr uint32_t k2Smem = k2OffBar + 8 * 8 + 16;
+constexpr uint32_t k2OffIdx = k2OffVec + 3 * 512;                   // [worker][3 bufs][k2IdxInts]
+constexpr uint32_t k2OffRed = k2OffIdx + k2Workers * 3 * k2IdxInts * 4;  // [worker][2][4 warps][32]
+constexpr uint32_t k2OffInv = k2OffRed + k2Workers * 2 * 128 * 4;   // [16 warps][32]
+constexpr uint32_t k2OffEnd = k2OffInv + 16 * 32 * 4;               // [worker][4] end masks (3 used)
+constexpr uint32_t k2OffBar = k2OffEnd + 64;                        // mbarriers: done_g1[4], done_g2[4]
+constexpr uint32_t k2OffState = k2OffBar + 16 * 8;                  // arrival counters [worker][2]; tmem base
+constexpr uint32_t k2Smem = k2OffState + 48;
 
 // D[tmem] (+)= A[tmem] * B[smem desc]; call from ALL lanes of one warp
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate,
@@ -86,17 +91,31 @@ __device__ __forceinline__ void umma_ss_rescale11(uint32_t tmem_d, uint64_t ades
   }
 }
 
-// split-precision GEMM (K = 128) into ONE accumulator:
-//   acc = (A_hi B_lo' + A_lo' B_hi) * 2^-11 + A_hi B_hi        (lo' = lo * 2^11)
-__device__ __forceinline__ void issue_gemm_ts(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t acc) {
+// split-precision GEMM (K = 128) into ONE accumulator.  Weights' low halves carry 2^11 (lo' = lo * 2^11).
+//   b_scaled:  acc = (A_hi B_lo' + A_lo' B_hi) * 2^-11 + A_hi B_hi
+//   !b_scaled: acc = (A_lo' B_hi) * 2^-11 + A_hi B_lo + A_hi B_hi        (activation lo unscaled)
+template <bool kBScaled>
+__device__ __forceinline__ void issue_gemm_ts(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t acc,
+                                              uint32_t idesc) {
+  if (kBScaled) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    umma_ts(acc, a_hi + j * 8, umma_desc(b_lo + j * 2 * kLboB, kLboB), j > 0 ? 1u : 0u, k2Idesc);
+    for (int j = 0; j < 8; ++j)
+      umma_ts(acc, a_hi + j * 8, umma_desc(b_lo + j * 2 * kLboB, kLboB), j > 0 ? 1u : 0u, idesc);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) umma_ts(acc, a_lo + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, k2Idesc);
-  umma_ts_rescale11(acc, a_hi, umma_desc(b_hi, kLboB), k2Idesc);
+    for (int j = 0; j < 8; ++j) umma_ts(acc, a_lo + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
+    umma_ts_rescale11(acc, a_hi, umma_desc(b_hi, kLboB), idesc);
 #pragma unroll
-  for (int j = 1; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, k2Idesc);
+    for (int j = 1; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      umma_ts(acc, a_lo + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), j > 0 ? 1u : 0u, idesc);
+    umma_ts_rescale11(acc, a_hi, umma_desc(b_lo, kLboB), idesc);
+#pragma unroll
+    for (int j = 1; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_lo + j * 2 * kLboB, kLboB), 1u, idesc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
+  }
 }
 
 // 16 columns of this warp's 32 TMEM lanes -> registers (thread == lane)
@@ -138,6 +157,24 @@ __device__ __forceinline__ void tmem_st16(uint32_t ta, const uint32_t (&x)[16]) 
       : "memory");
 }
 
+__device__ __forceinline__ bool mbar_test(uint32_t mbar, uint32_t parity) {  // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(mbar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // One 128x128 fp16 operand, stored in global memory in the UMMA K-major layout [k/8][m][k%8]
@@ -159,28 +196,46 @@ __device__ __forceinline__ void weight_to_tmem(const uint4* op, int lane_row, ui
   }
 }
 
+// kMn:      the hidden operand of GEMM 2 is written edge-contiguous (MN-major core matrices): a thread
+//           packs 8 consecutive edges of its feature into ONE 16-byte store (fp16 pairs converted two
+//           at a time) instead of 8 two-byte stores; same bytes, LBO / SBO as the K-major edge operand.
+// kNoScale: the activations' low halves are stored unscaled (lo = fp16(x - hi), fp16 subnormals keep
+//           them exact enough); only the weights' low halves carry the 2^11 factor, so the split costs
+//           one multiply less per element.  GEMM order: A_lo' B_hi, rescale, A_hi B_lo, A_hi B_hi.
+// kContig:  a CTA takes a CONTIGUOUS range of tiles (its four workers interleave inside it) instead of
+//           every gridDim-th group: consecutive receivers share most of their senders, so the P rows a
+//           worker gathers are still in L1 from the tiles just before.
+// Measured and dropped (no gain, LDC-3D 28k): L1 prefetch of the P rows one phase ahead; "last
+// arriving warp issues the GEMM" instead of bar.sync (a dedicated 17th MMA warp is worse still: 5
+// warps on one SM sub-partition cap every thread at 96 registers); requesting the residual rows
+// before phase A.
+template <bool kMn, bool kNoScale, bool kContig>
 __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a) {
+  constexpr bool kPref = false, kLast = false, kEarlyEold = false;  // see above
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const int wk = warp >> 2;              // worker: 4 warps, a two-tile software pipeline
   const int q = warp & 3;                // TMEM lane quarter of this warp == warp index inside the worker
-  const int wtid = tid & (k2WThreads - 1);
   const int f = q * 32 + lane;           // output feature == TMEM lane of this thread
   float* vec = reinterpret_cast<float*>(smem + k2OffVec);
-  int* idx_base = reinterpret_cast<int*>(smem + k2OffIdx) + wk * 2 * k2IdxInts;
-  float* red = reinterpret_cast<float*>(smem + k2OffRed) + wk * 128;
+  int* idx_base = reinterpret_cast<int*>(smem + k2OffIdx) + wk * 3 * k2IdxInts;
+  float* red_base = reinterpret_cast<float*>(smem + k2OffRed) + wk * 256;
   float* invs = reinterpret_cast<float*>(smem + k2OffInv) + warp * 32;
-  uint32_t* endm = reinterpret_cast<uint32_t*>(smem + k2OffEnd) + wk * 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + k2OffBar + 64);
-  const uint32_t bar_g1 = sbase + k2OffBar + 8 * wk, bar_g2 = sbase + k2OffBar + 32 + 8 * wk;
+  uint32_t* endm = reinterpret_cast<uint32_t*>(smem + k2OffEnd) + wk * 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + k2OffState + 32);
+  const uint32_t bar_g1 = sbase + k2OffBar + 8 * wk, bar_g2 = bar_g1 + 32;
   const uint32_t bar_worker = 1 + wk;            // named barriers: the worker's 128 threads
   const uint32_t bar_ln = 1 + k2Workers + wk;
 
   const int E = a.rowptr[a.n];
-  const int n_tiles = (E + k2Tile - 1) / k2Tile;
-  if ((int)blockIdx.x * k2Workers >= n_tiles) return;
+  const int n_tiles_all = (E + k2Tile - 1) / k2Tile;
+  const int per_cta = (n_tiles_all + (int)gridDim.x - 1) / (int)gridDim.x;
+  // this CTA's tiles: [t_begin, n_tiles), its worker wk takes t_begin + wk + i * tile_stride
+  const int t_begin = kContig ? (int)blockIdx.x * per_cta : (int)blockIdx.x * k2Workers;
+  const int n_tiles = kContig ? min(n_tiles_all, t_begin + per_cta) : n_tiles_all;
+  if (t_begin >= n_tiles) return;
 
   if (tid == 0) {
     for (int w = 0; w < 2 * k2Workers; ++w) mbar_init(sbase + k2OffBar + 8 * w, 1);
@@ -190,7 +245,8 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < 3 * 128; i += k2Threads) vec[i] = a.vec_tc[i];
+  for (int i = tid; i < 3 * 128; i += blockDim.x) vec[i] = a.vec_tc[i];
+  if (tid < 2 * k2Workers) reinterpret_cast<int*>(smem + k2OffState)[tid] = 0;  // operand arrival counters
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -202,8 +258,11 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   __syncthreads();
   tc_fence_after();
 
-  const float b2c = vec[f], ln_scale = vec[128 + f], ln_offset = vec[256 + f];
   const uint32_t w1_hi = tmem + k2ColW1Hi, w1_lo = tmem + k2ColW1Lo, w2_hi = tmem + k2ColW2Hi, w2_lo = tmem + k2ColW2Lo;
+  const int tile_stride = kContig ? k2Workers : (int)gridDim.x * k2Workers;
+
+  {
+  const float b2c = vec[f], ln_scale = vec[128 + f], ln_offset = vec[256 + f];
   const uint32_t acc0 = tmem + k2ColAcc + wk * 64;                       // + buf * 32
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
   // this worker's 32 operand rows inside every K slab; buffer b at + b * 2 * kBBytes, lo at + kBBytes
@@ -211,28 +270,49 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   // this thread's element (k = f) of operand row `e` (edge):
   const uint32_t elem_off = b_off + (uint32_t)(f >> 3) * kLboB + (uint32_t)(f & 7) * 2;
   const int r0 = q * 8;  // this warp's 8 edge rows in phase A
-  const int tile_stride = gridDim.x * k2Workers;
   uint32_t ph1 = 0, ph2 = 0;
-  int pre_a = 0, pre_b = 0;  // next tile's indices: warp 0: rcv[i], rcv[i + 1]; warp 1: snd[i]; warp 2 lane 0: rcv[-1]
+  // next tile's indices, one per lane: every warp keeps snd / rcv of its lane's edge (gather
+  // prefetch); warp 0 also rcv[i + 1] (bucket ends), warp 2 lane 0 the receiver before the tile
+  int pre_s = 0, pre_r = -1, pre_b = 0;
+
+  // Every thread has written its part of an operand (and fenced it for the async proxy).  Returns
+  // true in the one warp that must now issue the GEMM.  kLast: arrival counter, the last warp
+  // issues and nobody waits; otherwise a worker-wide bar.sync and the first warp issues.
+  int* arrive_cnt = reinterpret_cast<int*>(smem + k2OffState) + wk * 2;
+  auto operand_ready = [&](int which) -> bool {
+    if (kLast) {
+      __threadfence_block();
+      __syncwarp();
+      int old = 0;
+      if (lane == 0) old = atomicAdd(arrive_cnt + which, 1);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if ((old & 3) != 3) return false;
+      __threadfence_block();
+      return true;
+    } else {
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(k2WThreads) : "memory");
+      return q == 0;
+    }
+  };
 
   auto prefetch_idx = [&](int tile) {
     if (tile >= n_tiles) return;
     const int64_t s = (int64_t)tile * k2Tile + lane;
+    if (kPref || q == 0) pre_r = s < E ? __ldg(a.rcv + s) : -1;
+    if (kPref || q == 1) pre_s = s < E ? __ldg(a.snd + s) : 0;
     if (q == 0) {
-      pre_a = s < E ? __ldg(a.rcv + s) : -1;
       pre_b = s + 1 < E ? __ldg(a.rcv + s + 1) : -3;
-    } else if (q == 1) {
-      pre_a = s < E ? __ldg(a.snd + s) : 0;
     } else if (q == 2) {
-      pre_a = (lane == 0 && s > 0) ? __ldg(a.rcv + s - 1) : -2;
+      pre_b = (lane == 0 && s > 0) ? __ldg(a.rcv + s - 1) : -2;
     }
   };
 
-  // ---- phase A(tile -> buffer b): indices -> smem, edge latents -> fp16 hi/lo operand, issue GEMM 1
-  auto phase_a = [&](int tile, int b) {
+  // ---- phase A(tile -> operand buffer b, index buffer ib): indices -> smem, edge latents -> fp16
+  //      hi/lo operand, GEMM 1
+  auto phase_a = [&](int tile, int b, int ib) {
     const int64_t slot0 = (int64_t)tile * k2Tile;
     const int rows = min(k2Tile, E - (int)slot0);
-    int* sidx = idx_base + b * k2IdxInts;
+    int* sidx = idx_base + ib * k2IdxInts;
     int* rclamp = sidx + 32;
     int* ridx = rclamp + 32;  // ridx[0] = receiver before the tile, ridx[1 + i] = edge i, ridx[1 + rows] = after
     float4 v[8];
@@ -248,20 +328,24 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
         for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + (int64_t)i * kLatent));
       }
     }
+    if (kPref && lane < rows) {  // this warp's 128-byte segments of the tile's P rows -> L1
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a.P + (int64_t)pre_s * (2 * kLatent) + q * 32));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a.P + (int64_t)pre_r * (2 * kLatent) + kLatent + q * 32));
+    }
     if (q == 0) {
       const bool ok = lane < rows;
-      const int r_here = pre_a, r_next = pre_b;
+      const int r_here = pre_r, r_next = pre_b;
       rclamp[lane] = max(r_here, 0);
       ridx[1 + lane] = ok ? r_here : (lane == rows ? -3 : -1);  // -3: "no edge after the tile"
       // last edge of its receiver bucket inside the tile (== carry sub-tile)
       const bool end = ok && (r_next != r_here || lane == 31 || lane == rows - 1);
       const uint32_t m = __ballot_sync(0xffffffffu, end);
-      if (lane == 0) endm[b] = m;
+      if (lane == 0) endm[ib] = m;
       if (lane == 31 && ok) ridx[1 + 32] = r_next;  // receiver just after a full tile
     } else if (q == 1) {
-      sidx[lane] = pre_a;
+      sidx[lane] = pre_s;
     } else if (q == 2) {
-      if (lane == 0) ridx[0] = pre_a;
+      if (lane == 0) ridx[0] = pre_b;
     }
     prefetch_idx(tile + tile_stride);
     unsigned char* hi_p = smem + k2OffB + b * 2 * kBBytes + wk * (k2Tile * 16);
@@ -270,8 +354,9 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     for (int i = 0; i < 8; ++i) {
       const __half2 h01 = __floats2half2_rn(v[i].x, v[i].y), h23 = __floats2half2_rn(v[i].z, v[i].w);
       const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-      const __half2 l01 = __floats2half2_rn((v[i].x - f01.x) * kLoScale, (v[i].y - f01.y) * kLoScale);
-      const __half2 l23 = __floats2half2_rn((v[i].z - f23.x) * kLoScale, (v[i].w - f23.y) * kLoScale);
+      constexpr float kS = kNoScale ? 1.0f : kLoScale;
+      const __half2 l01 = __floats2half2_rn((v[i].x - f01.x) * kS, (v[i].y - f01.y) * kS);
+      const __half2 l23 = __floats2half2_rn((v[i].z - f23.x) * kS, (v[i].w - f23.y) * kS);
       const uint32_t off = (uint32_t)(lane >> 1) * kLboB + (uint32_t)(r0 + i) * 16 + (uint32_t)(lane & 1) * 8;
       *reinterpret_cast<uint2*>(hi_p + off) =
           make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
@@ -280,18 +365,21 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     }
     fence_async_smem();
     tc_fence_before();
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(k2WThreads) : "memory");
-    if (q == 0) {  // the worker's first warp issues (one elected lane per instruction)
+    if (operand_ready(0)) {  // this warp issues (one elected lane per instruction)
       tc_fence_after();
       const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
-      issue_gemm_ts(w1_hi, w1_lo, bh, bh + kBBytes, acc0 + b * 32);
+      issue_gemm_ts<!kNoScale>(w1_hi, w1_lo, bh, bh + kBBytes, acc0 + b * 32, k2Idesc);
       umma_commit(bar_g1);
     }
   };
 
-  // ---- E1(tile in buffer b): hidden = relu(acc + P_s[snd] + P_r[rcv]) -> operand, issue GEMM 2
-  auto phase_e1 = [&](int b) {
-    const int* sp = idx_base + b * k2IdxInts;
+  // ---- E1(tile in buffers b / ib): hidden = relu(acc + P_s[snd] + P_r[rcv]) -> operand, GEMM 2
+  auto phase_e1 = [&](int b, int ib) {
+    if (kLast) {  // the indices were written by sibling warps before they announced their operand part
+      mbar_wait(bar_g1, ph1);
+      ph1 ^= 1;
+    }
+    const int* sp = idx_base + ib * k2IdxInts;
     const int* rp = sp + 32;
     float ps[32], pr[32];
 #pragma unroll
@@ -307,43 +395,73 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       pr[j0 + 2] = __ldg(a.P + (int64_t)r4.z * (2 * kLatent) + kLatent + f);
       pr[j0 + 3] = __ldg(a.P + (int64_t)r4.w * (2 * kLatent) + kLatent + f);
     }
-    mbar_wait(bar_g1, ph1);
-    ph1 ^= 1;
+    if (!kLast) {
+      mbar_wait(bar_g1, ph1);
+      ph1 ^= 1;
+    }
     tc_fence_after();
-    unsigned char* hi_p = smem + elem_off + b * 2 * kBBytes;
-    unsigned char* lo_p = hi_p + kBBytes;
+    constexpr float kS = kNoScale ? 1.0f : kLoScale;
+    if (kMn) {
+      // edge-contiguous operand: 8 edges of feature k = f are one 16-byte chunk at
+      // (k / 8) * LBO + (e / 8) * 128 + (k % 8) * 16 inside the worker's 512 bytes of every K slab
+      unsigned char* hi_p = smem + b_off + b * 2 * kBBytes + (uint32_t)(f >> 3) * kLboB + (uint32_t)(f & 7) * 16;
+      unsigned char* lo_p = hi_p + kBBytes;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float acc[16];
-      tmem_ld16(acc0 + b * 32 + lane_sel + h * 16, acc);
+      for (int h = 0; h < 2; ++h) {
+        float acc[16];
+        tmem_ld16(acc0 + b * 32 + lane_sel + h * 16, acc);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int e = h * 16 + j;
-        const float hval = fmaxf(acc[j] + ps[e] + pr[e], 0.f);
-        const __half hi = __float2half_rn(hval);
-        const __half lo = __float2half_rn((hval - __half2float(hi)) * kLoScale);
-        *reinterpret_cast<__half*>(hi_p + (uint32_t)e * 16) = hi;
-        *reinterpret_cast<__half*>(lo_p + (uint32_t)e * 16) = lo;
+        for (int g = 0; g < 2; ++g) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int p2 = 0; p2 < 4; ++p2) {
+            const int j = g * 8 + p2 * 2, e = h * 16 + j;
+            const float x0 = fmaxf(acc[j] + ps[e] + pr[e], 0.f);
+            const float x1 = fmaxf(acc[j + 1] + ps[e + 1] + pr[e + 1], 0.f);
+            const __half2 hh = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn((x0 - hf.x) * kS, (x1 - hf.y) * kS);
+            hw[p2] = *reinterpret_cast<const uint32_t*>(&hh);
+            lw[p2] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          const uint32_t off = (uint32_t)(h * 2 + g) * 128;
+          *reinterpret_cast<uint4*>(hi_p + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(lo_p + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+    } else {
+      unsigned char* hi_p = smem + elem_off + b * 2 * kBBytes;
+      unsigned char* lo_p = hi_p + kBBytes;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float acc[16];
+        tmem_ld16(acc0 + b * 32 + lane_sel + h * 16, acc);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int e = h * 16 + j;
+          const float hval = fmaxf(acc[j] + ps[e] + pr[e], 0.f);
+          const __half hi = __float2half_rn(hval);
+          const __half lo = __float2half_rn((hval - __half2float(hi)) * kS);
+          *reinterpret_cast<__half*>(hi_p + (uint32_t)e * 16) = hi;
+          *reinterpret_cast<__half*>(lo_p + (uint32_t)e * 16) = lo;
+        }
       }
     }
     fence_async_smem();
     tc_fence_before();
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(k2WThreads) : "memory");
-    if (q == 0) {
+    if (operand_ready(1)) {
       tc_fence_after();
       const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
-      issue_gemm_ts(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32);
+      issue_gemm_ts<!kNoScale>(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, kMn ? k2IdescBMn : k2Idesc);
       umma_commit(bar_g2);
     }
   };
 
-  // ---- E2(tile in buffer b): LayerNorm (mean folded into the weights), residual, store, segmented sum
-  auto phase_e2 = [&](int tile, int b) {
+  float eold[32];  // residual rows of the tile E2 finishes
+  auto load_eold = [&](int tile) {
     const int64_t slot0 = (int64_t)tile * k2Tile;
-    const int valid = min(k2Tile, E - (int)slot0);  // edges of this tile that exist (>= 1)
-    const int* ridx = idx_base + b * k2IdxInts + 64;
-    float* const erow = a.e + slot0 * kLatent + f;
-    float eold[32];
+    const int valid = min(k2Tile, E - (int)slot0);
+    const float* erow = a.e + slot0 * kLatent + f;
     if (valid == 32) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) eold[j] = erow[(int64_t)j * kLatent];
@@ -351,6 +469,16 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
 #pragma unroll
       for (int j = 0; j < 32; ++j) eold[j] = j < valid ? erow[(int64_t)j * kLatent] : 0.f;
     }
+  };
+
+  // ---- E2(tile in buffers b / ib): LayerNorm (mean folded into the weights), residual, store, segmented sum
+  auto phase_e2 = [&](int tile, int b, int ib) {
+    const int64_t slot0 = (int64_t)tile * k2Tile;
+    const int valid = min(k2Tile, E - (int)slot0);  // edges of this tile that exist (>= 1)
+    const int* ridx = idx_base + ib * k2IdxInts + 64;
+    float* const erow = a.e + slot0 * kLatent + f;
+    float* red = red_base + b * 128;
+    if (!kEarlyEold) load_eold(tile);
     mbar_wait(bar_g2, ph2);
     ph2 ^= 1;
     tc_fence_after();
@@ -373,7 +501,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       invs[lane] = 1.0f / sqrtf(var + 1e-5f);  // once per edge per warp (same value in the 4 warps)
     }
     __syncwarp();
-    const uint32_t emask = endm[b];
+    const uint32_t emask = endm[ib];
     const bool first_cont = ridx[0] == ridx[1];
     const bool last_cont = ridx[1 + valid] == ridx[valid];
     float* const cfirst = a.carry_first + (int64_t)tile * kLatent + f;
@@ -413,17 +541,23 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   };
 
   // two-tile software pipeline per worker:  A(k0) ; { E1(k) ; A(k+1) ; E2(k) }
-  const int k0 = blockIdx.x * k2Workers + wk;
+  // operand / accumulator buffers alternate (i & 1); the index buffers rotate over three because a
+  // sibling warp may still be finishing E2(k) when this warp writes the indices of tile k + 2... + 3
+  const int k0 = t_begin + wk;
   if (k0 < n_tiles) {
     prefetch_idx(k0);
-    phase_a(k0, 0);
+    phase_a(k0, 0, 0);
   }
-  int buf = 0;
+  int buf = 0, ib = 0;
   for (int tile = k0; tile < n_tiles; tile += tile_stride) {
-    phase_e1(buf);
-    if (tile + tile_stride < n_tiles) phase_a(tile + tile_stride, buf ^ 1);
-    phase_e2(tile, buf);
+    const int ib_next = ib == 2 ? 0 : ib + 1;
+    phase_e1(buf, ib);
+    if (kEarlyEold) load_eold(tile);
+    if (tile + tile_stride < n_tiles) phase_a(tile + tile_stride, buf ^ 1, ib_next);
+    phase_e2(tile, buf, ib);
     buf ^= 1;
+    ib = ib_next;
+  }
   }
   tc_fence_before();
   __syncthreads();
@@ -432,21 +566,40 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   }
 }
 
-int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
+template <bool kMn, bool kNoScale, bool kContig>
+static int launch_variant(const EdgeTcArgs& a, int grid, cudaStream_t s) {
   static int attr_rc = -1;
-  static int sms = 0;
-  if (attr_rc < 0) {
-    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem);
-    int dev = 0;
-    if (attr_rc == 0) attr_rc = (int)cudaGetDevice(&dev);
-    if (attr_rc == 0) attr_rc = (int)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  if (attr_rc < 0)
+    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel<kMn, kNoScale, kContig>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem);
   if (attr_rc) return attr_rc;
-  const int n_groups = cdiv(cdiv(e_cap, k2Tile), k2Workers);
-  const int grid = n_groups < sms ? n_groups : sms;
-  edge_mp_tc2_kernel<<<grid, k2Threads, k2Smem, s>>>(a);
+  edge_mp_tc2_kernel<kMn, kNoScale, kContig><<<grid, k2Threads, k2Smem, s>>>(a);
   LB_LAUNCHED(1);
   return 0;
+}
+
+int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
+  static int sms = 0, variant = -1;
+  if (variant < 0) {
+    int dev = 0;
+    int rc = (int)cudaGetDevice(&dev);
+    if (rc == 0) rc = (int)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (rc) return rc;
+    const char* e = getenv("LB200_TC2_VARIANT");  // bit 0: kMn, bit 1: kNoScale, bit 2: kContig
+    variant = e ? (atoi(e) & 7) : k2DefaultVariant;
+  }
+  const int n_groups = cdiv(cdiv(e_cap, k2Tile), k2Workers);
+  const int grid = n_groups < sms ? n_groups : sms;
+  switch (variant & 7) {
+    case 0: return launch_variant<false, false, false>(a, grid, s);
+    case 1: return launch_variant<true, false, false>(a, grid, s);
+    case 2: return launch_variant<false, true, false>(a, grid, s);
+    case 3: return launch_variant<true, true, false>(a, grid, s);
+    case 4: return launch_variant<false, false, true>(a, grid, s);
+    case 5: return launch_variant<true, false, true>(a, grid, s);
+    case 6: return launch_variant<false, true, true>(a, grid, s);
+    default: return launch_variant<true, true, true>(a, grid, s);
+  }
 }
 
 // =====================================================================================
@@ -455,12 +608,16 @@ int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
 //                                 vs the same A read from shared memory
 //   out[1] = max |D_scaled - (A B + (A B) 2^-11)|   scale-input-d = 11
 //   out[2] = max |D_ss|          (sanity: non-zero)
+//   out[3] = max |D_mn - D_ss|   B operand in the MN-major (edge-contiguous) core-matrix layout
+//   out[4] = max |D_sub 2^18 - D_ss|   B scaled by 2^-18 into fp16 subnormals (must not be flushed)
 __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(float* out) {
   __shared__ __align__(128) unsigned char sm_a[128 * 32];   // A: 128 rows x K 16 fp16, K-major core matrices
   __shared__ __align__(128) unsigned char sm_b[32 * 32];    // B: 32 rows x K 16
+  __shared__ __align__(128) unsigned char sm_b2[32 * 32];   // B, MN-major: (k/8)*512 + (n/8)*128 + (k%8)*16 + (n%8)*2
+  __shared__ __align__(128) unsigned char sm_b3[32 * 32];   // B * 2^-18 (fp16 subnormals), K-major
   __shared__ __align__(8) unsigned long long bar;
   __shared__ uint32_t slot;
-  __shared__ float red[3][4];
+  __shared__ float red[5][4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t mb = smem_u32(&bar);
   if (tid == 0) {
@@ -468,7 +625,7 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(float* out) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // A[m][k] = ((m * 7 + k * 3) % 17 - 8) / 8 ; B[n][k] = ((n * 5 + k) % 13 - 6) / 4   (exact in fp16)
@@ -484,6 +641,8 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(float* out) {
     if (tid < 32) {
       const float bv = (float)((tid * 5 + k) % 13 - 6) * 0.25f;
       *reinterpret_cast<__half*>(sm_b + (k >> 3) * 512 + tid * 16 + (k & 7) * 2) = __float2half_rn(bv);
+      *reinterpret_cast<__half*>(sm_b2 + (k >> 3) * 512 + (tid >> 3) * 128 + (k & 7) * 16 + (tid & 7) * 2) = __float2half_rn(bv);
+      *reinterpret_cast<__half*>(sm_b3 + (k >> 3) * 512 + tid * 16 + (k & 7) * 2) = __float2half_rn(bv * 3.814697265625e-06f);
     }
   }
   fence_async_smem();
@@ -507,45 +666,55 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(float* out) {
     umma_ts(tmem + 32, tmem + 96, bd, 0u, k2Idesc);     // D_ts  (columns 32..63)
     umma_f16(tmem + 64, ad, bd, 0u, k2Idesc);           // D_scaled = A B, then A B + D 2^-11
     umma_ss_rescale11(tmem + 64, ad, bd, k2Idesc);
+    umma_f16(tmem + 128, ad, umma_desc(smem_u32(sm_b2), 512), 0u, k2IdescBMn);  // D_mn
+    umma_f16(tmem + 160, ad, umma_desc(smem_u32(sm_b3), 512), 0u, k2Idesc);     // D_sub
     umma_commit(mb);
   }
   mbar_wait(mb, 0);
   tc_fence_after();
-  float dss[32], dts[32], dsc[32];
+  float dss[32], dts[32];
+  float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f, e4 = 0.f;
   tmem_ld32(tmem + lane_sel + 0, dss);
   tmem_ld32(tmem + lane_sel + 32, dts);
-  tmem_ld32(tmem + lane_sel + 64, dsc);
-  float e0 = 0.f, e1 = 0.f, e2 = 0.f;
   for (int j = 0; j < 32; ++j) {
     e0 = fmaxf(e0, fabsf(dts[j] - dss[j]));
-    e1 = fmaxf(e1, fabsf(dsc[j] - (dss[j] + dss[j] * (1.0f / 2048.0f))));
     e2 = fmaxf(e2, fabsf(dss[j]));
   }
+  tmem_ld32(tmem + lane_sel + 64, dts);
+  for (int j = 0; j < 32; ++j) e1 = fmaxf(e1, fabsf(dts[j] - (dss[j] + dss[j] * (1.0f / 2048.0f))));
+  tmem_ld32(tmem + lane_sel + 128, dts);
+  for (int j = 0; j < 32; ++j) e3 = fmaxf(e3, fabsf(dts[j] - dss[j]));
+  tmem_ld32(tmem + lane_sel + 160, dts);
+  for (int j = 0; j < 32; ++j) e4 = fmaxf(e4, fabsf(dts[j] * 262144.0f - dss[j]));
   for (int off = 16; off >= 1; off >>= 1) {
     e0 = fmaxf(e0, __shfl_xor_sync(0xffffffffu, e0, off));
     e1 = fmaxf(e1, __shfl_xor_sync(0xffffffffu, e1, off));
     e2 = fmaxf(e2, __shfl_xor_sync(0xffffffffu, e2, off));
+    e3 = fmaxf(e3, __shfl_xor_sync(0xffffffffu, e3, off));
+    e4 = fmaxf(e4, __shfl_xor_sync(0xffffffffu, e4, off));
   }
   if (lane == 0) {
     red[0][warp] = e0;
     red[1][warp] = e1;
     red[2][warp] = e2;
+    red[3][warp] = e3;
+    red[4][warp] = e4;
   }
   tc_fence_before();
   __syncthreads();
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i) out[i] = fmaxf(fmaxf(red[i][0], red[i][1]), fmaxf(red[i][2], red[i][3]));
+    for (int i = 0; i < 5; ++i) out[i] = fmaxf(fmaxf(red[i][0], red[i][1]), fmaxf(red[i][2], red[i][3]));
   }
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
   }
 }
 
 }  // namespace lb
 
-extern "C" int lb200_tc_selftest(float* out3_dev, void* stream) {
-  if (!out3_dev) return LB200_EINVAL;
-  lb::tc_selftest_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(out3_dev);
+extern "C" int lb200_tc_selftest(float* out5_dev, void* stream) {
+  if (!out5_dev) return LB200_EINVAL;
+  lb::tc_selftest_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(out5_dev);
   LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return 0;

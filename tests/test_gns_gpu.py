@@ -106,20 +106,23 @@ def test_tensor_core_kernel_matches_cuda_core_kernel():
 
 
 def test_tcgen05_selftest_tmem_operand_and_rescaled_accumulate():
-    """The two hardware features the pipelined message kernel relies on: the A operand read
+    """The hardware features (also: MN-major B operand, fp16 subnormal inputs) the pipelined message kernel relies on: the A operand read
     from tensor memory must equal the same operand read from shared memory, and
     scale-input-d = 11 must compute A B + D * 2^-11 exactly."""
     from lagrangebench_b200 import _cabi
 
     lib = _cabi.load()
-    out = torch.full((3,), -1.0, device="cuda")
+    out = torch.full((5,), -1.0, device="cuda")
     _cabi.check(lib.lb200_tc_selftest(_cabi.ptr(out), _cabi.stream()))
     torch.cuda.synchronize()
-    ts_vs_ss, scaled, mag = out.cpu().tolist()
-    print(f"tc selftest: |D_ts - D_ss| {ts_vs_ss:.3e}  |D_scaled - expected| {scaled:.3e}  max|D| {mag:.3f}")
+    ts_vs_ss, scaled, mag, mn_vs_k, subnormal = out.cpu().tolist()
+    print(f"tc selftest: |D_ts - D_ss| {ts_vs_ss:.3e}  |D_scaled - expected| {scaled:.3e}  max|D| {mag:.3f}  "
+          f"|D_mn - D_ss| {mn_vs_k:.3e}  |D_sub 2^18 - D_ss| {subnormal:.3e}")
     assert mag > 1.0
     assert ts_vs_ss == 0.0
     assert scaled <= 1e-6 * mag
+    assert mn_vs_k == 0.0      # B operand in the MN-major (edge-contiguous) layout
+    assert subnormal == 0.0    # fp16 subnormal inputs are honoured
 
 
 def test_pipelined_message_kernel_matches_first_tensor_core_kernel():
