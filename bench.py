@@ -37,17 +37,62 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled from a thread every
+    ~2 ms (the default timed region lasts tens of milliseconds); nvidia-smi -lms as the fallback."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                   0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, device_index):
         self.device_index = device_index
         self.proc = None
+        self.thread = None
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = False
+        self._nvml = None
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(device_index).uuid)
+                self._handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self._handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _poll(self):
+        nv = self._nvml
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM)))
+                bits = int(reasons_fn(self._handle))
+                for bit, name in self.REASON_BITS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self._nvml is not None:
+            import threading
+
+            self._stop = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
@@ -56,6 +101,12 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            sm = self.samples
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml, 2 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -79,7 +130,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def ncu_traffic(workload, kernel="edge_mp_tc_kernel"):
@@ -99,7 +150,8 @@ def build_workload(name, n_future, seed, dtype_name):
     from lagrangebench_b200 import synthetic
 
     npd = np.float64 if dtype_name == "float64" else np.float32
-    return synthetic.make_case(name, 6, n_future, seed, npd)
+    # quiet dynamics: a random-init network must not blow the cloud up over a long horizon (synthetic.py)
+    return synthetic.make_case(name, 6, n_future, seed, npd, quiet=True)
 
 
 def node_in_of(case_spec):
@@ -139,7 +191,7 @@ def oracle_steps(spec, n_steps, warmup, seed, dtype_name):
         lo, hi = np.array(force.lo), np.array(force.hi)
         ofn = lambda r: hi if r[force.axis] > force.threshold else lo  # noqa: E731
     case = ocase.case_builder(spec["box"], spec["metadata"], 6, cfg_neighbors={"multiplier": spec["multiplier"]},
-                              external_force_fn=ofn, dtype=npd)
+                              external_force_fn=ofn, dtype=npd, noise_std=0.0)
     d = spec["metadata"]["dim"]
     params = ogns.init_params(node_in_of(spec), d + 1, d, num_mp_steps=MP_STEPS, seed=seed, perturb=False)
     current = spec["positions"][:, :6].astype(npd)
@@ -246,7 +298,7 @@ def run_ours(args):
     d = spec["metadata"]["dim"]
     n = spec["positions"].shape[0]
     case = case_builder(spec["box"], spec["metadata"], 6, cfg_neighbors={"multiplier": spec["multiplier"]},
-                        external_force_fn=spec["force"], dtype=args.dtype)
+                        external_force_fn=spec["force"], dtype=args.dtype, noise_std=0.0)
     params = lbmodels.init_params(node_in_of(spec), d, 128, MP_STEPS, 16, seed=args.seed)
     model = GNS(d, 128, 2, MP_STEPS, 16)
     engine = RolloutEngine(case, model, params, steps_per_sync=max(K, W, 1))
@@ -255,43 +307,44 @@ def run_ours(args):
     targets_all = torch.as_tensor(spec["positions"][:, 6:6 + K + W]).permute(1, 0, 2).to(dev, tdt).contiguous()
     ptype = torch.as_tensor(spec["particle_type"]).to(dev)
 
-    # warm-up (also sizes the neighbor capacities and scratch)
+    # warm-up (also sizes the neighbor capacities and scratch, and captures the step graph)
     _, nbrs = engine.run(window, ptype, targets_all[:W], W)
     barrier()
     launches0 = lib.lb200_launch_count()
     realloc0 = engine.n_reallocations
-    lib.lb200_profile(1)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    preds, nbrs = engine.run(window, ptype, targets_all[W:W + K], K, nbrs)
+    preds, nbrs = engine.run(window, ptype, targets_all[W:W + K], K, nbrs)  # the API path: CUDA-graph replay
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     launches = lib.lb200_launch_count() - launches0
+    n_edges = nbrs.n_edges
+    assert torch.isfinite(preds).all(), "rollout diverged"
+    # kernel leg (roofline): the same K steps once more with a CUDA event pair around every message /
+    # node kernel launch on its launch stream (event records switch the graph replay off, so this
+    # pass runs the launches eagerly; its own wall time is reported in config)
     import ctypes as C
 
+    window_p = torch.as_tensor(spec["positions"][:, :6]).to(dev, tdt).contiguous()
+    _, nb_p = engine.run(window_p, ptype, targets_all[:W], W)
+    barrier()
+    lib.lb200_profile(1)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    engine.run(window_p, ptype, targets_all[W:W + K], K, nb_p)
+    g1.record()
+    barrier()
+    ms_prof = g0.elapsed_time(g1)
     kms = (C.c_double * 2)()
     kl = (C.c_int64 * 2)()
     _cabi.check(lib.lb200_profile_read(kms, kl))
     lib.lb200_profile(0)
-    n_edges = nbrs.n_edges
-    assert torch.isfinite(preds).all(), "rollout diverged"
-    # informational: the same K steps with per-kernel events off, so that lb200_rollout_steps replays
-    # them from a CUDA graph (the API path); reported in config, not as `value`
-    window_g = torch.as_tensor(spec["positions"][:, :6]).to(dev, tdt).contiguous()
-    _, nb_g = engine.run(window_g, ptype, targets_all[:W], W)
-    barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    engine.run(window_g, ptype, targets_all[W:W + K], K, nb_g)
-    g1.record()
-    barrier()
-    ms_graph = g0.elapsed_time(g1)
 
     # end-to-end leg: the same steps through the public per-step API with HOST buffers --
     # every step uploads that step's kinematic-target frame from pinned memory and reads the
@@ -303,7 +356,7 @@ def run_ours(args):
     window_e = torch.as_tensor(spec["positions"][:, :6]).to(dev, tdt).contiguous()
     engine_e = RolloutEngine(case, model, params, steps_per_sync=1)
     nb_e = None
-    for t in range(min(W, 3)):
+    for t in range(min(W, 3) + 4):  # untimed: also lets the per-step graphs (two alternating output buffers) be captured
         d_tgt[0].copy_(h_targets[t], non_blocking=True)
         p, nb_e = engine_e.run(window_e, ptype, d_tgt, 1, nb_e)
         h_out.copy_(p[0], non_blocking=True)
@@ -344,13 +397,16 @@ def run_ours(args):
                        if n_edges * 512 > 126e6 else "working set below L2 (edge latents %.0f MB): latency-bound"
                        % (n_edges * 512 / 1e6),
                        "reallocations_in_timed_region": engine.n_reallocations - realloc0,
-                       "ms_per_step_cuda_graph_replay": ms_graph / K},
+                       "step_loop": "device-resident, CUDA-graph replay (lb200_rollout_steps)",
+                       "dynamics": "quiet synthetic statistics (vel_std 2e-4 dx, acc_std 1e-7 dx, noise_std 0): a "
+                                   "random-init model keeps the cloud on its lattice for any K",
+                       "ms_per_step_kernel_leg_eager_with_events": ms_prof / K},
             "roofline": {"bound": "hbm", "kernel": "edge_mp_tc_kernel (tcgen05: fused gather + edge MLP + LayerNorm "
                          "+ residual + segmented sum)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(args.workload),
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_kind,
                          "avg_launch_ms": edge_ms_avg, "launches": int(kl[0]),
-                         "share_of_step": kms[0] / ms, "node_kernel_share_of_step": kms[1] / ms,
+                         "share_of_step": kms[0] / ms_prof, "node_kernel_share_of_step": kms[1] / ms_prof,
                          "fp32_tflops": flops_launch / (edge_ms_avg * 1e-3) / 1e12 if edge_ms_avg > 0 else 0.0},
             "e2e": {"value": world * n * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * d * esz,
                     "d2h_bytes_per_step": n * d * esz},

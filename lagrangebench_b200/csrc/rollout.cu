@@ -2,8 +2,12 @@
 // (lagrangebench/evaluate/rollout.py:125-169) for several consecutive steps, enqueued on one
 // stream with no host round trip.  The reference's blocking overflow read (rollout.py:135)
 // becomes a sticky device flag that turns the remaining integrate steps into no-ops.
+#include <stddef.h>
 #include <stdlib.h>
+#include <string.h>
 
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -62,6 +66,104 @@ __global__ void rollout_step_done_kernel(const int32_t* __restrict__ nbr_stats, 
 __global__ void rollout_init_kernel(int32_t* nbr_stats, int32_t* status) {
   nbr_stats[0] = nbr_stats[1] = nbr_stats[2] = nbr_stats[3] = 0;
   status[0] = status[1] = status[2] = status[3] = 0;
+}
+
+
+// ---- CUDA graphs of one rollout step, kept across lb200_rollout_steps calls
+struct GraphEntry {
+  std::string key;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches_per_step = 0;
+};
+static std::vector<GraphEntry> g_graphs;       // small LRU (front = oldest)
+static std::vector<std::string> g_seen_once;   // keys of single-step calls seen once, not yet captured
+constexpr size_t kMaxGraphs = 8, kMaxSeen = 32;
+
+template <typename T>
+static void key_put(std::string& k, const T& v) {
+  k.append(reinterpret_cast<const char*>(&v), sizeof(T));
+}
+
+// Everything the launches of a step depend on: the configuration (including the per-step weight
+// offset tables it points to), every device pointer, the stream.
+static std::string graph_key(const lb200_rollout_cfg* c, const void* w, const void* window, const void* ptype,
+                             const void* force, const void* targets, const void* preds, const void* idx,
+                             const void* status, const void* scratch, int64_t scratch_bytes, const void* stream) {
+  std::string k;
+  k.reserve(sizeof(*c) + 1024);
+  // raw bytes of the caller's struct (a struct assignment need not copy padding), with the two host
+  // pointers blanked: the tables they point to are appended instead
+  k.append(reinterpret_cast<const char*>(c), sizeof(*c));
+  const size_t off_gns = offsetof(lb200_rollout_cfg, gns);
+  memset(&k[off_gns + offsetof(lb200_gns_cfg, proc_edge)], 0, sizeof(void*));
+  memset(&k[off_gns + offsetof(lb200_gns_cfg, proc_node)], 0, sizeof(void*));
+  for (int m = 0; m < c->gns.num_mp_steps; ++m) {
+    key_put(k, c->gns.proc_edge[m]);
+    key_put(k, c->gns.proc_node[m]);
+  }
+  const void* ptrs[] = {w, window, ptype, force, targets, preds, idx, status, scratch, stream};
+  key_put(k, ptrs);
+  key_put(k, scratch_bytes);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  key_put(k, dev);
+  return k;
+}
+
+static GraphEntry* graph_find(const std::string& key) {
+  for (size_t i = 0; i < g_graphs.size(); ++i)
+    if (g_graphs[i].key == key) {
+      if (i + 1 != g_graphs.size()) {  // move to the back (most recently used)
+        GraphEntry e = std::move(g_graphs[i]);
+        g_graphs.erase(g_graphs.begin() + i);
+        g_graphs.push_back(std::move(e));
+      }
+      return &g_graphs.back();
+    }
+  return nullptr;
+}
+
+static bool graph_seen_before(const std::string& key) {
+  for (size_t i = 0; i < g_seen_once.size(); ++i)
+    if (g_seen_once[i] == key) {
+      g_seen_once.erase(g_seen_once.begin() + i);
+      return true;
+    }
+  if (g_seen_once.size() >= kMaxSeen) g_seen_once.erase(g_seen_once.begin());
+  g_seen_once.push_back(key);
+  return false;
+}
+
+// Capture one step (nothing executes) and keep the instantiated graph.  nullptr if capture fails.
+template <typename Step>
+static GraphEntry* graph_capture(const std::string& key, cudaStream_t s, Step& one_step) {
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  const int64_t launches0 = g_launches;
+  const int rc = one_step();
+  const int64_t per_step = g_launches - launches0;
+  g_launches = launches0;  // the captured launches did not execute
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(s, &graph);
+  const bool ok = rc == 0 && e == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) {
+    cudaGetLastError();  // capture failed: clear the error, the caller finishes eagerly
+    return nullptr;
+  }
+  if (g_graphs.size() >= kMaxGraphs) {
+    cudaGraphExecDestroy(g_graphs.front().exec);
+    g_graphs.erase(g_graphs.begin());
+  }
+  GraphEntry ent;
+  ent.key = key;
+  ent.exec = exec;
+  ent.launches_per_step = per_step;
+  g_graphs.push_back(std::move(ent));
+  return &g_graphs.back();
 }
 
 struct RolloutBufs {
@@ -173,35 +275,34 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
     { rollout_step_done_kernel<<<1, 1, 0, s>>>(b.stats, status_dev); LB_LAUNCHED(1); }
     return 0;
   };
+  // Launch-bound inner loop (about 100 launches per step): steps are replayed from a CUDA graph, which is
+  // kept across calls -- every argument a step depends on is part of the key, so a per-step caller
+  // (steps_per_sync = 1) replays too.  Not on the legacy default stream (capture is unsupported there),
+  // not while per-kernel events are on, not with a host halo callback inside the forward.
+  const bool graph_ok = s != nullptr && s != cudaStreamLegacy && !prof_enabled() && c->gns.halo_fn == nullptr &&
+                        getenv("LB200_NO_GRAPH") == nullptr;
   int t = 0;
-  if (n_steps > 0) {  // the first step runs eagerly (it also performs every one-time kernel attribute setup)
-    int rc = one_step();
-    if (rc) return rc;
-    t = 1;
-  }
-  // Launch-bound inner loop (about 100 launches per step): replay the remaining steps from a CUDA graph.
-  // Not on the legacy default stream (capture is unsupported there) and not while per-kernel events are on.
-  const bool want_graph = n_steps - t >= 2 && s != nullptr && s != cudaStreamLegacy && !prof_enabled() &&
-                          getenv("LB200_NO_GRAPH") == nullptr;
-  if (want_graph && cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
-    const int64_t launches0 = g_launches;
-    int rc = one_step();
-    const int64_t per_step = g_launches - launches0;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    cudaError_t e = cudaStreamEndCapture(s, &graph);
-    if (rc == 0 && e == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
-      g_launches = launches0;  // the captured launches did not execute
-      for (; t < n_steps; ++t) {
-        if (cudaGraphLaunch(exec, s) != cudaSuccess) break;
-        g_launches += per_step;
-      }
-    } else {
-      g_launches = launches0;
-      cudaGetLastError();  // capture failed: clear the error and finish eagerly
+  if (graph_ok && n_steps > 0) {
+    std::string key = graph_key(c, weights_dev, window_dev, ptype_dev, force_dev, targets_dev, preds_dev, idx_dev,
+                                status_dev, scratch_dev, scratch_bytes, stream);
+    GraphEntry* hit = graph_find(key);
+    if (!hit) {
+      // first sight of this configuration: one eager step (it also performs every one-time kernel attribute
+      // setup), then capture -- at once when the call has steps left to replay, else when the key comes back
+      int rc = one_step();
+      if (rc) return rc;
+      t = 1;
+      if (n_steps - t >= 2 || graph_seen_before(key)) hit = graph_capture(key, s, one_step);
     }
-    if (exec) cudaGraphExecDestroy(exec);
-    if (graph) cudaGraphDestroy(graph);
+    if (hit) {
+      for (; t < n_steps; ++t) {
+        if (cudaGraphLaunch(hit->exec, s) != cudaSuccess) {
+          cudaGetLastError();
+          break;
+        }
+        g_launches += hit->launches_per_step;
+      }
+    }
   }
   for (; t < n_steps; ++t) {
     int rc = one_step();

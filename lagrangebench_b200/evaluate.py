@@ -97,6 +97,9 @@ class RolloutEngine:
         self._cfg = None
         self._scratch = None
         self._stream = None  # non-default stream: lets lb200_rollout_steps replay steps from a CUDA graph
+        # persistent small buffers: stable device pointers let the library reuse its captured graph
+        self._status = None
+        self._ptype = (None, None)  # (source tensor, int32 device copy)
         self.n_reallocations = 0
         self.n_launch_calls = 0
 
@@ -127,7 +130,11 @@ class RolloutEngine:
         assert window.is_cuda and window.is_contiguous() and window.dtype == h["dtype"]
         n, isl, dim = window.shape
         dev = window.device
-        ptype = torch.as_tensor(particle_type).to(dev, torch.int32).contiguous()
+        if self._ptype[0] is particle_type and self._ptype[1].device == dev:
+            ptype = self._ptype[1]
+        else:
+            ptype = torch.as_tensor(particle_type).to(dev, torch.int32).contiguous()
+            self._ptype = (particle_type, ptype)
         if neighbors is None:
             neighbors = h["neighbor_fn"].allocate(window[:, -1].contiguous())
         self._configure(neighbors)
@@ -135,7 +142,9 @@ class RolloutEngine:
         if targets is not None:
             targets = targets.to(dev, window.dtype).contiguous()
             assert targets.shape == (n_steps, n, dim)
-        status = torch.zeros(4, dtype=torch.int32, device=dev)
+        if self._status is None or self._status.device != dev:
+            self._status = torch.zeros(4, dtype=torch.int32, device=dev)
+        status = self._status  # reset on the device at the start of every lb200_rollout_steps call
         if self._stream is None:
             self._stream = torch.cuda.Stream(device=dev)
         caller = torch.cuda.current_stream(dev)

@@ -101,6 +101,41 @@ def test_engine_equals_per_step_loop_bitwise():
     assert torch.equal(slow, fast)
 
 
+def test_per_step_calls_replay_the_cached_graph_bitwise():
+    """steps_per_sync = 1: from the second sight of the same buffers on, every call replays the step
+    graph the library kept; the trajectory must equal the one-call rollout bit for bit, and the
+    library must report the same number of kernel launches per step either way."""
+    from lagrangebench_b200 import _cabi
+
+    lib = _cabi.load()
+    n_steps = 8
+    c, ours, _, params, model, _ = _setup("tgv2d", "float32", n_steps)
+    ptype = torch.as_tensor(c["particle_type"]).cuda().to(torch.int32)
+    targets = torch.as_tensor(c["positions"][:, 6:6 + n_steps]).permute(1, 0, 2).cuda().contiguous()
+    w_ref = torch.as_tensor(c["positions"][:, :6]).cuda().contiguous()
+    l0 = lib.lb200_launch_count()
+    ref_engine = RolloutEngine(ours, model, params)
+    ref, _ = ref_engine.run(w_ref, ptype, targets, n_steps)
+    ref_launches = lib.lb200_launch_count() - l0 - ref_engine.n_launch_calls  # one init kernel per call
+    window = torch.as_tensor(c["positions"][:, :6]).cuda().contiguous()
+    engine = RolloutEngine(ours, model, params, steps_per_sync=1)
+    tgt1 = torch.empty_like(targets[:1])
+    out = torch.empty_like(ref)
+    nbrs = None
+    l0 = lib.lb200_launch_count()
+    for t in range(n_steps):
+        tgt1[0].copy_(targets[t])
+        p, nbrs = engine.run(window, ptype, tgt1, 1, nbrs)
+        out[t].copy_(p[0])
+        del p  # the caching allocator hands the same output block to the next call
+    got_launches = lib.lb200_launch_count() - l0 - engine.n_launch_calls
+    assert torch.equal(out, ref)
+    assert torch.equal(window, w_ref)
+    if ref_engine.n_reallocations == 0 and engine.n_reallocations == 0:
+        # replayed launches are counted like eager ones (bench.py's gpu_launches)
+        assert got_launches == ref_launches, (got_launches, ref_launches)
+
+
 def test_overflow_reallocates_and_retries_same_step():
     n_steps = 3
     c, ours, _, params, model, _ = _setup("tgv2d", "float32", n_steps)
