@@ -46,8 +46,9 @@ class ClockSampler:
     REASON_BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                    0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, device_index):
+    def __init__(self, device_index, period_s=0.002):
         self.device_index = device_index
+        self.period_s = period_s
         self.proc = None
         self.thread = None
         self.samples = []
@@ -83,7 +84,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period_s)
 
     def start(self):
         if self._nvml is not None:
@@ -106,7 +107,7 @@ class ClockSampler:
             self.thread.join(timeout=2)
             sm = self.samples
             return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
-                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml, 2 ms period"}
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml, %g ms period" % (self.period_s * 1e3)}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -133,7 +134,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
-def ncu_traffic(workload, kernel="edge_mp_tc_kernel"):
+def ncu_traffic(workload, kernel="edge_mp_tc2_kernel"):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     of this workload (profiles/ncu_traffic.json), or None when no capture exists for it."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -401,8 +402,8 @@ def run_ours(args):
                        "dynamics": "quiet synthetic statistics (vel_std 2e-4 dx, acc_std 1e-7 dx, noise_std 0): a "
                                    "random-init model keeps the cloud on its lattice for any K",
                        "ms_per_step_kernel_leg_eager_with_events": ms_prof / K},
-            "roofline": {"bound": "hbm", "kernel": "edge_mp_tc_kernel (tcgen05: fused gather + edge MLP + LayerNorm "
-                         "+ residual + segmented sum)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "edge_mp_tc2_kernel (tcgen05, weights in TMEM: fused gather + edge MLP + "
+                         "LayerNorm + residual + segmented sum)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(args.workload),
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_kind,
                          "avg_launch_ms": edge_ms_avg, "launches": int(kl[0]),
@@ -459,13 +460,15 @@ def run_sharded(args):
     params = lbmodels.init_params(node_in_of(spec), d, 128, MP_STEPS, 16, seed=args.seed)
     tdt = torch.float64 if args.dtype == "float64" else torch.float32
     dr = DistributedRollout(spec["box"], spec["metadata"], params, MP_STEPS, force=spec["force"], dtype=tdt,
-                            multiplier=spec["multiplier"]).scatter(spec["positions"], spec["particle_type"])
+                            multiplier=spec["multiplier"], noise_std=0.0, timing=True)
+    dr.scatter(spec["positions"], spec["particle_type"])
     for _ in range(W):
         dr.step()
     barrier()
+    dr.read_phase_ms()  # drop the warm-up marks
     launches0 = lib.lb200_launch_count()
     lib.lb200_profile(1)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, period_s=0.025)  # NVML queries share a driver lock with kernel launches
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -479,6 +482,14 @@ def run_sharded(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
+    phase_ms = {k: round(v, 3) for k, v in dr.read_phase_ms().items()}
+    phase_host_ms = {k: round(v, 3) for k, v in dr.phase_host_ms.items()}
+    dr.timing = False
+    if world > 1:  # every rank's table (device time between marks, host time enqueuing)
+        tables = [None] * world
+        dist.all_gather_object(tables, {"device": phase_ms, "host": phase_host_ms})
+    else:
+        tables = [{"device": phase_ms, "host": phase_host_ms}]
     launches = lib.lb200_launch_count() - launches0
     kms, kl = (C.c_double * 2)(), (C.c_int64 * 2)()
     _cabi.check(lib.lb200_profile_read(kms, kl))
@@ -522,8 +533,10 @@ def run_sharded(args):
                        "mp_steps": MP_STEPS, "latent": 128, "positions": args.dtype,
                        "multi_gpu": f"slab decomposition along axis {dr.axis}, halo exchange of P per MP step (NCCL)",
                        "halo_bytes_per_step_rank0": halo_bytes // max(K, 1),
+                       "phase_ms_per_rank": tables, "reallocations_rank0": dr.n_reallocations,
+                       "dynamics": "quiet synthetic statistics (synthetic.py), noise_std 0",
                        "l2": "inputs larger than L2 (edge latents %.0f MB per rank)" % (n_edges * 512 / 1e6)},
-            "roofline": {"bound": "hbm", "kernel": "edge_mp_tc_kernel (rank 0)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "edge_mp_tc2_kernel (rank 0)", "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "traffic": None, "peak_source": peak_kind, "avg_launch_ms": edge_ms_avg,
                          "launches": int(kl[0]), "share_of_step": kms[0] / ms,

@@ -97,29 +97,56 @@ def exchange_rows_sized(domain, to_left, to_right, n_from_left, n_from_right, gr
     return from_left, from_right
 
 
+def halo_sets(domain, coord, group=None):
+    """Indices (ascending) of the owned particles the left / right neighbour needs as ghosts, and
+    the number of ghosts this rank will receive from each side: ``(send_left, send_right,
+    n_from_left, n_from_right)``.  One host synchronisation (the all-gathered counts)."""
+    m_left, m_right = domain.halo_masks(coord)
+    if domain.world == 1:
+        e = torch.empty(0, dtype=torch.int64, device=coord.device)
+        return e, e, 0, 0
+    counts = torch.stack([m_left.sum(), m_right.sum()]).to(torch.int64)
+    all_counts = torch.empty(domain.world * 2, dtype=torch.int64, device=coord.device)
+    dist.all_gather_into_tensor(all_counts, counts, group=group)
+    all_counts = all_counts.view(domain.world, 2).cpu()
+    n_left, n_right = int(all_counts[domain.rank, 0]), int(all_counts[domain.rank, 1])
+    # stable sort of the negated mask: the selected rows first, in ascending index order -- no
+    # second synchronisation (nonzero() would need one per mask)
+    send_left = torch.argsort((~m_left).to(torch.uint8), stable=True)[:n_left]
+    send_right = torch.argsort((~m_right).to(torch.uint8), stable=True)[:n_right]
+    return send_left, send_right, int(all_counts[domain.left, 1]), int(all_counts[domain.right, 0])
+
+
 def migrate(domain, coord, tensors, group=None):
     """Move rows to the rank that now owns them.  ``tensors``: list of tensors with the same
-    leading dimension; returns the list with departed rows removed and arrivals appended."""
+    leading dimension; returns the list with departed rows removed and arrivals appended
+    (stayers keep their relative order).  One host synchronisation (the all-gathered counts)."""
     if domain.world == 1:
         return tensors
     dest = domain.owner(coord)
-    stay = dest == domain.rank
     dev = coord.device
     send_counts = torch.bincount(dest, minlength=domain.world)
     matrix = torch.empty(domain.world * domain.world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(matrix, send_counts.to(torch.int64), group=group)
     matrix = matrix.view(domain.world, domain.world).cpu()
-    out = []
-    ops, recv_bufs, keep = [], [], []
+    row = [int(v) for v in matrix[domain.rank]]
+    if sum(row) == row[domain.rank] and int(matrix[:, domain.rank].sum()) == row[domain.rank]:
+        return tensors  # nobody leaves, nobody arrives
+    order = torch.argsort(dest, stable=True)  # rows grouped by destination rank
+    starts = [0]
+    for v in row:
+        starts.append(starts[-1] + v)
+    out, ops, recv_bufs, keep = [], [], [], []
     for t in tensors:
-        keep.append(t[stay])
+        grouped = t.index_select(0, order)
+        keep.append(grouped[starts[domain.rank]:starts[domain.rank + 1]])
         bufs = []
         for r in range(domain.world):
             if r == domain.rank:
                 continue
-            n_send, n_recv = int(matrix[domain.rank, r]), int(matrix[r, domain.rank])
+            n_send, n_recv = row[r], int(matrix[r, domain.rank])
             if n_send:
-                ops.append(dist.P2POp(dist.isend, t[dest == r].contiguous(), r, group))
+                ops.append(dist.P2POp(dist.isend, grouped[starts[r]:starts[r + 1]].contiguous(), r, group))
             if n_recv:
                 b = t.new_empty((n_recv,) + tuple(t.shape[1:]))
                 ops.append(dist.P2POp(dist.irecv, b, r, group))
@@ -138,7 +165,7 @@ class DistributedRollout:
     kinematic particles -- the RPF-3D shape of BASELINE.json's 1 M-particle configuration)."""
 
     def __init__(self, box, metadata, params, num_mp_steps, force=None, axis=None, dtype=torch.float32,
-                 multiplier=1.25, input_seq_length=6, group=None):
+                 multiplier=1.25, input_seq_length=6, group=None, noise_std=3.0e-4, timing=False):
         _cabi.require_cuda()
         self.lib = _cabi.load()
         self.group = group
@@ -153,7 +180,7 @@ class DistributedRollout:
         npd = np.float64 if dtype == torch.float64 else np.float32
         self.radius = float(npd(metadata["default_connectivity_radius"]))
         self.domain = SlabDomain(self.box, self.axis, self.world, self.rank, self.radius)
-        self.stats = get_dataset_stats(metadata, False, 3.0e-4, npd)
+        self.stats = get_dataset_stats(metadata, False, noise_std, npd)
         self.multiplier = float(multiplier)
         self.isl = int(input_seq_length)
         self.force = force
@@ -167,6 +194,10 @@ class DistributedRollout:
         self.n_reallocations = 0
         self.edges_last = 0
         self._halo_error = None
+        # optional per-phase CUDA-event timing of step(): phase name -> [ms summed, count]
+        self.timing = bool(timing)
+        self._marks = []
+        self.phase_ms = {}
 
     # ------------------------------------------------------------------ state
     def scatter(self, positions, particle_type):
@@ -240,38 +271,67 @@ class DistributedRollout:
         except BaseException as exc:  # noqa: BLE001
             self._halo_error = exc
 
+    # ------------------------------------------------------------------ phase timing
+    def _mark(self, name):
+        if self.timing:
+            import time
+
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((name, ev, time.perf_counter()))
+
+    def read_phase_ms(self):
+        """Mean milliseconds per step of each phase since the last call (synchronises)."""
+        torch.cuda.synchronize()
+        acc = {}
+        for (n0, e0, c0), (n1, e1, c1) in zip(self._marks[:-1], self._marks[1:]):
+            if n1 == "begin":
+                continue
+            t = acc.setdefault(n1, [0.0, 0, 0.0])
+            t[0] += e0.elapsed_time(e1)
+            t[1] += 1
+            t[2] += (c1 - c0) * 1e3
+        self._marks = []
+        steps = max((v[1] for v in acc.values()), default=1)
+        self.phase_host_ms = {k: v[2] / steps for k, v in acc.items()}  # host wall time spent enqueuing the phase
+        return {k: v[0] / steps for k, v in acc.items()}
+
     # ------------------------------------------------------------------ one rollout step
     def step(self):
+        """Three host synchronisations per step: the ghost counts, the neighbor-list overflow flag
+        (re-allocate and retry, evaluate/rollout.py:135-151 -- local, before any neighbour is
+        involved) and the migration counts."""
         lib, dom, dev = self.lib, self.domain, self.window.device
         st = _cabi.stream()
         n_own = self.window.shape[0]
+        self._mark("begin")
         pos_own = self.window[:, -1].contiguous()
         self.halo_bytes = 0
         if self.world > 1:
-            m_left, m_right = dom.halo_masks(pos_own[:, self.axis])
-            self.send_left = m_left.nonzero().squeeze(1)
-            self.send_right = m_right.nonzero().squeeze(1)
-            g_left, g_right = exchange_rows(dom, pos_own.index_select(0, self.send_left),
-                                            pos_own.index_select(0, self.send_right), self.group)
-            if g_left.shape[0]:
-                g_left = g_left.clone()
-                g_left[:, self.axis] += dom.ghost_shift(True)
-            if g_right.shape[0]:
-                g_right = g_right.clone()
-                g_right[:, self.axis] += dom.ghost_shift(False)
-            pos_loc = torch.cat([pos_own, g_left, g_right], dim=0).contiguous()
-            self.n_ghost_left, self.n_ghost_right = g_left.shape[0], g_right.shape[0]
+            self.send_left, self.send_right, n_fl, n_fr = halo_sets(dom, pos_own[:, self.axis], self.group)
+            self._mark("ghost sets (counts all-gather, host sync)")
+            pos_loc = torch.empty((n_own + n_fl + n_fr, self.dim), dtype=pos_own.dtype, device=dev)
+            pos_loc[:n_own] = pos_own
+            exchange_rows_sized(dom, pos_own.index_select(0, self.send_left), pos_own.index_select(0, self.send_right),
+                                n_fl, n_fr, self.group, out_left=pos_loc[n_own:n_own + n_fl],
+                                out_right=pos_loc[n_own + n_fl:])
+            # place the neighbours' particles next to this slab across the periodic wrap
+            if n_fl and dom.ghost_shift(True) != 0.0:
+                pos_loc[n_own:n_own + n_fl, self.axis] += dom.ghost_shift(True)
+            if n_fr and dom.ghost_shift(False) != 0.0:
+                pos_loc[n_own + n_fl:, self.axis] += dom.ghost_shift(False)
+            self.n_ghost_left, self.n_ghost_right = n_fl, n_fr
         else:
             pos_loc = pos_own
             self.n_ghost_left = self.n_ghost_right = 0
         self.n_own = n_own
         n_loc = pos_loc.shape[0]
         self._ensure(n_loc)
-        # ---- neighbor list (re-allocate on first use or overflow, evaluate/rollout.py:135-151)
+        self._mark("ghost positions")
         while True:
             n_cap, e_cap, cell_cap = self._cap
             self.grid.n = n_loc
-            if e_cap == 0:
+            if e_cap == 0:  # first use, or after an overflow: size the list from this cloud (host read)
                 _cabi.check(lib.lb200_nbr_build(C.byref(self.grid), _cabi.ptr(pos_loc), 0, None, 0,
                                                 _cabi.ptr(self.stats_dev), _cabi.ptr(self.nbr_scratch),
                                                 self.nbr_scratch.numel(), st))
@@ -283,16 +343,17 @@ class DistributedRollout:
             _cabi.check(lib.lb200_nbr_build(C.byref(self.grid), _cabi.ptr(pos_loc), cell_cap, _cabi.ptr(self.idx),
                                             e_cap, _cabi.ptr(self.stats_dev), _cabi.ptr(self.nbr_scratch),
                                             self.nbr_scratch.numel(), st))
-            n_edges, _, overflow, _ = self.stats_dev.tolist()
-            if not overflow:
-                break
-            self.n_reallocations += 1
-            self._cap = (n_cap, 0, 0)
-            self.stats_dev.zero_()
-        self.edges_last = n_edges
+            n_edges, _, overflow, _ = self.stats_dev.tolist()  # host read (rollout.py:135): the retry is local,
+            if overflow:                                        # the neighbours are not involved yet
+                self.n_reallocations += 1
+                self._cap = (n_cap, 0, 0)
+                self.stats_dev.zero_()
+                continue
+            break
         _cabi.check(lib.lb200_csr_build(_cabi.ptr(self.idx), n_loc, e_cap, _cabi.ptr(self.rowptr), _cabi.ptr(self.perm),
                                         _cabi.ptr(self.snd), _cabi.ptr(self.rcv), _cabi.ptr(self.csr_scratch),
                                         self.csr_scratch.numel(), st))
+        self._mark("neighbor list + csr")
         # ---- features: nodes from the owned window, edges from the local (owned + ghost) positions
         fc = self._feature_cfg(n_own, self.isl)
         node_feat = torch.empty((n_own, fc.node_stride), dtype=torch.float32, device=dev)
@@ -300,6 +361,7 @@ class DistributedRollout:
         fe = self._feature_cfg(n_loc, 1)
         _cabi.check(lib.lb200_features(C.byref(fe), _cabi.ptr(pos_loc), None, _cabi.ptr(self.idx), e_cap, None,
                                        _cabi.ptr(self.edge_feat), st))
+        self._mark("features")
         # ---- forward with the per-MP-step halo exchange of P
         scratch = self._gns_buffers(n_loc, e_cap)
         cfg = gns_cfg(self.packed, n_loc, e_cap, fc.node_stride, fc.node_stride)
@@ -307,14 +369,15 @@ class DistributedRollout:
             cfg.n_owned = n_own
             cfg.halo_fn = C.cast(self._halo_cb, C.c_void_p).value
         out = torch.empty((n_own, self.dim), dtype=torch.float32, device=dev)
-        ptype_loc = self.ptype
         _cabi.check(lib.lb200_gns_forward(C.byref(cfg), _cabi.ptr(self.packed.blob), _cabi.ptr(node_feat),
-                                          _cabi.ptr(self.edge_feat), _cabi.ptr(ptype_loc), _cabi.ptr(self.rowptr),
+                                          _cabi.ptr(self.edge_feat), _cabi.ptr(self.ptype), _cabi.ptr(self.rowptr),
                                           _cabi.ptr(self.perm), _cabi.ptr(self.snd), _cabi.ptr(self.rcv), _cabi.ptr(out),
                                           _cabi.ptr(scratch), scratch.numel(), st))
         if self._halo_error is not None:
             err, self._halo_error = self._halo_error, None
             raise err
+        self._mark("forward (10 x [halo of P, message, node])")
+        self.edges_last = n_edges
         # ---- integrate the owned particles (periodic shift along every axis), then migrate
         ic = _cabi.IntegrateCfg()
         ic.n, ic.dim, ic.t_window = n_own, self.dim, self.isl
@@ -324,12 +387,14 @@ class DistributedRollout:
         ic.std = _cabi.vec3(self.stats["acceleration"]["std"], 1.0)
         _cabi.check(lib.lb200_integrate(C.byref(ic), _cabi.ptr(out), _cabi.ptr(self.window), _cabi.ptr(self.ptype), None,
                                         None, None, st))
+        self._mark("integrate")
         if self.world > 1:
             n = self.window.shape[0]
             w2, pt, gid = migrate(dom, self.window[:, -1, self.axis], [self.window.view(n, -1), self.ptype, self.gid],
                                   self.group)
             self.window = w2.view(-1, self.isl, self.dim).contiguous()
             self.ptype, self.gid = pt.contiguous(), gid.contiguous()
+            self._mark("migrate")
 
     def _feature_cfg(self, n, t_window):
         fc = _cabi.FeatureCfg()

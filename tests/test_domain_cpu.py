@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from lagrangebench_b200.domain import SlabDomain, exchange_rows, migrate
+from lagrangebench_b200.domain import SlabDomain, exchange_rows, exchange_rows_sized, halo_sets, migrate
 
 
 def test_slab_geometry():
@@ -47,11 +47,21 @@ def _worker(rank, world, port, results):
             right_dom = SlabDomain(box, 1, world, dom.right, 0.1)
             ok &= bool((from_left[:, 1] >= left_dom.hi - 0.1).all())   # the left neighbour's right face
             ok &= bool((from_right[:, 1] < right_dom.lo + 0.1).all())  # the right neighbour's left face
+        # --- the single-synchronisation variant used by the rollout: same sets, same order, known counts
+        s_l, s_r, n_fl, n_fr = halo_sets(dom, pos[:, 1])
+        ok &= torch.equal(s_l, m_l.nonzero().squeeze(1)) and torch.equal(s_r, m_r.nonzero().squeeze(1))
+        if world > 1:
+            fl2, fr2 = exchange_rows_sized(dom, payload.index_select(0, s_l), payload.index_select(0, s_r), n_fl, n_fr)
+            ok &= torch.equal(fl2, from_left) and torch.equal(fr2, from_right)
+        else:
+            ok &= n_fl == 0 and n_fr == 0
         # --- migration: move everything by +0.6 slab widths (periodic), rows are conserved
         moved = pos.clone()
         moved[:, 1] = torch.remainder(moved[:, 1] + 0.6 * dom.width, box[1])
         new_pos, new_gid = migrate(dom, moved[:, 1], [moved, gid])
         ok &= bool((dom.owner(new_pos[:, 1]) == rank).all())
+        stay = dom.owner(moved[:, 1]) == rank  # stayers first, in their original order
+        ok &= torch.equal(new_gid[:int(stay.sum())], gid[stay])
         ok &= new_pos.shape[0] == new_gid.shape[0]
         total = torch.tensor([new_gid.shape[0]])
         dist.all_reduce(total)
