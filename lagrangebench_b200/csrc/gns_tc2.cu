@@ -9,7 +9,9 @@
 //   * ONE accumulator per GEMM: the cross terms A_hi B_lo' + A_lo' B_hi (lo' = lo * 2^11) are
 //     accumulated first, and the first A_hi B_hi instruction rescales them with
 //     scale-input-d = 11 (D = A B + D * 2^-11), so the epilogues read half the TMEM columns;
-//   * the next tile's indices prefetched into registers one phase ahead.
+//   * the next tile's indices prefetched into registers one phase ahead, its fp32 rows brought in by
+//     one 16 KB bulk async copy (cp.async.bulk + mbarrier) a pipeline round ahead, and the P rows it
+//     will gather prefetched into L1.
 // Math, operand layouts and the carry protocol are those of v1 (gns_tc.cu).
 //
 //   hidden = relu(e @ W1e + P_s[snd] + P_r[rcv])        (P = per-node projections)
@@ -24,7 +26,7 @@ namespace lb {
 
 constexpr int k2Threads = 512;
 constexpr int k2Workers = 4;
-constexpr int k2DefaultVariant = 3;  // see launch_edge_mp_tc2
+constexpr int k2DefaultVariant = 15;  // see launch_edge_mp_tc2
 constexpr int k2Tile = 32;  // edges per worker tile == one carry sub-tile (kEdgeTile)
 constexpr int k2WThreads = k2Threads / k2Workers;
 static_assert(k2Tile == kEdgeTile, "a tile is one carry sub-tile");
@@ -43,9 +45,11 @@ constexpr uint32_t k2OffIdx = k2OffVec + 3 * 512;                   // [worker][
 constexpr uint32_t k2OffRed = k2OffIdx + k2Workers * 3 * k2IdxInts * 4;  // [worker][2][4 warps][32]
 constexpr uint32_t k2OffInv = k2OffRed + k2Workers * 2 * 128 * 4;   // [16 warps][32]
 constexpr uint32_t k2OffEnd = k2OffInv + 16 * 32 * 4;               // [worker][4] end masks (3 used)
-constexpr uint32_t k2OffBar = k2OffEnd + 64;                        // mbarriers: done_g1[4], done_g2[4]
+constexpr uint32_t k2OffBar = k2OffEnd + 64;                        // mbarriers: done_g1[4], done_g2[4], staged[4]
 constexpr uint32_t k2OffState = k2OffBar + 16 * 8;                  // arrival counters [worker][2]; tmem base
-constexpr uint32_t k2Smem = k2OffState + 48;
+constexpr uint32_t k2OffStage = ((k2OffState + 48 + 127) / 128) * 128;  // [worker] fp32 edge-latent tile (TMA bulk copy)
+constexpr uint32_t k2StageBytes = k2Tile * kLatent * 4;
+constexpr uint32_t k2Smem = k2OffStage + k2Workers * k2StageBytes;
 
 // D[tmem] (+)= A[tmem] * B[smem desc]; call from ALL lanes of one warp
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate,
@@ -202,16 +206,21 @@ __device__ __forceinline__ void weight_to_tmem(const uint4* op, int lane_row, ui
 // kNoScale: the activations' low halves are stored unscaled (lo = fp16(x - hi), fp16 subnormals keep
 //           them exact enough); only the weights' low halves carry the 2^11 factor, so the split costs
 //           one multiply less per element.  GEMM order: A_lo' B_hi, rescale, A_hi B_lo, A_hi B_hi.
-// kContig:  a CTA takes a CONTIGUOUS range of tiles (its four workers interleave inside it) instead of
-//           every gridDim-th group: consecutive receivers share most of their senders, so the P rows a
-//           worker gathers are still in L1 from the tiles just before.
-// Measured and dropped (no gain, LDC-3D 28k): L1 prefetch of the P rows one phase ahead; "last
-// arriving warp issues the GEMM" instead of bar.sync (a dedicated 17th MMA warp is worse still: 5
-// warps on one SM sub-partition cap every thread at 96 registers); requesting the residual rows
-// before phase A.
-template <bool kMn, bool kNoScale, bool kContig>
+// kStage:   the fp32 edge-latent tile of phase A arrives by ONE bulk async copy (cp.async.bulk, 16 KB,
+//           completion on an mbarrier) issued a whole pipeline round earlier -- right after the previous
+//           tile's operand was built -- instead of 8 LDG.128 per thread followed by a wait.
+// kPref:    prefetch.global.L1 of this warp's 128-byte segments of the tile's P rows, issued in phase A,
+//           one phase before E1 gathers them.  Pays only together with kStage: the edge tiles then no
+//           longer pass through L1 and the prefetched lines survive until they are used.
+// kNoAlloc: residual rows read with ld.global.L1::no_allocate -- measured slower, kept for A/B only.
+// Measured on LDC-3D 28k (us per launch): v1 176 -> TMEM weights + pipeline 149 -> kMn + kNoScale 141
+// -> kStage 138 -> kPref 131 (52 % of the measured HBM roofline).  Tried and dropped (no gain):
+// contiguous tile ranges per CTA; "last arriving warp issues the GEMM" instead of bar.sync (a dedicated
+// 17th MMA warp is worse still: 5 warps on one SM sub-partition cap every thread at 96 registers);
+// requesting the residual rows before phase A.
+template <bool kMn, bool kNoScale, bool kStage, bool kPref, bool kNoAlloc>
 __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a) {
-  constexpr bool kPref = false, kLast = false, kEarlyEold = false;  // see above
+  constexpr bool kLast = false, kEarlyEold = false, kContig = false;  // see above
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -225,7 +234,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   float* invs = reinterpret_cast<float*>(smem + k2OffInv) + warp * 32;
   uint32_t* endm = reinterpret_cast<uint32_t*>(smem + k2OffEnd) + wk * 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + k2OffState + 32);
-  const uint32_t bar_g1 = sbase + k2OffBar + 8 * wk, bar_g2 = bar_g1 + 32;
+  const uint32_t bar_g1 = sbase + k2OffBar + 8 * wk, bar_g2 = bar_g1 + 32, bar_st = bar_g1 + 64;
   const uint32_t bar_worker = 1 + wk;            // named barriers: the worker's 128 threads
   const uint32_t bar_ln = 1 + k2Workers + wk;
 
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   if (t_begin >= n_tiles) return;
 
   if (tid == 0) {
-    for (int w = 0; w < 2 * k2Workers; ++w) mbar_init(sbase + k2OffBar + 8 * w, 1);
+    for (int w = 0; w < 3 * k2Workers; ++w) mbar_init(sbase + k2OffBar + 8 * w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -270,7 +279,17 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   // this thread's element (k = f) of operand row `e` (edge):
   const uint32_t elem_off = b_off + (uint32_t)(f >> 3) * kLboB + (uint32_t)(f & 7) * 2;
   const int r0 = q * 8;  // this warp's 8 edge rows in phase A
-  uint32_t ph1 = 0, ph2 = 0;
+  uint32_t ph1 = 0, ph2 = 0, ph_st = 0;
+  // one elected lane of the calling warp: bulk-copy the tile's rows (contiguous in e) into the worker's stage
+  auto stage_rows = [&](int tile) {
+    if (tile >= n_tiles) return;
+    if (elect_one()) {
+      const int64_t s0 = (int64_t)tile * k2Tile;
+      const uint32_t bytes = (uint32_t)min(k2Tile, E - (int)s0) * (kLatent * 4);
+      mbar_expect_tx(bar_st, bytes);
+      bulk_g2s(sbase + k2OffStage + wk * k2StageBytes, a.e + s0 * kLatent, bytes, bar_st);
+    }
+  };
   // next tile's indices, one per lane: every warp keeps snd / rcv of its lane's edge (gather
   // prefetch); warp 0 also rcv[i + 1] (bucket ends), warp 2 lane 0 the receiver before the tile
   int pre_s = 0, pre_r = -1, pre_b = 0;
@@ -316,11 +335,18 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     int* rclamp = sidx + 32;
     int* ridx = rclamp + 32;  // ridx[0] = receiver before the tile, ridx[1 + i] = edge i, ridx[1 + rows] = after
     float4 v[8];
+    if (kStage) {
+      mbar_wait(bar_st, ph_st);  // the tile's rows were bulk-copied a pipeline round ago
+      ph_st ^= 1;
+      const float4* srow = reinterpret_cast<const float4*>(smem + k2OffStage + wk * k2StageBytes) + r0 * 32 + lane;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      v[i] = r0 + i < rows ? reinterpret_cast<const float4*>(a.e + (slot0 + r0 + i) * kLatent)[lane]
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-    {  // pull the rows of the tile after this one into L2
+      for (int i = 0; i < 8; ++i) v[i] = r0 + i < rows ? srow[i * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        v[i] = r0 + i < rows ? reinterpret_cast<const float4*>(a.e + (slot0 + r0 + i) * kLatent)[lane]
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      // pull the rows of the tile after this one into L2
       const int nt = tile + tile_stride;
       if (nt < n_tiles) {
         const float* nrow = a.e + ((int64_t)nt * k2Tile + r0) * kLatent + lane * 4;
@@ -370,6 +396,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
       issue_gemm_ts<!kNoScale>(w1_hi, w1_lo, bh, bh + kBBytes, acc0 + b * 32, k2Idesc);
       umma_commit(bar_g1);
+      if (kStage) stage_rows(tile + tile_stride);  // every warp is done reading the staged tile
     }
   };
 
@@ -462,12 +489,20 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     const int64_t slot0 = (int64_t)tile * k2Tile;
     const int valid = min(k2Tile, E - (int)slot0);
     const float* erow = a.e + slot0 * kLatent + f;
+    auto ld = [&](int j) -> float {
+      if (kNoAlloc) {  // streamed once: keep L1 for the gathered P rows
+        float v;
+        asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(erow + (int64_t)j * kLatent));
+        return v;
+      }
+      return erow[(int64_t)j * kLatent];
+    };
     if (valid == 32) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) eold[j] = erow[(int64_t)j * kLatent];
+      for (int j = 0; j < 32; ++j) eold[j] = ld(j);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) eold[j] = j < valid ? erow[(int64_t)j * kLatent] : 0.f;
+      for (int j = 0; j < 32; ++j) eold[j] = j < valid ? ld(j) : 0.f;
     }
   };
 
@@ -545,6 +580,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   // sibling warp may still be finishing E2(k) when this warp writes the indices of tile k + 2... + 3
   const int k0 = t_begin + wk;
   if (k0 < n_tiles) {
+    if (kStage && q == 0) stage_rows(k0);
     prefetch_idx(k0);
     phase_a(k0, 0, 0);
   }
@@ -566,14 +602,14 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   }
 }
 
-template <bool kMn, bool kNoScale, bool kContig>
+template <bool kMn, bool kNoScale, bool kStage, bool kPref, bool kNoAlloc>
 static int launch_variant(const EdgeTcArgs& a, int grid, cudaStream_t s) {
   static int attr_rc = -1;
   if (attr_rc < 0)
-    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel<kMn, kNoScale, kContig>,
+    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel<kMn, kNoScale, kStage, kPref, kNoAlloc>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem);
   if (attr_rc) return attr_rc;
-  edge_mp_tc2_kernel<kMn, kNoScale, kContig><<<grid, k2Threads, k2Smem, s>>>(a);
+  edge_mp_tc2_kernel<kMn, kNoScale, kStage, kPref, kNoAlloc><<<grid, k2Threads, k2Smem, s>>>(a);
   LB_LAUNCHED(1);
   return 0;
 }
@@ -585,20 +621,20 @@ int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
     int rc = (int)cudaGetDevice(&dev);
     if (rc == 0) rc = (int)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (rc) return rc;
-    const char* e = getenv("LB200_TC2_VARIANT");  // bit 0: kMn, bit 1: kNoScale, bit 2: kContig
-    variant = e ? (atoi(e) & 7) : k2DefaultVariant;
+    const char* e = getenv("LB200_TC2_VARIANT");  // bit 0: kMn, bit 1: kNoScale, bit 2: kStage, bit 3: kPref, bit 4: kNoAlloc
+    variant = e ? (atoi(e) & 31) : k2DefaultVariant;
   }
   const int n_groups = cdiv(cdiv(e_cap, k2Tile), k2Workers);
   const int grid = n_groups < sms ? n_groups : sms;
-  switch (variant & 7) {
-    case 0: return launch_variant<false, false, false>(a, grid, s);
-    case 1: return launch_variant<true, false, false>(a, grid, s);
-    case 2: return launch_variant<false, true, false>(a, grid, s);
-    case 3: return launch_variant<true, true, false>(a, grid, s);
-    case 4: return launch_variant<false, false, true>(a, grid, s);
-    case 5: return launch_variant<true, false, true>(a, grid, s);
-    case 6: return launch_variant<false, true, true>(a, grid, s);
-    default: return launch_variant<true, true, true>(a, grid, s);
+  switch (variant) {  // the combinations kept for A/B measurements
+    case 0: return launch_variant<false, false, false, false, false>(a, grid, s);
+    case 1: return launch_variant<true, false, false, false, false>(a, grid, s);
+    case 3: return launch_variant<true, true, false, false, false>(a, grid, s);
+    case 7: return launch_variant<true, true, true, false, false>(a, grid, s);
+    case 15: return launch_variant<true, true, true, true, false>(a, grid, s);
+    case 23: return launch_variant<true, true, true, false, true>(a, grid, s);
+    case 31: return launch_variant<true, true, true, true, true>(a, grid, s);
+    default: return launch_variant<true, true, true, false, false>(a, grid, s);
   }
 }
 
