@@ -7,7 +7,9 @@ kernels behind the C ABI of ``include/lb200.h``.
 """
 
 from . import models  # noqa: F401
+from . import data  # noqa: F401
 from .case_setup import CaseSetupFn, PiecewiseForce, case_builder  # noqa: F401
+from .data import H5Dataset  # noqa: F401
 from .defaults import defaults  # noqa: F401
 from .evaluate import MetricsComputer, RolloutEngine, averaged_metrics, eval_rollout, infer  # noqa: F401
 from .models import GNS  # noqa: F401
