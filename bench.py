@@ -234,7 +234,7 @@ def oracle_sample_spec(workload, n_target, seed, dtype_name):
     dims = full if n_target >= int(np.prod(full)) else sub_lattice_dims(full, n_target)
     if workload == "dam2d":
         dims = full  # masked lattice: always the full tank
-    return synthetic.make_case(workload, 6, 0, seed, npd, dims=dims), dims
+    return synthetic.make_case(workload, 6, 0, seed, npd, dims=dims, quiet=True), dims
 
 
 def run_reference_arm(args):
