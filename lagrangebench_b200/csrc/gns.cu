@@ -608,7 +608,31 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   ne.nxt = mlp_ptrs(w, c->proc_edge[0]);
   ne.h = h;
   ne.P = P;
-  { node_encoder_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeEnc, s>>>(ne); LB_LAUNCHED(1); }
+  if (c->edge_impl != 1 && c->enc_node.tc_w >= 0 && c->enc_node.tc_vec >= 0) {
+    // tensor-core encoder: the node-update kernel in encoder mode over the zero-padded input features
+    rc = launch_node_embed(node_feat_dev, c->node_in, c->node_stride, ptype_dev, w + c->embedding, c->embed_size,
+                           c->num_particle_types, n_own, h, s);
+    if (rc) return rc;
+    NodeTcArgs na;
+    na.n = n_own;
+    na.last = 0;
+    na.enc = 1;
+    na.dim = c->dim;
+    na.rowptr = rowptr_dev;
+    na.agg = nullptr;
+    na.carry_first = nullptr;
+    na.carry_last = nullptr;
+    na.w_tc = w + c->enc_node.tc_w;
+    na.vec_tc = w + c->enc_node.tc_vec;
+    na.h = h;
+    na.P = P;
+    na.out = out_dev;
+    rc = launch_node_mp_tc(na, s);
+    if (rc) return rc;
+  } else {
+    node_encoder_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeEnc, s>>>(ne);
+    LB_LAUNCHED(1);
+  }
 
   if (c->edge_impl != 1 && c->enc_edge.tc_w >= 0 && c->enc_edge.tc_vec >= 0 &&
       c->enc_edge.b0 == c->enc_edge.w0 + 4 * kLatent) {
@@ -628,7 +652,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     et.edge_feat = reinterpret_cast<const float4*>(edge_feat_dev);
     et.perm = perm_dev;
     et.enc_vec = w + c->enc_edge.w0;
-    rc = launch_edge_mp_tc(et, e_cap, s);
+    rc = edge_tc_version(c->edge_impl) == 2 ? launch_edge_mp_tc2(et, e_cap, s) : launch_edge_mp_tc(et, e_cap, s);
     if (rc) return rc;
   } else {
     EdgeEncArgs ee;
@@ -687,6 +711,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       NodeTcArgs nt_args;
       nt_args.n = n_own;
       nt_args.last = last;
+      nt_args.enc = 0;
       nt_args.dim = c->dim;
       nt_args.rowptr = rowptr_dev;
       nt_args.agg = agg;

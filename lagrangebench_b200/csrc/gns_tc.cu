@@ -350,6 +350,9 @@ constexpr uint32_t kNOffInv = kNOffRed + 3 * 4 * 4 * 32 * 4;                   /
 constexpr uint32_t kNOffBar = kNOffInv + 16 * 32 * 4;
 constexpr uint32_t kSmemNodeTc = kNOffBar + 48;
 
+// kEnc: node ENCODER mode (NodeTcArgs::enc) as a compile-time switch, so that the message-passing
+// instantiation is exactly the kernel it was before the encoder existed
+template <bool kEnc>
 __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -444,7 +447,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
       if (r < rows) {
         const int64_t v = row0 + r;
         hv = reinterpret_cast<const float4*>(a.h + v * kLatent)[lane];
-        const int e0 = a.rowptr[v], e1 = a.rowptr[v + 1];
+        const int e0 = kEnc ? 0 : a.rowptr[v], e1 = kEnc ? 0 : a.rowptr[v + 1];
         if (e1 > e0) {
           const int ta = e0 / kEdgeTile, tb = (e1 - 1) / kEdgeTile;
           if (ta == tb) {
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
         }
       }
       put_row4(bh_hi_p, bh_lo_p, r, hv);
-      put_row4(ba_hi_p, ba_lo_p, r, av);
+      if (!kEnc) put_row4(ba_hi_p, ba_lo_p, r, av);
     }
     fence_async_smem();
     tc_fence_before();
@@ -469,17 +472,21 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
       tc_fence_after();
       wait_w();
       issue_gemm(w_hi, w_lo, bh_hi, bh_lo, acc_hh, acc_x, kIdescN128, false);
-      umma_commit(bar_mid);
-      mbar_wait(bar_mid, ph_mid);
-      ph_mid ^= 1;
-      load_w(1);
-      wait_w();
-      tc_fence_after();
-      issue_gemm(w_hi, w_lo, ba_hi, ba_lo, acc_hh, acc_x, kIdescN128, true);
-      umma_commit(bar_mma);
+      if (kEnc) {  // encoder: a single input operand
+        umma_commit(bar_mma);
+      } else {
+        umma_commit(bar_mid);
+        mbar_wait(bar_mid, ph_mid);
+        ph_mid ^= 1;
+        load_w(1);
+        wait_w();
+        tc_fence_after();
+        issue_gemm(w_hi, w_lo, ba_hi, ba_lo, acc_hh, acc_x, kIdescN128, true);
+        umma_commit(bar_mma);
+      }
     }
     wait_all();
-    if (warp == 0) load_w(2);  // W2c streams in while the hidden layer is written
+    if (warp == 0) load_w(kEnc ? 1 : 2);  // W2c streams in while the hidden layer is written
     // hidden = relu(acc + b1) -> operand (over the aggregate, which is no longer needed)
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
@@ -501,9 +508,9 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
     float* const hrow = a.h + (row0 + g * 32) * kLatent + f;
     float hold[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) hold[j] = j < valid ? hrow[(int64_t)j * kLatent] : 0.f;
+    for (int j = 0; j < 32; ++j) hold[j] = (j < valid && !kEnc) ? hrow[(int64_t)j * kLatent] : 0.f;  // no residual in the encoder
     wait_all();
-    if (warp == 0) load_w(3);
+    if (warp == 0) load_w(kEnc ? 2 : 3);
     {
       float yc[32];
       float part;
@@ -550,7 +557,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
     }
     wait_all();
     if (!a.last) {
-      if (warp == 0) load_w(4);
+      if (warp == 0) load_w(kEnc ? 3 : 4);
       float* const prow = a.P + (row0 + g * 32) * (2 * kLatent) + f;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -613,6 +620,31 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
   }
 }
 
+__global__ void node_embed_kernel(const float* __restrict__ node_feat, int node_in, int node_stride,
+                                  const int32_t* __restrict__ ptype, const float* __restrict__ embedding, int embed,
+                                  int n_types, int n, float* __restrict__ h) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * kLatent) return;
+  const int64_t r = i / kLatent;
+  const int c = (int)(i % kLatent);
+  float v = 0.f;
+  if (c < node_in) {
+    v = node_feat[r * node_stride + c];
+  } else if (c < node_in + embed) {
+    const int t = min(max(ptype[r], 0), n_types - 1);
+    v = embedding[t * embed + (c - node_in)];
+  }
+  h[i] = v;
+}
+
+int launch_node_embed(const float* node_feat, int node_in, int node_stride, const int32_t* ptype, const float* embedding,
+                      int embed, int n_types, int n, float* h, cudaStream_t s) {
+  const int64_t total = (int64_t)n * kLatent;
+  node_embed_kernel<<<cdiv(total, 256), 256, 0, s>>>(node_feat, node_in, node_stride, ptype, embedding, embed, n_types, n, h);
+  LB_LAUNCHED(1);
+  return 0;
+}
+
 static int g_num_sms = 0;
 
 int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
@@ -641,7 +673,9 @@ int launch_node_mp_tc(const NodeTcArgs& a, cudaStream_t s) {
   static int attr_rc = -1;
   static int sms = 0;
   if (attr_rc < 0) {
-    attr_rc = (int)cudaFuncSetAttribute(node_mp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNodeTc);
+    attr_rc = (int)cudaFuncSetAttribute(node_mp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNodeTc);
+    if (attr_rc == 0)
+      attr_rc = (int)cudaFuncSetAttribute(node_mp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNodeTc);
     int dev = 0;
     if (attr_rc == 0) attr_rc = (int)cudaGetDevice(&dev);
     if (attr_rc == 0) attr_rc = (int)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -649,7 +683,12 @@ int launch_node_mp_tc(const NodeTcArgs& a, cudaStream_t s) {
   if (attr_rc) return attr_rc;
   const int n_tiles = cdiv(a.n, kNtTile);
   const int grid = n_tiles < sms ? n_tiles : sms;
-  { node_mp_tc_kernel<<<grid, kNtThreads, kSmemNodeTc, s>>>(a); LB_LAUNCHED(1); }
+  if (a.enc) {
+    node_mp_tc_kernel<true><<<grid, kNtThreads, kSmemNodeTc, s>>>(a);
+  } else {
+    node_mp_tc_kernel<false><<<grid, kNtThreads, kSmemNodeTc, s>>>(a);
+  }
+  LB_LAUNCHED(1);
   return 0;
 }
 

@@ -28,6 +28,8 @@ int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s);
 struct NodeTcArgs {
   int n;     // owned nodes
   int last;  // last message-passing step: decoder instead of the next step's projections
+  int enc;   // node ENCODER (gns.py:65-81): h holds the zero-padded input features, no aggregate, no
+             // residual; w_tc streams 4 operands W0pad^T, W1c^T, next W1s^T, next W1r^T (hi|lo each)
   int dim;
   const int32_t* rowptr;
   const float *agg, *carry_first, *carry_last;
@@ -37,5 +39,8 @@ struct NodeTcArgs {
 };
 
 int launch_node_mp_tc(const NodeTcArgs& a, cudaStream_t s);
+// h[i] = [node_feat[i] | embedding[ptype[i]] | 0 ...] (128 wide): the encoder's input operand
+int launch_node_embed(const float* node_feat, int node_in, int node_stride, const int32_t* ptype, const float* embedding,
+                      int embed, int n_types, int n, float* h, cudaStream_t s);
 
 }  // namespace lb

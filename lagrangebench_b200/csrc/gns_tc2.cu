@@ -218,7 +218,7 @@ __device__ __forceinline__ void weight_to_tmem(const uint4* op, int lane_row, ui
 // contiguous tile ranges per CTA; "last arriving warp issues the GEMM" instead of bar.sync (a dedicated
 // 17th MMA warp is worse still: 5 warps on one SM sub-partition cap every thread at 96 registers);
 // requesting the residual rows before phase A.
-template <bool kMn, bool kNoScale, bool kStage, bool kPref, bool kNoAlloc>
+template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref, bool kNoAlloc>
 __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a) {
   constexpr bool kLast = false, kEarlyEold = false, kContig = false;  // see above
   extern __shared__ __align__(128) unsigned char smem[];
@@ -261,7 +261,9 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   // resident weights -> TMEM: warp group g (4 warps, one per lane quarter) loads operand g
-  weight_to_tmem(reinterpret_cast<const uint4*>(a.w_tc) + wk * 2048, f, tmem + ((uint32_t)(q * 32) << 16) + wk * 64);
+  if (!kEnc || wk >= 2)  // encoder: w_tc holds only the second-layer pair, which goes to the W2 slots
+    weight_to_tmem(reinterpret_cast<const uint4*>(a.w_tc) + (kEnc ? wk - 2 : wk) * 2048, f,
+                   tmem + ((uint32_t)(q * 32) << 16) + wk * 64);
   tmem_st_wait();
   tc_fence_before();
   __syncthreads();
@@ -513,9 +515,19 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     const int* ridx = idx_base + ib * k2IdxInts + 64;
     float* const erow = a.e + slot0 * kLatent + f;
     float* red = red_base + b * 128;
-    if (!kEarlyEold) load_eold(tile);
-    mbar_wait(bar_g2, ph2);
-    ph2 ^= 1;
+    if (kEnc) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) eold[j] = 0.f;
+    } else if (!kEarlyEold) {
+      load_eold(tile);
+    }
+    if (kEnc && b) {  // encoder: two GEMMs of the same kind are in flight, one barrier per buffer
+      mbar_wait(bar_g1, ph1);
+      ph1 ^= 1;
+    } else {
+      mbar_wait(bar_g2, ph2);
+      ph2 ^= 1;
+    }
     tc_fence_after();
     float yc[32];
     float part;
@@ -536,9 +548,9 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       invs[lane] = 1.0f / sqrtf(var + 1e-5f);  // once per edge per warp (same value in the 4 warps)
     }
     __syncwarp();
-    const uint32_t emask = endm[ib];
-    const bool first_cont = ridx[0] == ridx[1];
-    const bool last_cont = ridx[1 + valid] == ridx[valid];
+    const uint32_t emask = kEnc ? 0u : endm[ib];
+    const bool first_cont = !kEnc && ridx[0] == ridx[1];
+    const bool last_cont = !kEnc && ridx[1 + valid] == ridx[valid];
     float* const cfirst = a.carry_first + (int64_t)tile * kLatent + f;
     float* const clast = a.carry_last + (int64_t)tile * kLatent + f;
     float seg_sum = 0.f;
@@ -556,7 +568,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
           if (kFull || j < valid) {
             erow[(int64_t)j * kLatent] = msg + eold[j];  // residual (gns.py:120-122)
             seg_sum += msg;
-            if ((emask >> j) & 1u) {  // bucket ends here (uniform across the worker)
+            if (!kEnc && ((emask >> j) & 1u)) {  // bucket ends here (uniform across the worker)
               float* dst = a.agg + (int64_t)ridx[1 + j] * kLatent + f;
               if (j == valid - 1 && last_cont) dst = clast;
               if (seg_first && first_cont) dst = cfirst;
@@ -575,6 +587,74 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     tc_fence_before();
   };
 
+  // ---- encoder (gns.py:65-81, edge MLP): e = LN(relu(feat W0 + b0) W1c + b1c).  The first layer
+  //      (K = dim + 1 <= 4) runs on CUDA cores straight into the operand of the one GEMM; no gather, no
+  //      residual, no aggregation.  Pipeline per worker: A'(k0) ; { A'(k+1) ; E2(k) }.
+  if constexpr (kEnc) {
+    const float ew0 = a.enc_vec[f], ew1 = a.enc_vec[128 + f], ew2 = a.enc_vec[256 + f], ew3 = a.enc_vec[384 + f];
+    const float eb0 = a.enc_vec[512 + f];
+    float4* feat_w = reinterpret_cast<float4*>(smem + k2OffStage) + warp * 32;  // this warp's copy of the tile's features
+    // edge features live in LIST order and are addressed through perm; the next tile's are fetched a phase ahead
+    auto feat_of = [&](int tile) -> float4 {
+      const int64_t s = (int64_t)tile * k2Tile + lane;
+      return (tile < n_tiles && s < E) ? a.edge_feat[a.perm[s]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 pre_f = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto phase_a_enc = [&](int tile, int b) {
+      feat_w[lane] = pre_f;
+      __syncwarp();
+      pre_f = feat_of(tile + tile_stride);
+      constexpr float kS = kNoScale ? 1.0f : kLoScale;
+      unsigned char* hi_p = smem + b_off + b * 2 * kBBytes + (uint32_t)(f >> 3) * kLboB + (uint32_t)(f & 7) * 16;
+      unsigned char* lo_p = hi_p + kBBytes;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int p2 = 0; p2 < 4; ++p2) {
+          float x[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const float4 ft = feat_w[g * 8 + p2 * 2 + t];
+            float v = ft.x * ew0;
+            v = fmaf(ft.y, ew1, v);
+            v = fmaf(ft.z, ew2, v);
+            v = fmaf(ft.w, ew3, v);
+            x[t] = fmaxf(v + eb0, 0.f);
+          }
+          const __half2 hh = __floats2half2_rn(x[0], x[1]);
+          const float2 hf = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn((x[0] - hf.x) * kS, (x[1] - hf.y) * kS);
+          hw[p2] = *reinterpret_cast<const uint32_t*>(&hh);
+          lw[p2] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        *reinterpret_cast<uint4*>(hi_p + g * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(lo_p + g * 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+      __syncwarp();  // feat_w is rewritten by the next call
+      fence_async_smem();
+      tc_fence_before();
+      if (operand_ready(1)) {
+        tc_fence_after();
+        const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
+        issue_gemm_ts<!kNoScale>(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, k2IdescBMn);
+        // A'(k+1) commits before E2(k) waits: each buffer has its own barrier, so that no barrier
+        // ever runs two phases ahead of a waiter (a parity wait cannot tell phase n from n + 2)
+        umma_commit(b ? bar_g1 : bar_g2);
+      }
+    };
+    const int k0 = t_begin + wk;
+    if (k0 < n_tiles) {
+      pre_f = feat_of(k0);
+      phase_a_enc(k0, 0);
+    }
+    int buf = 0;
+    for (int tile = k0; tile < n_tiles; tile += tile_stride) {
+      if (tile + tile_stride < n_tiles) phase_a_enc(tile + tile_stride, buf ^ 1);
+      phase_e2(tile, buf, 0);
+      buf ^= 1;
+    }
+  } else {
   // two-tile software pipeline per worker:  A(k0) ; { E1(k) ; A(k+1) ; E2(k) }
   // operand / accumulator buffers alternate (i & 1); the index buffers rotate over three because a
   // sibling warp may still be finishing E2(k) when this warp writes the indices of tile k + 2... + 3
@@ -595,6 +675,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     ib = ib_next;
   }
   }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -602,14 +683,14 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   }
 }
 
-template <bool kMn, bool kNoScale, bool kStage, bool kPref, bool kNoAlloc>
+template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref, bool kNoAlloc>
 static int launch_variant(const EdgeTcArgs& a, int grid, cudaStream_t s) {
   static int attr_rc = -1;
   if (attr_rc < 0)
-    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel<kMn, kNoScale, kStage, kPref, kNoAlloc>,
+    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref, kNoAlloc>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem);
   if (attr_rc) return attr_rc;
-  edge_mp_tc2_kernel<kMn, kNoScale, kStage, kPref, kNoAlloc><<<grid, k2Threads, k2Smem, s>>>(a);
+  edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref, kNoAlloc><<<grid, k2Threads, k2Smem, s>>>(a);
   LB_LAUNCHED(1);
   return 0;
 }
@@ -626,15 +707,16 @@ int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
   }
   const int n_groups = cdiv(cdiv(e_cap, k2Tile), k2Workers);
   const int grid = n_groups < sms ? n_groups : sms;
+  if (a.encoder) return launch_variant<true, true, true, false, false, false>(a, grid, s);
   switch (variant) {  // the combinations kept for A/B measurements
-    case 0: return launch_variant<false, false, false, false, false>(a, grid, s);
-    case 1: return launch_variant<true, false, false, false, false>(a, grid, s);
-    case 3: return launch_variant<true, true, false, false, false>(a, grid, s);
-    case 7: return launch_variant<true, true, true, false, false>(a, grid, s);
-    case 15: return launch_variant<true, true, true, true, false>(a, grid, s);
-    case 23: return launch_variant<true, true, true, false, true>(a, grid, s);
-    case 31: return launch_variant<true, true, true, true, true>(a, grid, s);
-    default: return launch_variant<true, true, true, false, false>(a, grid, s);
+    case 0: return launch_variant<false, false, false, false, false, false>(a, grid, s);
+    case 1: return launch_variant<false, true, false, false, false, false>(a, grid, s);
+    case 3: return launch_variant<false, true, true, false, false, false>(a, grid, s);
+    case 7: return launch_variant<false, true, true, true, false, false>(a, grid, s);
+    case 15: return launch_variant<false, true, true, true, true, false>(a, grid, s);
+    case 23: return launch_variant<false, true, true, true, false, true>(a, grid, s);
+    case 31: return launch_variant<false, true, true, true, true, true>(a, grid, s);
+    default: return launch_variant<false, true, true, true, false, false>(a, grid, s);
   }
 }
 

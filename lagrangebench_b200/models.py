@@ -134,6 +134,29 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
                                        np.asarray(ln["offset"], np.float32), np.asarray(nxt_l0["b"], np.float32),
                                        wd1.reshape(-1), bd1]))
 
+    def put_tc_node_encoder(mods, nxt_l0, o):
+        """Tensor-core operands of the node encoder (the node-update kernel in encoder mode): four
+        streamed 128x128 operands hi|lo -- W0^T zero-padded to 128 input columns, W1c^T (LayerNorm
+        mean folded in), then the two halves of the first edge MLP's first layer (-> P) -- and the
+        vector block b0 | b1c | ln_scale | ln_offset | b_next | (decoder slots unused)."""
+        l0, l1, ln = mods
+        w0 = np.asarray(l0["w"], dtype=np.float32)
+        w0pad = np.zeros((latent, latent), np.float32)
+        w0pad[:w0.shape[0]] = w0
+        w1 = np.asarray(l1["w"], dtype=np.float64)
+        b1 = np.asarray(l1["b"], dtype=np.float64)
+        w1c_t = (w1 - w1.mean(axis=1, keepdims=True)).astype(np.float32).T
+        b1c = (b1 - b1.mean()).astype(np.float32)
+        wn = np.asarray(nxt_l0["w"], dtype=np.float32)
+        halves = []
+        for m in (w0pad.T, w1c_t, wn[:latent].T, wn[latent:2 * latent].T):
+            hi, lo = umma_operand(m)
+            halves += [hi, lo]
+        o.tc_w = put(np.concatenate(halves).view(np.float32))
+        o.tc_vec = put(np.concatenate([np.asarray(l0["b"], np.float32), b1c, np.asarray(ln["scale"], np.float32),
+                                       np.asarray(ln["offset"], np.float32), np.asarray(nxt_l0["b"], np.float32),
+                                       np.zeros(3 * latent + 4, np.float32)]))
+
     def put_mlp(mods, in_rows, out_cols, rows_pad=None):
         l0, l1, ln = mods
         w0, w1 = np.asarray(l0["w"]), np.asarray(l1["w"])
@@ -168,6 +191,8 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
     enc_edge = put_mlp(enc_edge_mods, edge_in, latent, rows_pad=4)
     assert enc_edge.b0 == enc_edge.w0 + 4 * latent  # W0[4][128] | b0[128] contiguous (encoder kernel)
     put_tc_encoder(enc_edge_mods, enc_edge)
+    if node_in_total <= latent:
+        put_tc_node_encoder(enc_node_mods, _mlp_modules(params, "_processor", 0)[0], enc_node)
     proc_edge = (_cabi.MlpOff * num_mp_steps)()
     proc_node = (_cabi.MlpOff * num_mp_steps)()
     for m in range(num_mp_steps):
