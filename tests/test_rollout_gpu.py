@@ -207,4 +207,5 @@ def test_infer_from_an_hdf5_dataset_with_saved_checkpoint(tmp_path):
     mem = synthetic.SyntheticDataset("rpf2d", 6, n_rollout_steps=n_steps, n_trajs=n_traj, seed=5)
     from_memory = infer(model, case, mem, params=params, state=state, cfg_eval_infer=cfg, n_rollout_steps=n_steps)
     for k in ("rollout_0", "rollout_1"):
-        assert np.array_equal(np.asarray(from_files[k]["mse"]), np.asarray(from_memory[k]["mse"]))
+        a, b = torch.as_tensor(from_files[k]["mse"]).cpu(), torch.as_tensor(from_memory[k]["mse"]).cpu()
+        assert a.shape == (n_steps,) and torch.equal(a, b)
