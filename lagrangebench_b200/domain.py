@@ -117,18 +117,35 @@ def halo_sets(domain, coord, group=None):
     return send_left, send_right, int(all_counts[domain.left, 1]), int(all_counts[domain.right, 0])
 
 
-def migrate(domain, coord, tensors, group=None):
+def step_counts(domain, coord, group=None):
+    """ONE collective + ONE host synchronisation for everything a step needs to know about the other
+    ranks: the migration send-count matrix and every rank's (left, right) halo counts, both computed
+    from the same coordinates.  Returns ``(matrix (world, world), halo_counts (world, 2), m_left,
+    m_right)``; the halo part is only valid when the matrix is diagonal (nobody changes owner)."""
+    w = domain.world
+    m_left, m_right = domain.halo_masks(coord)
+    payload = torch.cat([torch.bincount(domain.owner(coord), minlength=w).to(torch.int64),
+                         torch.stack([m_left.sum(), m_right.sum()]).to(torch.int64)])
+    allp = torch.empty(w * (w + 2), dtype=torch.int64, device=coord.device)
+    dist.all_gather_into_tensor(allp, payload, group=group)
+    allp = allp.view(w, w + 2).cpu()
+    return allp[:, :w], allp[:, w:], m_left, m_right
+
+
+def migrate(domain, coord, tensors, group=None, matrix=None):
     """Move rows to the rank that now owns them.  ``tensors``: list of tensors with the same
     leading dimension; returns the list with departed rows removed and arrivals appended
-    (stayers keep their relative order).  One host synchronisation (the all-gathered counts)."""
+    (stayers keep their relative order).  One host synchronisation (the all-gathered counts),
+    none when the caller already holds the ``(world, world)`` send-count ``matrix`` (host tensor)."""
     if domain.world == 1:
         return tensors
     dest = domain.owner(coord)
     dev = coord.device
-    send_counts = torch.bincount(dest, minlength=domain.world)
-    matrix = torch.empty(domain.world * domain.world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(matrix, send_counts.to(torch.int64), group=group)
-    matrix = matrix.view(domain.world, domain.world).cpu()
+    if matrix is None:
+        send_counts = torch.bincount(dest, minlength=domain.world)
+        matrix = torch.empty(domain.world * domain.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(matrix, send_counts.to(torch.int64), group=group)
+        matrix = matrix.view(domain.world, domain.world).cpu()
     row = [int(v) for v in matrix[domain.rank]]
     if sum(row) == row[domain.rank] and int(matrix[:, domain.rank].sum()) == row[domain.rank]:
         return tensors  # nobody leaves, nobody arrives
@@ -192,6 +209,7 @@ class DistributedRollout:
         self._cap = None  # (n_cap, e_cap, cell_cap) the buffers are sized for
         self._halo_cb = _cabi.HALO_FN(self._halo_exchange)
         self.n_reallocations = 0
+        self.n_migrations = 0
         self.edges_last = 0
         self._halo_error = None
         # optional per-phase CUDA-event timing of step(): phase name -> [ms summed, count]
@@ -298,9 +316,9 @@ class DistributedRollout:
 
     # ------------------------------------------------------------------ one rollout step
     def step(self):
-        """Three host synchronisations per step: the ghost counts, the neighbor-list overflow flag
-        (re-allocate and retry, evaluate/rollout.py:135-151 -- local, before any neighbour is
-        involved) and the migration counts."""
+        """Two host synchronisations per step: one all-gather carrying the migration matrix and the
+        ghost counts, and the neighbor-list overflow flag (re-allocate and retry,
+        evaluate/rollout.py:135-151 -- local, before any neighbour is involved)."""
         lib, dom, dev = self.lib, self.domain, self.window.device
         st = _cabi.stream()
         n_own = self.window.shape[0]
@@ -308,8 +326,24 @@ class DistributedRollout:
         pos_own = self.window[:, -1].contiguous()
         self.halo_bytes = 0
         if self.world > 1:
-            self.send_left, self.send_right, n_fl, n_fr = halo_sets(dom, pos_own[:, self.axis], self.group)
-            self._mark("ghost sets (counts all-gather, host sync)")
+            # one collective: who changed owner during the last integrate, and the halo counts
+            matrix, halo_counts, m_left, m_right = step_counts(dom, pos_own[:, self.axis], self.group)
+            if int(matrix.sum()) != int(matrix.diagonal().sum()):  # somebody migrates (rare): move, then recount
+                n = self.window.shape[0]
+                w2, pt, gid = migrate(dom, self.window[:, -1, self.axis],
+                                      [self.window.view(n, -1), self.ptype, self.gid], self.group, matrix=matrix)
+                self.window = w2.view(-1, self.isl, self.dim).contiguous()
+                self.ptype, self.gid = pt.contiguous(), gid.contiguous()
+                n_own = self.window.shape[0]
+                pos_own = self.window[:, -1].contiguous()
+                self.n_migrations += 1
+                self.send_left, self.send_right, n_fl, n_fr = halo_sets(dom, pos_own[:, self.axis], self.group)
+            else:
+                n_left, n_right = int(halo_counts[dom.rank, 0]), int(halo_counts[dom.rank, 1])
+                self.send_left = torch.argsort((~m_left).to(torch.uint8), stable=True)[:n_left]
+                self.send_right = torch.argsort((~m_right).to(torch.uint8), stable=True)[:n_right]
+                n_fl, n_fr = int(halo_counts[dom.left, 1]), int(halo_counts[dom.right, 0])
+            self._mark("owner + ghost counts (one all-gather, host sync)")
             pos_loc = torch.empty((n_own + n_fl + n_fr, self.dim), dtype=pos_own.dtype, device=dev)
             pos_loc[:n_own] = pos_own
             exchange_rows_sized(dom, pos_own.index_select(0, self.send_left), pos_own.index_select(0, self.send_right),
@@ -388,13 +422,18 @@ class DistributedRollout:
         _cabi.check(lib.lb200_integrate(C.byref(ic), _cabi.ptr(out), _cabi.ptr(self.window), _cabi.ptr(self.ptype), None,
                                         None, None, st))
         self._mark("integrate")
+        # particles that left the slab move to their new owner at the start of the next step (or in
+        # settle()): its single collective carries the migration counts together with the halo counts
+
+    def settle(self):
+        """Hand particles that left their slab during the last step to their new owner (a step does
+        this lazily at its start)."""
         if self.world > 1:
             n = self.window.shape[0]
-            w2, pt, gid = migrate(dom, self.window[:, -1, self.axis], [self.window.view(n, -1), self.ptype, self.gid],
-                                  self.group)
+            w2, pt, gid = migrate(self.domain, self.window[:, -1, self.axis],
+                                  [self.window.view(n, -1), self.ptype, self.gid], self.group)
             self.window = w2.view(-1, self.isl, self.dim).contiguous()
             self.ptype, self.gid = pt.contiguous(), gid.contiguous()
-            self._mark("migrate")
 
     def _feature_cfg(self, n, t_window):
         fc = _cabi.FeatureCfg()

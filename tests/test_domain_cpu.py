@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from lagrangebench_b200.domain import SlabDomain, exchange_rows, exchange_rows_sized, halo_sets, migrate
+from lagrangebench_b200.domain import SlabDomain, exchange_rows, exchange_rows_sized, halo_sets, migrate, step_counts
 
 
 def test_slab_geometry():
@@ -55,10 +55,18 @@ def _worker(rank, world, port, results):
             ok &= torch.equal(fl2, from_left) and torch.equal(fr2, from_right)
         else:
             ok &= n_fl == 0 and n_fr == 0
+        # --- the merged collective of a rollout step: migration matrix + every rank's halo counts
+        matrix, halo_counts, m_l2, m_r2 = step_counts(dom, pos[:, 1])
+        ok &= int(matrix.sum()) == int(matrix.diagonal().sum())  # everybody is at home
+        ok &= int(matrix[rank, rank]) == n and torch.equal(m_l2, m_l) and torch.equal(m_r2, m_r)
+        ok &= (int(halo_counts[rank, 0]), int(halo_counts[rank, 1])) == (int(m_l.sum()), int(m_r.sum()))
+        ok &= (int(halo_counts[dom.left, 1]), int(halo_counts[dom.right, 0])) == (n_fl, n_fr) or world == 1
         # --- migration: move everything by +0.6 slab widths (periodic), rows are conserved
         moved = pos.clone()
         moved[:, 1] = torch.remainder(moved[:, 1] + 0.6 * dom.width, box[1])
-        new_pos, new_gid = migrate(dom, moved[:, 1], [moved, gid])
+        matrix2 = step_counts(dom, moved[:, 1])[0]
+        ok &= world == 1 or int(matrix2.sum()) != int(matrix2.diagonal().sum())
+        new_pos, new_gid = migrate(dom, moved[:, 1], [moved, gid], matrix=matrix2 if world > 1 else None)
         ok &= bool((dom.owner(new_pos[:, 1]) == rank).all())
         stay = dom.owner(moved[:, 1]) == rank  # stayers first, in their original order
         ok &= torch.equal(new_gid[:int(stay.sum())], gid[stay])
