@@ -120,16 +120,22 @@ def halo_sets(domain, coord, group=None):
 def step_counts(domain, coord, group=None):
     """ONE collective + ONE host synchronisation for everything a step needs to know about the other
     ranks: the migration send-count matrix and every rank's (left, right) halo counts, both computed
-    from the same coordinates.  Returns ``(matrix (world, world), halo_counts (world, 2), m_left,
-    m_right)``; the halo part is only valid when the matrix is diagonal (nobody changes owner)."""
+    from the same coordinates.  Returns ``(matrix (world, world), halo_counts (world, 2), order_left,
+    order_right)`` -- ``order_x[:halo_counts[rank, k]]`` are the ascending indices of the rows the
+    left / right neighbour needs; the halo part is only valid when the matrix is diagonal (nobody
+    changes owner)."""
     w = domain.world
     m_left, m_right = domain.halo_masks(coord)
     payload = torch.cat([torch.bincount(domain.owner(coord), minlength=w).to(torch.int64),
                          torch.stack([m_left.sum(), m_right.sum()]).to(torch.int64)])
     allp = torch.empty(w * (w + 2), dtype=torch.int64, device=coord.device)
     dist.all_gather_into_tensor(allp, payload, group=group)
+    # enqueued BEFORE the host read, so that the device is not idle while the host launches them:
+    # selected rows first, in ascending index order (the caller slices [:count])
+    order_left = torch.argsort((~m_left).to(torch.uint8), stable=True)
+    order_right = torch.argsort((~m_right).to(torch.uint8), stable=True)
     allp = allp.view(w, w + 2).cpu()
-    return allp[:, :w], allp[:, w:], m_left, m_right
+    return allp[:, :w], allp[:, w:], order_left, order_right
 
 
 def migrate(domain, coord, tensors, group=None, matrix=None):
@@ -327,7 +333,7 @@ class DistributedRollout:
         self.halo_bytes = 0
         if self.world > 1:
             # one collective: who changed owner during the last integrate, and the halo counts
-            matrix, halo_counts, m_left, m_right = step_counts(dom, pos_own[:, self.axis], self.group)
+            matrix, halo_counts, order_left, order_right = step_counts(dom, pos_own[:, self.axis], self.group)
             if int(matrix.sum()) != int(matrix.diagonal().sum()):  # somebody migrates (rare): move, then recount
                 n = self.window.shape[0]
                 w2, pt, gid = migrate(dom, self.window[:, -1, self.axis],
@@ -340,8 +346,7 @@ class DistributedRollout:
                 self.send_left, self.send_right, n_fl, n_fr = halo_sets(dom, pos_own[:, self.axis], self.group)
             else:
                 n_left, n_right = int(halo_counts[dom.rank, 0]), int(halo_counts[dom.rank, 1])
-                self.send_left = torch.argsort((~m_left).to(torch.uint8), stable=True)[:n_left]
-                self.send_right = torch.argsort((~m_right).to(torch.uint8), stable=True)[:n_right]
+                self.send_left, self.send_right = order_left[:n_left], order_right[:n_right]
                 n_fl, n_fr = int(halo_counts[dom.left, 1]), int(halo_counts[dom.right, 0])
             self._mark("owner + ghost counts (one all-gather, host sync)")
             pos_loc = torch.empty((n_own + n_fl + n_fr, self.dim), dtype=pos_own.dtype, device=dev)

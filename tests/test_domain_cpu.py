@@ -56,9 +56,10 @@ def _worker(rank, world, port, results):
         else:
             ok &= n_fl == 0 and n_fr == 0
         # --- the merged collective of a rollout step: migration matrix + every rank's halo counts
-        matrix, halo_counts, m_l2, m_r2 = step_counts(dom, pos[:, 1])
+        matrix, halo_counts, o_l, o_r = step_counts(dom, pos[:, 1])
         ok &= int(matrix.sum()) == int(matrix.diagonal().sum())  # everybody is at home
-        ok &= int(matrix[rank, rank]) == n and torch.equal(m_l2, m_l) and torch.equal(m_r2, m_r)
+        ok &= int(matrix[rank, rank]) == n
+        ok &= torch.equal(o_l[:int(m_l.sum())], s_l) and torch.equal(o_r[:int(m_r.sum())], s_r)
         ok &= (int(halo_counts[rank, 0]), int(halo_counts[rank, 1])) == (int(m_l.sum()), int(m_r.sum()))
         ok &= (int(halo_counts[dom.left, 1]), int(halo_counts[dom.right, 0])) == (n_fl, n_fr) or world == 1
         # --- migration: move everything by +0.6 slab widths (periodic), rows are conserved
