@@ -46,7 +46,7 @@ constexpr uint32_t k2OffRed = k2OffIdx + k2Workers * 3 * k2IdxInts * 4;  // [wor
 constexpr uint32_t k2OffInv = k2OffRed + k2Workers * 2 * 128 * 4;   // [16 warps][32]
 constexpr uint32_t k2OffEnd = k2OffInv + 16 * 32 * 4;               // [worker][4] end masks (3 used)
 constexpr uint32_t k2OffBar = k2OffEnd + 64;                        // mbarriers: done_g1[4], done_g2[4], staged[4]
-constexpr uint32_t k2OffState = k2OffBar + 16 * 8;                  // arrival counters [worker][2]; tmem base
+constexpr uint32_t k2OffState = k2OffBar + 16 * 8;                  // tmem base address
 constexpr uint32_t k2OffStage = ((k2OffState + 48 + 127) / 128) * 128;  // [worker] fp32 edge-latent tile (TMA bulk copy)
 constexpr uint32_t k2StageBytes = k2Tile * kLatent * 4;
 constexpr uint32_t k2Smem = k2OffStage + k2Workers * k2StageBytes;
@@ -212,15 +212,13 @@ __device__ __forceinline__ void weight_to_tmem(const uint4* op, int lane_row, ui
 // kPref:    prefetch.global.L1 of this warp's 128-byte segments of the tile's P rows, issued in phase A,
 //           one phase before E1 gathers them.  Pays only together with kStage: the edge tiles then no
 //           longer pass through L1 and the prefetched lines survive until they are used.
-// kNoAlloc: residual rows read with ld.global.L1::no_allocate -- measured slower, kept for A/B only.
 // Measured on LDC-3D 28k (us per launch): v1 176 -> TMEM weights + pipeline 149 -> kMn + kNoScale 141
 // -> kStage 138 -> kPref 131 (52 % of the measured HBM roofline).  Tried and dropped (no gain):
 // contiguous tile ranges per CTA; "last arriving warp issues the GEMM" instead of bar.sync (a dedicated
 // 17th MMA warp is worse still: 5 warps on one SM sub-partition cap every thread at 96 registers);
-// requesting the residual rows before phase A.
-template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref, bool kNoAlloc>
+// requesting the residual rows before phase A; ld.global.L1::no_allocate for the residual rows (slower).
+template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref>
 __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a) {
-  constexpr bool kLast = false, kEarlyEold = false, kContig = false;  // see above
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -239,11 +237,9 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   const uint32_t bar_ln = 1 + k2Workers + wk;
 
   const int E = a.rowptr[a.n];
-  const int n_tiles_all = (E + k2Tile - 1) / k2Tile;
-  const int per_cta = (n_tiles_all + (int)gridDim.x - 1) / (int)gridDim.x;
-  // this CTA's tiles: [t_begin, n_tiles), its worker wk takes t_begin + wk + i * tile_stride
-  const int t_begin = kContig ? (int)blockIdx.x * per_cta : (int)blockIdx.x * k2Workers;
-  const int n_tiles = kContig ? min(n_tiles_all, t_begin + per_cta) : n_tiles_all;
+  const int n_tiles = (E + k2Tile - 1) / k2Tile;
+  // this CTA's tiles: worker wk takes t_begin + wk + i * tile_stride
+  const int t_begin = (int)blockIdx.x * k2Workers;
   if (t_begin >= n_tiles) return;
 
   if (tid == 0) {
@@ -255,7 +251,6 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = tid; i < 3 * 128; i += blockDim.x) vec[i] = a.vec_tc[i];
-  if (tid < 2 * k2Workers) reinterpret_cast<int*>(smem + k2OffState)[tid] = 0;  // operand arrival counters
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -270,7 +265,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   tc_fence_after();
 
   const uint32_t w1_hi = tmem + k2ColW1Hi, w1_lo = tmem + k2ColW1Lo, w2_hi = tmem + k2ColW2Hi, w2_lo = tmem + k2ColW2Lo;
-  const int tile_stride = kContig ? k2Workers : (int)gridDim.x * k2Workers;
+  const int tile_stride = (int)gridDim.x * k2Workers;
 
   {
   const float b2c = vec[f], ln_scale = vec[128 + f], ln_offset = vec[256 + f];
@@ -296,24 +291,11 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   // prefetch); warp 0 also rcv[i + 1] (bucket ends), warp 2 lane 0 the receiver before the tile
   int pre_s = 0, pre_r = -1, pre_b = 0;
 
-  // Every thread has written its part of an operand (and fenced it for the async proxy).  Returns
-  // true in the one warp that must now issue the GEMM.  kLast: arrival counter, the last warp
-  // issues and nobody waits; otherwise a worker-wide bar.sync and the first warp issues.
-  int* arrive_cnt = reinterpret_cast<int*>(smem + k2OffState) + wk * 2;
-  auto operand_ready = [&](int which) -> bool {
-    if (kLast) {
-      __threadfence_block();
-      __syncwarp();
-      int old = 0;
-      if (lane == 0) old = atomicAdd(arrive_cnt + which, 1);
-      old = __shfl_sync(0xffffffffu, old, 0);
-      if ((old & 3) != 3) return false;
-      __threadfence_block();
-      return true;
-    } else {
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(k2WThreads) : "memory");
-      return q == 0;
-    }
+  // Every thread has written its part of an operand (and fenced it for the async proxy): a worker-wide
+  // bar.sync, after which the worker's first warp issues the GEMM.  Returns true in that warp.
+  auto operand_ready = [&]() -> bool {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(k2WThreads) : "memory");
+    return q == 0;
   };
 
   auto prefetch_idx = [&](int tile) {
@@ -393,7 +375,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     }
     fence_async_smem();
     tc_fence_before();
-    if (operand_ready(0)) {  // this warp issues (one elected lane per instruction)
+    if (operand_ready()) {  // this warp issues (one elected lane per instruction)
       tc_fence_after();
       const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
       issue_gemm_ts<!kNoScale>(w1_hi, w1_lo, bh, bh + kBBytes, acc0 + b * 32, k2Idesc);
@@ -404,10 +386,6 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
 
   // ---- E1(tile in buffers b / ib): hidden = relu(acc + P_s[snd] + P_r[rcv]) -> operand, GEMM 2
   auto phase_e1 = [&](int b, int ib) {
-    if (kLast) {  // the indices were written by sibling warps before they announced their operand part
-      mbar_wait(bar_g1, ph1);
-      ph1 ^= 1;
-    }
     const int* sp = idx_base + ib * k2IdxInts;
     const int* rp = sp + 32;
     float ps[32], pr[32];
@@ -424,10 +402,8 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       pr[j0 + 2] = __ldg(a.P + (int64_t)r4.z * (2 * kLatent) + kLatent + f);
       pr[j0 + 3] = __ldg(a.P + (int64_t)r4.w * (2 * kLatent) + kLatent + f);
     }
-    if (!kLast) {
-      mbar_wait(bar_g1, ph1);
-      ph1 ^= 1;
-    }
+    mbar_wait(bar_g1, ph1);
+    ph1 ^= 1;
     tc_fence_after();
     constexpr float kS = kNoScale ? 1.0f : kLoScale;
     if (kMn) {
@@ -478,7 +454,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     }
     fence_async_smem();
     tc_fence_before();
-    if (operand_ready(1)) {
+    if (operand_ready()) {
       tc_fence_after();
       const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
       issue_gemm_ts<!kNoScale>(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, kMn ? k2IdescBMn : k2Idesc);
@@ -491,20 +467,12 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     const int64_t slot0 = (int64_t)tile * k2Tile;
     const int valid = min(k2Tile, E - (int)slot0);
     const float* erow = a.e + slot0 * kLatent + f;
-    auto ld = [&](int j) -> float {
-      if (kNoAlloc) {  // streamed once: keep L1 for the gathered P rows
-        float v;
-        asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(erow + (int64_t)j * kLatent));
-        return v;
-      }
-      return erow[(int64_t)j * kLatent];
-    };
     if (valid == 32) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) eold[j] = ld(j);
+      for (int j = 0; j < 32; ++j) eold[j] = erow[(int64_t)j * kLatent];
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) eold[j] = j < valid ? ld(j) : 0.f;
+      for (int j = 0; j < 32; ++j) eold[j] = j < valid ? erow[(int64_t)j * kLatent] : 0.f;
     }
   };
 
@@ -518,7 +486,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     if (kEnc) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) eold[j] = 0.f;
-    } else if (!kEarlyEold) {
+    } else {
       load_eold(tile);
     }
     if (kEnc && b) {  // encoder: two GEMMs of the same kind are in flight, one barrier per buffer
@@ -634,7 +602,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       __syncwarp();  // feat_w is rewritten by the next call
       fence_async_smem();
       tc_fence_before();
-      if (operand_ready(1)) {
+      if (operand_ready()) {
         tc_fence_after();
         const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
         issue_gemm_ts<!kNoScale>(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, k2IdescBMn);
@@ -668,7 +636,6 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   for (int tile = k0; tile < n_tiles; tile += tile_stride) {
     const int ib_next = ib == 2 ? 0 : ib + 1;
     phase_e1(buf, ib);
-    if (kEarlyEold) load_eold(tile);
     if (tile + tile_stride < n_tiles) phase_a(tile + tile_stride, buf ^ 1, ib_next);
     phase_e2(tile, buf, ib);
     buf ^= 1;
@@ -683,14 +650,14 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   }
 }
 
-template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref, bool kNoAlloc>
+template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref>
 static int launch_variant(const EdgeTcArgs& a, int grid, cudaStream_t s) {
   static int attr_rc = -1;
   if (attr_rc < 0)
-    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref, kNoAlloc>,
+    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem);
   if (attr_rc) return attr_rc;
-  edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref, kNoAlloc><<<grid, k2Threads, k2Smem, s>>>(a);
+  edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref><<<grid, k2Threads, k2Smem, s>>>(a);
   LB_LAUNCHED(1);
   return 0;
 }
@@ -702,21 +669,18 @@ int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
     int rc = (int)cudaGetDevice(&dev);
     if (rc == 0) rc = (int)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (rc) return rc;
-    const char* e = getenv("LB200_TC2_VARIANT");  // bit 0: kMn, bit 1: kNoScale, bit 2: kStage, bit 3: kPref, bit 4: kNoAlloc
-    variant = e ? (atoi(e) & 31) : k2DefaultVariant;
+    const char* e = getenv("LB200_TC2_VARIANT");  // bit 0: kMn, bit 1: kNoScale, bit 2: kStage, bit 3: kPref
+    variant = e ? (atoi(e) & 15) : k2DefaultVariant;
   }
   const int n_groups = cdiv(cdiv(e_cap, k2Tile), k2Workers);
   const int grid = n_groups < sms ? n_groups : sms;
-  if (a.encoder) return launch_variant<true, true, true, false, false, false>(a, grid, s);
-  switch (variant) {  // the combinations kept for A/B measurements
-    case 0: return launch_variant<false, false, false, false, false, false>(a, grid, s);
-    case 1: return launch_variant<false, true, false, false, false, false>(a, grid, s);
-    case 3: return launch_variant<false, true, true, false, false, false>(a, grid, s);
-    case 7: return launch_variant<false, true, true, true, false, false>(a, grid, s);
-    case 15: return launch_variant<false, true, true, true, true, false>(a, grid, s);
-    case 23: return launch_variant<false, true, true, true, false, true>(a, grid, s);
-    case 31: return launch_variant<false, true, true, true, true, true>(a, grid, s);
-    default: return launch_variant<false, true, true, true, false, false>(a, grid, s);
+  if (a.encoder) return launch_variant<true, true, true, false, false>(a, grid, s);
+  switch (variant) {  // the measured ladder, kept for A/B runs
+    case 0: return launch_variant<false, false, false, false, false>(a, grid, s);
+    case 1: return launch_variant<false, true, false, false, false>(a, grid, s);
+    case 3: return launch_variant<false, true, true, false, false>(a, grid, s);
+    case 7: return launch_variant<false, true, true, true, false>(a, grid, s);
+    default: return launch_variant<false, true, true, true, true>(a, grid, s);
   }
 }
 
