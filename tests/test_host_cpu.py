@@ -68,6 +68,58 @@ def test_pack_params_layout():
         assert off % 4 == 0  # 16-byte alignment for cp.async / float4 loads
 
 
+def _tc_operands(blob, off, count):
+    """``count`` 128x128 fp16 operands stored [k/8][m][k%8] (UMMA K-major core matrices) -> (count, m, k) float32."""
+    halves = blob[off:off + count * 128 * 128 // 2].view(np.float16).reshape(count, 16, 128, 8)
+    return halves.transpose(0, 2, 1, 3).reshape(count, 128, 128).astype(np.float32)
+
+
+def test_pack_params_tensor_core_operands_reconstruct_the_weights():
+    """hi + lo * 2^-11 must give back every weight to ~2^-22 relative (the split the tcgen05 kernels
+    rely on), in the transposed (out feature, in feature) orientation, LayerNorm's mean folded into
+    the second layer; the node encoder's first layer is zero-padded to 128 input columns."""
+    params = ogns.init_params(12, 3, 2, num_mp_steps=2, seed=5, perturb=True)
+    pk = models.pack_params(params, 2, 2, device="cpu")
+    blob = pk.blob.numpy()
+
+    def check(hi, lo, want):
+        got = hi + lo / 2048.0
+        assert np.abs(got - want).max() <= 2.0 ** -21 * max(1.0, np.abs(want).max())
+        assert np.abs(lo).max() <= 1024.5  # |x - hi| <= half an fp16 ulp of x, times 2^11
+
+    # processor edge MLP of step 1: W1e^T hi|lo, W2c^T hi|lo + b2c | scale | offset
+    l0 = params["gns/~_processor/MLP_2/~/linear_0"]
+    l1 = params["gns/~_processor/MLP_2/~/linear_1"]
+    ln = params["gns/~_processor/layer_norm_2"]
+    ops = _tc_operands(blob, pk.proc_edge[1].tc_w, 4)
+    check(ops[0], ops[1], l0["w"][256:384].T)
+    w2 = l1["w"].astype(np.float64)
+    check(ops[2], ops[3], (w2 - w2.mean(axis=1, keepdims=True)).astype(np.float32).T)
+    vec = blob[pk.proc_edge[1].tc_vec:pk.proc_edge[1].tc_vec + 384]
+    assert np.allclose(vec[:128], l1["b"] - l1["b"].mean(), atol=1e-7)
+    assert np.array_equal(vec[128:256], ln["scale"]) and np.array_equal(vec[256:], ln["offset"])
+    # node encoder: W0pad^T, W1c^T, then the two halves of the first edge MLP's first layer
+    e0 = params["gns/~_encoder/MLP/~/linear_0"]
+    e1 = params["gns/~_encoder/MLP/~/linear_1"]
+    first = params["gns/~_processor/MLP/~/linear_0"]
+    ops = _tc_operands(blob, pk.enc_node.tc_w, 8)
+    k_in = e0["w"].shape[0]
+    check(ops[0][:, :k_in], ops[1][:, :k_in], e0["w"].T)
+    assert not ops[0][:, k_in:].any() and not ops[1][:, k_in:].any()
+    w1 = e1["w"].astype(np.float64)
+    check(ops[2], ops[3], (w1 - w1.mean(axis=1, keepdims=True)).astype(np.float32).T)
+    check(ops[4], ops[5], first["w"][:128].T)
+    check(ops[6], ops[7], first["w"][128:256].T)
+    vec = blob[pk.enc_node.tc_vec:pk.enc_node.tc_vec + 640]
+    assert np.array_equal(vec[:128], e0["b"]) and np.array_equal(vec[512:640], first["b"])
+    # edge encoder: only the second layer goes through the tensor cores
+    ee1 = params["gns/~_encoder/MLP_1/~/linear_1"]
+    ops = _tc_operands(blob, pk.enc_edge.tc_w, 2)
+    we = ee1["w"].astype(np.float64)
+    check(ops[0], ops[1], (we - we.mean(axis=1, keepdims=True)).astype(np.float32).T)
+    assert pk.enc_edge.b0 == pk.enc_edge.w0 + 4 * 128  # W0[4][128] | b0[128] contiguous (encoder kernel)
+
+
 def test_pack_params_accepts_alternate_embed_name_and_rejects_other_widths():
     params = ogns.init_params(10, 3, 2, num_mp_steps=1, seed=0)
     params["gns/embed"] = params.pop("gns/~/embed")
