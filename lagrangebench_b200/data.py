@@ -84,8 +84,10 @@ class H5Dataset:
         self.name = get_dataset_name_from_path(dataset_path) if name is None else name
         if not osp.exists(dataset_path):
             raise FileNotFoundError(f"{dataset_path} does not exist (datasets cannot be downloaded here)")
-        assert split in ["train", "valid", "test"]
-        assert input_seq_length > 1, "To compute at least one past velocity, input_seq_length must be >= 2."
+        if split not in ("train", "valid", "test"):
+            raise ValueError(f"unknown split {split!r}")
+        if input_seq_length < 2:
+            raise ValueError("input_seq_length must be at least 2 (one past velocity needs two positions)")
         self.dataset_path = dataset_path
         self.file_path = osp.join(dataset_path, split + ".h5")
         self.input_seq_length = input_seq_length
@@ -104,14 +106,15 @@ class H5Dataset:
             self.num_samples = int(samples_per_traj * len(self.traj_keys))
             self.getter = self.get_window
         else:
-            assert extra_seq_length > 0, "extra_seq_length must be > 0 for validation and testing."
+            if extra_seq_length <= 0:
+                raise ValueError("valid / test splits need extra_seq_length > 0 (the rollout length of interest)")
             self.subseq_length = input_seq_length + extra_seq_length
             self._split_valid_traj_into_n = self.sequence_length // self.subseq_length
             self.num_samples = self._split_valid_traj_into_n * len(self.traj_keys)
             self.getter = self.get_trajectory
-        assert self.sequence_length >= self.subseq_length, (
-            f"# steps in dataset trajectory ({self.sequence_length}) must be >= subsequence length "
-            f"({self.subseq_length}). Reduce either input_seq_length or extra_seq_length.")
+        if self.sequence_length < self.subseq_length:
+            raise ValueError(f"trajectories have {self.sequence_length} frames, a sample needs {self.subseq_length}: "
+                             "reduce input_seq_length or extra_seq_length")
 
     def _open_hdf5(self):
         if self.db_hdf5 is None:

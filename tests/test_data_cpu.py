@@ -75,7 +75,7 @@ def test_h5dataset_windowing_matches_the_reference_rules(tmp_path):
     pad = H5Dataset("test", path, input_seq_length=6, extra_seq_length=10, nl_backend="matscipy")
     pos, ptype = pad[0]
     assert pos.shape == (7, 16, 2) and ptype.tolist() == [0, 1, 2, 0, 1, -1, -1] and (pos[5:] == 0).all()
-    with pytest.raises(AssertionError):
+    with pytest.raises(ValueError):
         H5Dataset("valid", path, input_seq_length=6, extra_seq_length=0)
     batch = numpy_collate([ds[0], ds[1]])
     assert batch[0].shape == (2, 5, 16, 2) and batch[1].shape == (2, 5)
