@@ -120,11 +120,13 @@ class RolloutEngine:
             self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=neighbors.idx.device)
         self._cfg = cfg
 
-    def run(self, window, particle_type, targets, n_steps, neighbors=None):
+    def run(self, window, particle_type, targets, n_steps, neighbors=None, out=None):
         """Advance ``window`` (N, isl, d) in place by ``n_steps``.
 
         ``targets`` (n_steps, N, d) or None supplies the positions of kinematic particles.
-        Returns ``(predictions (n_steps, N, d), neighbors)``."""
+        ``out``: optional preallocated ``(n_steps, N, d)`` tensor for the predictions (a caller that
+        repeats a call with the very same buffers lets the library replay its captured step graph
+        from the first step on).  Returns ``(predictions (n_steps, N, d), neighbors)``."""
         lib = _cabi.load()
         h = self.h
         assert window.is_cuda and window.is_contiguous() and window.dtype == h["dtype"]
@@ -138,7 +140,12 @@ class RolloutEngine:
         if neighbors is None:
             neighbors = h["neighbor_fn"].allocate(window[:, -1].contiguous())
         self._configure(neighbors)
-        preds = torch.empty((n_steps, n, dim), dtype=window.dtype, device=dev)
+        if out is not None:
+            assert out.shape == (n_steps, n, dim) and out.dtype == window.dtype and out.device == dev \
+                and out.is_contiguous()
+            preds = out
+        else:
+            preds = torch.empty((n_steps, n, dim), dtype=window.dtype, device=dev)
         if targets is not None:
             targets = targets.to(dev, window.dtype).contiguous()
             assert targets.shape == (n_steps, n, dim)
