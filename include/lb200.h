@@ -44,7 +44,10 @@ const char* lb200_error_string(int code);
  * lagrangebench/case_setup/case.py:120-130).  Host-only, no CUDA work.
  */
 typedef struct {
-  int32_t n;               /* particles */
+  int32_t n;               /* particles (rows of the position array; the pad value of the list) */
+  int32_t n_valid;         /* the first n_valid rows are real particles, the rest padding (particle type
+                              PAD_VALUE, data.py:183-197) that must not enter the search: the reference's
+                              `num_particles` argument (case.py:182-190).  lb200_grid_init sets it to n. */
   int32_t dim;             /* 2 or 3 */
   int32_t pos_f64;         /* 0: float positions, 1: double positions */
   int32_t periodic;        /* bit k set: dimension k is periodic.  The reference is all-or-none
@@ -81,6 +84,26 @@ int64_t lb200_csr_scratch_bytes(int32_t n, int32_t e_cap);
 int lb200_nbr_build(const lb200_grid* g, const void* pos_dev, int32_t cell_capacity,
                     int32_t* idx_dev, int32_t e_cap, int32_t* stats_dev, void* scratch_dev,
                     int64_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Neighbor search straight into the receiver-major view (cell-list grids only): the same edges as
+ * lb200_nbr_build followed by lb200_csr_build -- the in-edges of every receiver in ascending list
+ * position -- without materialising the list; the step loop (lb200_rollout_steps) uses it.
+ *
+ *   pos_stride     elements between consecutive particles in pos_dev (dim for a compact array;
+ *                  t_window * dim with pos_dev pointing at the most recent frame of a window)
+ *   n_receivers    only receivers < n_receivers get a bucket (domain decomposition: ghosts send but
+ *                  do not receive); 0 = all
+ *   rowptr/snd/rcv as lb200_csr_build; rowptr is clamped to e_cap (edges past the capacity are dropped
+ *                  and LB200_OVF_NEIGHBOR_LIST is raised, as for the truncated list)
+ *   edge_feat      dev float[e_cap][4] or NULL: rel_disp | rel_dist | 0 per SLOT (features.py:115-124)
+ *   tmp            dev int32[e_cap] scratch
+ *   stats          as lb200_nbr_build
+ */
+int lb200_nbr_csr_build(const lb200_grid* g, const void* pos_dev, int64_t pos_stride, int32_t cell_capacity,
+                        int32_t n_receivers, int32_t* rowptr_dev, int32_t* snd_dev, int32_t* rcv_dev,
+                        float* edge_feat_dev, int32_t* tmp_dev, int32_t e_cap, int32_t* stats_dev,
+                        void* scratch_dev, int64_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Receiver-major view of an edge list for the deterministic segmented aggregation.
@@ -185,7 +208,8 @@ int lb200_gns_scratch_layout(int32_t n, int32_t e_cap, int64_t* off_h, int64_t* 
 /*
  *   node_feat, edge_feat  as produced by lb200_features (edge_feat in LIST order)
  *   ptype                 dev int32[n]
- *   rowptr/perm/snd/rcv   as produced by lb200_csr_build
+ *   rowptr/perm/snd/rcv   as produced by lb200_csr_build; perm may be NULL when edge_feat is already in
+ *                         SLOT order (lb200_nbr_csr_build)
  *   out                   dev float[n][dim]  normalised acceleration ({"acc": ...})
  */
 int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_dev, const float* node_feat_dev,
@@ -225,9 +249,16 @@ int lb200_integrate(const lb200_integrate_cfg* c, const float* out_dev, void* wi
  * and all later ones are no-ops and status[0] holds the index of the first such step; the
  * host then re-allocates and calls again from that step (same retry contract).
  *
- *   targets   dev T[n_steps][n][dim] or NULL  ground-truth positions for kinematic particles
- *   preds     dev T[n_steps][n][dim]          predicted positions per step
- *   status    dev int32[4]: [0] steps completed, [1] overflow bits, [2] last E, [3] reserved
+ *   targets   dev T[..][n][dim] or NULL        ground-truth positions for kinematic particles
+ *   preds     dev T[..][n][dim]                predicted positions per step
+ *   first_frame                                step k of this call reads targets[first_frame + k] and writes
+ *                                              preds[first_frame + k]: a caller that advances a long rollout in
+ *                                              chunks passes the same base pointers every time (one cached step graph)
+ *   idx       dev int32[2][e_cap] or NULL     the jax-md ordered list of every step, when the caller wants it;
+ *                                             NULL (cell-list grids): the step works on the receiver-major
+ *                                             view alone (lb200_nbr_csr_build) -- same edges, same results,
+ *                                             and the list of any state can be had from lb200_nbr_build
+ *   status    dev int32[4]: [0] steps completed, [1] overflow bits, [2] last E, [3] first_frame
  */
 typedef struct {
   lb200_grid grid;
@@ -242,7 +273,7 @@ int64_t lb200_rollout_scratch_bytes(const lb200_rollout_cfg* c);
 
 int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, const float* weights_dev,
                         void* window_dev, const int32_t* ptype_dev, const float* force_dev,
-                        const void* targets_dev, void* preds_dev, int32_t* idx_dev,
+                        const void* targets_dev, void* preds_dev, int32_t first_frame, int32_t* idx_dev,
                         int32_t* status_dev, void* scratch_dev, int64_t scratch_bytes,
                         void* stream);
 

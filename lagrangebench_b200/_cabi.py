@@ -20,8 +20,8 @@ OVF_CELL_LIST = 2
 
 
 class Grid(C.Structure):
-    _fields_ = [("n", C.c_int32), ("dim", C.c_int32), ("pos_f64", C.c_int32), ("periodic", C.c_int32),
-                ("box", C.c_double * 3), ("r_cutoff", C.c_double), ("use_cells", C.c_int32),
+    _fields_ = [("n", C.c_int32), ("n_valid", C.c_int32), ("dim", C.c_int32), ("pos_f64", C.c_int32),
+                ("periodic", C.c_int32), ("box", C.c_double * 3), ("r_cutoff", C.c_double), ("use_cells", C.c_int32),
                 ("cells_per_side", C.c_int32 * 3), ("cell_size", C.c_float * 3), ("n_cells", C.c_int32),
                 ("n_cand_cells", C.c_int32)]
 
@@ -71,6 +71,8 @@ _SIGNATURES = {
     "lb200_nbr_scratch_bytes": (_I64, [C.POINTER(Grid)]),
     "lb200_csr_scratch_bytes": (_I64, [_I32, _I32]),
     "lb200_nbr_build": (C.c_int, [C.POINTER(Grid), _VP, _I32, _VP, _I32, _VP, _VP, _I64, _VP]),
+    "lb200_nbr_csr_build": (C.c_int, [C.POINTER(Grid), _VP, _I64, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _I64,
+                                      _VP]),
     "lb200_csr_build": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _I64, _VP]),
     "lb200_node_feature_width": (_I32, [C.POINTER(FeatureCfg)]),
     "lb200_features": (C.c_int, [C.POINTER(FeatureCfg), _VP, _VP, _VP, _I32, _VP, _VP, _VP]),
@@ -79,7 +81,8 @@ _SIGNATURES = {
     "lb200_gns_forward": (C.c_int, [C.POINTER(GnsCfg), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP]),
     "lb200_integrate": (C.c_int, [C.POINTER(IntegrateCfg), _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "lb200_rollout_scratch_bytes": (_I64, [C.POINTER(RolloutCfg)]),
-    "lb200_rollout_steps": (C.c_int, [C.POINTER(RolloutCfg), _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP]),
+    "lb200_rollout_steps": (C.c_int, [C.POINTER(RolloutCfg), _I32, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _I64,
+                                      _VP]),
     "lb200_tc_selftest": (C.c_int, [_VP, _VP]),
     "lb200_launch_count": (_I64, []),
     "lb200_profile": (C.c_int, [_I32]),

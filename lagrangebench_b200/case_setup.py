@@ -56,16 +56,33 @@ class FeatureDict(dict):
 
 class NeighborList:
     """Mirror of jax-md's ``NeighborList`` fields that lagrangebench uses
-    (``evaluate/rollout.py:135-151``, ``case_setup/features.py:110``)."""
+    (``evaluate/rollout.py:135-151``, ``case_setup/features.py:110``).
 
-    def __init__(self, fn, idx, stats, reference_position, cell_list_capacity, max_occupancy, scratch):
+    ``idx`` may be lazy: the device-resident step loop works on the receiver-major view alone and
+    hands back a list object that builds the jax-md ordered ``(2, E_cap)`` array from
+    ``reference_position`` the first time it is read."""
+
+    def __init__(self, fn, idx, stats, reference_position, cell_list_capacity, max_occupancy, scratch, grid=None):
         self._fn = fn
-        self.idx = idx  # (2, E_cap) int32: row 0 receivers, row 1 senders; pad = N
+        self._idx = idx  # (2, E_cap) int32: row 0 receivers, row 1 senders; pad = N
         self._stats = stats  # device int32[4]: E, max cell occupancy, overflow bits, -
         self.reference_position = reference_position
         self.cell_list_capacity = cell_list_capacity
         self.max_occupancy = max_occupancy
         self._scratch = scratch
+        self._grid = grid
+
+    @property
+    def idx(self):
+        if self._idx is None:  # materialise: the list of reference_position, capacities unchanged
+            self._idx = torch.empty((2, self.max_occupancy), dtype=torch.int32, device=self.reference_position.device)
+            stats = torch.zeros(4, dtype=torch.int32, device=self._idx.device)
+            self._fn._build_into(self, self.reference_position, self._idx, stats)
+        return self._idx
+
+    @idx.setter
+    def idx(self, value):
+        self._idx = value
 
     @property
     def did_buffer_overflow(self):
@@ -76,12 +93,12 @@ class NeighborList:
     def n_edges(self):
         return int(self._stats[0].item())
 
-    def update(self, position, **kwargs):
-        return self._fn.update(position, self)
+    def update(self, position, num_particles=None, **kwargs):
+        return self._fn.update(position, self, num_particles=num_particles)
 
     def tree_map(self, fn):  # lets utils.broadcast_* treat the list as a pytree of arrays
         return NeighborList(self._fn, fn(self.idx), fn(self._stats), fn(self.reference_position),
-                            self.cell_list_capacity, self.max_occupancy, self._scratch)
+                            self.cell_list_capacity, self.max_occupancy, self._scratch, self._grid)
 
 
 class _NeighborFn:
@@ -96,12 +113,13 @@ class _NeighborFn:
         self.multiplier = float(multiplier)
         self.tdtype = tdtype
 
-    def _grid(self, n):
+    def _grid(self, n, num_particles=None):
         lib = _cabi.load()
         g = _cabi.Grid()
         box = (C.c_double * 3)(*(self.box + [1.0] * (3 - self.dim)))
         _cabi.check(lib.lb200_grid_init(C.byref(g), n, self.dim, int(self.tdtype == torch.float64),
                                         int(self.periodic), box, self.r_cutoff))
+        g.n_valid = _n_valid(n, num_particles)
         return g
 
     def _position(self, position):
@@ -111,11 +129,13 @@ class _NeighborFn:
             p = p.cuda()
         return p.to(self.tdtype).contiguous()
 
-    def allocate(self, position, **kwargs):
+    def allocate(self, position, num_particles=None, **kwargs):
+        """``num_particles``: the first ``num_particles`` rows are real, the rest padding that stays
+        out of the search (``case.py:182-186``)."""
         lib = _cabi.load()
         pos = self._position(position)
         n = pos.shape[0]
-        g = self._grid(n)
+        g = self._grid(n, num_particles)
         nbytes = lib.lb200_nbr_scratch_bytes(C.byref(g))
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=pos.device)
         stats = torch.zeros(4, dtype=torch.int32, device=pos.device)
@@ -130,29 +150,51 @@ class _NeighborFn:
         e_cap = max(1, min(int(n_edges * self.multiplier), n * n_cand, n * n))
         idx = torch.empty((2, e_cap), dtype=torch.int32, device=pos.device)
         stats.zero_()
-        nl = NeighborList(self, idx, stats, pos, cap if g.use_cells else None, e_cap, scratch)
-        nl._grid = g
-        self._build(nl, pos)
+        nl = NeighborList(self, idx, stats, pos, cap if g.use_cells else None, e_cap, scratch, g)
+        self._build_into(nl, pos, idx, stats)
         return nl
 
-    def _build(self, nl, pos):
+    def _build_into(self, nl, pos, idx, stats):
         lib = _cabi.load()
-        g = nl._grid
-        _cabi.check(lib.lb200_nbr_build(C.byref(g), _cabi.ptr(pos), nl.cell_list_capacity or 0, _cabi.ptr(nl.idx),
-                                        nl.max_occupancy, _cabi.ptr(nl._stats), _cabi.ptr(nl._scratch),
+        _cabi.check(lib.lb200_nbr_build(C.byref(nl._grid), _cabi.ptr(pos), nl.cell_list_capacity or 0, _cabi.ptr(idx),
+                                        nl.max_occupancy, _cabi.ptr(stats), _cabi.ptr(nl._scratch),
                                         nl._scratch.numel(), _cabi.stream()))
 
-    def update(self, position, nbrs, **kwargs):
+    def update(self, position, nbrs, num_particles=None, **kwargs):
         """Rebuild into the list's own buffers (fixed capacity).  The returned object shares
         ``idx`` with ``nbrs``; the overflow bits are sticky like jax-md's error code."""
         pos = self._position(position)
-        if pos.shape[0] != nbrs._grid.n:
+        if nbrs._grid is None or pos.shape[0] != nbrs._grid.n:
             raise ValueError("number of particles changed: allocate a new neighbor list")
+        grid = nbrs._grid
+        nv = _n_valid(grid.n, num_particles)
+        if nv != grid.n_valid:
+            grid = _cabi.Grid.from_buffer_copy(grid)
+            grid.n_valid = nv
         out = NeighborList(self, nbrs.idx, nbrs._stats, pos, nbrs.cell_list_capacity, nbrs.max_occupancy,
-                           nbrs._scratch)
-        out._grid = nbrs._grid
-        self._build(out, pos)
+                           nbrs._scratch, grid)
+        self._build_into(out, pos, out.idx, out._stats)
         return out
+
+
+def _n_valid(n, num_particles):
+    if num_particles is None:
+        return n
+    nv = int(num_particles)
+    if not 0 < nv <= n:
+        raise ValueError(f"num_particles={nv} outside (0, {n}]")
+    return nv
+
+
+def num_real_particles(particle_type):
+    """``(particle_type != -1).sum()`` (``case.py:182``) as a host int; padding must be trailing
+    (``data.py:183-197`` appends it)."""
+    pt = particle_type.detach().cpu().numpy() if isinstance(particle_type, torch.Tensor) else np.asarray(particle_type)
+    real = pt != -1
+    nv = int(real.sum())
+    if nv < pt.shape[0] and not real[:nv].all():
+        raise NotImplementedError("padding particles (type -1) must follow the real ones")
+    return nv
 
 
 @dataclass
@@ -327,10 +369,11 @@ def case_builder(box, metadata, input_seq_length, cfg_neighbors=None, cfg_model=
     def _preprocess(sample, neighbors=None, is_allocate=False, mode="train", unroll_steps=0):
         pos_input = _to_device(sample[0], tdtype)
         most_recent_position = pos_input[:, isl - 1].contiguous()
+        num_particles = num_real_particles(sample[1])  # case.py:182
         if is_allocate:
-            neighbors = neighbor_fn.allocate(most_recent_position)
+            neighbors = neighbor_fn.allocate(most_recent_position, num_particles=num_particles)
         else:
-            neighbors = neighbors.update(most_recent_position)
+            neighbors = neighbors.update(most_recent_position, num_particles=num_particles)
         features = feature_transform(pos_input[:, :isl], neighbors)
         if mode == "train":
             begin = isl - 2 + unroll_steps

@@ -73,10 +73,18 @@ __device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
 __device__ __forceinline__ float fmod_x(float a, float b) { return fmodf(a, b); }
 __device__ __forceinline__ double fmod_x(double a, double b) { return fmod(a, b); }
 
-// jnp.mod for side > 0: C fmod, then + side where the remainder is negative.
+// jnp.mod for side > 0: C fmod, then + side where the remainder is negative.  fmod is exact, and
+// for |x| < 2 side it is x, or x - side (exact by Sterbenz' lemma): those ranges -- every value a
+// displacement or a one-step shift takes -- skip the (slow, iterative) library fmod bit for bit.
 template <typename T>
 __device__ __forceinline__ T floor_mod(T x, T side) {
-  T r = fmod_x(x, side);
+  T r;
+  if (x >= T(0)) {
+    if (x < side) return x;
+    r = x < add_rn(side, side) ? sub_rn(x, side) : fmod_x(x, side);
+    return r;
+  }
+  r = x > -side ? x : fmod_x(x, side);
   return r < T(0) ? add_rn(r, side) : r;
 }
 
@@ -95,8 +103,8 @@ __device__ __forceinline__ T shift1(T r, T dr, T side, bool periodic) {
 }
 
 // Exclusive scan of int32 (n elements -> n+1 outputs, out[n] = total).
-// scratch: int32[cdiv(n, 1024) + 1].
+// One memset node + one kernel (decoupled look-back).  scratch: int32[scan_scratch_elems(n)], 8-byte aligned.
 int exclusive_scan_i32(const int32_t* in, int32_t* out, int n, int32_t* scratch, cudaStream_t s);
-static inline int64_t scan_scratch_elems(int64_t n) { return (n + 1023) / 1024 + 1; }
+static inline int64_t scan_scratch_elems(int64_t n) { return 2 * ((n + 2047) / 2048 + 2) + 2; }
 
 }  // namespace lb

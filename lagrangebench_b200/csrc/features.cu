@@ -114,7 +114,7 @@ __global__ void integrate_kernel(IntegDev c, const float* __restrict__ net_out, 
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
   if (step_counter != nullptr) {  // device-resident loop: frame index = steps completed so far
-    const int64_t frame = (int64_t)(*step_counter) * c.n * DIM;
+    const int64_t frame = (int64_t)(step_counter[0] + step_counter[3]) * c.n * DIM;  // [3]: first frame of this call
     if (target != nullptr) target += frame;
     if (pred != nullptr) pred += frame;
   }

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 2) edge_encoder_kernel(EdgeEncArgs a
   const int rows = min(kTM, E - (int)slot0);
   for (int f = threadIdx.x; f < 4 * kLatent; f += kThreads) w0s[f] = a.enc.w0[f];
   if (threadIdx.x < kTM)
-    efs[threadIdx.x] = threadIdx.x < rows ? a.edge_feat[a.perm[slot0 + threadIdx.x]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    efs[threadIdx.x] = threadIdx.x < rows ? a.edge_feat[a.perm ? a.perm[slot0 + threadIdx.x] : slot0 + threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][8];
@@ -573,7 +573,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
                                  const float* edge_feat_dev, const int32_t* ptype_dev, const int32_t* rowptr_dev,
                                  const int32_t* perm_dev, const int32_t* snd_dev, const int32_t* rcv_dev,
                                  float* out_dev, void* scratch_dev, int64_t scratch_bytes, void* stream) {
-  if (!c || !weights_dev || !node_feat_dev || !edge_feat_dev || !ptype_dev || !rowptr_dev || !perm_dev ||
+  if (!c || !weights_dev || !node_feat_dev || !edge_feat_dev || !ptype_dev || !rowptr_dev ||
       !snd_dev || !rcv_dev || !out_dev || !scratch_dev)
     return LB200_EINVAL;
   if (c->num_mp_steps < 1 || c->node_in + c->embed_size > kEncK || (c->dim != 2 && c->dim != 3) || c->e_cap < 1)

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
       const bool ok = wtid < rows;
       const int r_here = ok ? a.rcv[slot0 + wtid] : -1;
       const int r_next = (slot0 + wtid + 1 < E) ? a.rcv[slot0 + wtid + 1] : -3;
-      sidx[wtid] = ok ? (kEnc ? a.perm[slot0 + wtid] : a.snd[slot0 + wtid]) : 0;
+      sidx[wtid] = ok ? (kEnc ? (a.perm ? a.perm[slot0 + wtid] : (int)(slot0 + wtid)) : a.snd[slot0 + wtid]) : 0;
       rclamp[wtid] = max(r_here, 0);
       ridx[1 + wtid] = ok ? r_here : (wtid == rows ? -3 : -1);  // -3: "no edge after the tile"
       // last edge of its receiver bucket inside its 32-edge carry sub-tile
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a)
       // ---- encoder: first layer (K = dim + 1 <= 4) on CUDA cores straight into the layer-2 operand
       float4* feat_s = reinterpret_cast<float4*>(smem + kOffFeat) + wk * kTcTile;
       if (wtid < kTcTile)  // the tile's edge features, gathered once through perm (list order -> slot order)
-        feat_s[wtid] = wtid < rows ? a.edge_feat[a.perm[slot0 + wtid]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        feat_s[wtid] = wtid < rows ? a.edge_feat[a.perm ? a.perm[slot0 + wtid] : slot0 + wtid] : make_float4(0.f, 0.f, 0.f, 0.f);
       asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(kWThreads) : "memory");
 #pragma unroll 8
       for (int j = 0; j < 32; ++j) {

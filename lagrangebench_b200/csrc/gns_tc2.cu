@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     // edge features live in LIST order and are addressed through perm; the next tile's are fetched a phase ahead
     auto feat_of = [&](int tile) -> float4 {
       const int64_t s = (int64_t)tile * k2Tile + lane;
-      return (tile < n_tiles && s < E) ? a.edge_feat[a.perm[s]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      return (tile < n_tiles && s < E) ? a.edge_feat[a.perm ? a.perm[s] : s] : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     float4 pre_f = make_float4(0.f, 0.f, 0.f, 0.f);
     auto phase_a_enc = [&](int tile, int b) {

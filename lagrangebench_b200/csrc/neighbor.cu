@@ -1,24 +1,30 @@
 // (i) Cell-list radius neighbor search + receiver-major CSR view.
 //
-// Produces the same (2, E_cap) int32 edge list as jax_md.partition.neighbor_list
-// (Sparse, mask_self=False) -- third-party jax-sph 0.0.3, call sites
-// lagrangebench/case_setup/case.py:120-130,184-190 -- in the same order (see
-// oracle/partition.py for the restated rules), without materialising jax-md's
-// (N, 3^d * capacity) candidate table: two sweeps (count, fill) around a prefix sum.
+// Two products of one cell structure:
+//   * the (2, E_cap) int32 edge list of jax_md.partition.neighbor_list (Sparse, mask_self=False)
+//     -- third-party jax-sph 0.0.3, call sites lagrangebench/case_setup/case.py:120-130,184-190 --
+//     in jax-md's order (oracle/partition.py restates the rules), without materialising its
+//     (N, 3^d * capacity) candidate table: lb200_nbr_build;
+//   * the receiver-major view the deterministic aggregation consumes (rowptr / snd / rcv and the
+//     edge features in slot order), built STRAIGHT from the cells: the in-edges of receiver v are
+//     found by v's own sweep with the predicate of the reverse pair, and because a sender holds a
+//     receiver at most once, "ascending list position" inside a bucket is "ascending sender id":
+//     lb200_nbr_csr_build.  No list, no permutation, no atomics on the edge arrays.
 //
-// HBM-bound integer/byte work: positions are re-laid out in cell order once so that the
-// 3^d-cell sweeps read contiguous memory; the list itself is written as one contiguous run
-// per particle.
+// HBM/latency-bound integer work: positions are re-laid out in cell order once; a WARP sweeps the
+// 3^d cells of one particle (x-adjacent cells are contiguous in that layout, so a sweep is 3^(d-1)
+// contiguous ranges); prefix sums are single-launch decoupled look-back scans.
 #include <math.h>
 
 #include "common.cuh"
 
 namespace lb {
 
-// ------------------------------------------------------------------ exclusive scan
+// ------------------------------------------------------------------ exclusive scan (decoupled look-back)
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 4;
-constexpr int kScanBlock = kScanThreads * kScanItems;  // 1024
+constexpr int kScanItems = 8;
+constexpr int kScanBlock = kScanThreads * kScanItems;  // 2048
+constexpr unsigned long long kStAgg = 1ull << 62, kStPrefix = 2ull << 62, kStMask = (1ull << 62) - 1;
 
 __device__ __forceinline__ int warp_incl_scan(int v) {
 #pragma unroll
@@ -49,69 +55,91 @@ __device__ __forceinline__ int block_incl_scan(int v, int* total) {
   return inc + base;
 }
 
-__global__ void scan_block_sums(const int32_t* __restrict__ in, int n, int32_t* __restrict__ bsum) {
-  int base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
-  int s = 0;
-#pragma unroll
-  for (int i = 0; i < kScanItems; ++i)
-    if (base + i < n) s += in[base + i];
-  int total;
-  block_incl_scan(s, &total);
-  if (threadIdx.x == 0) bsum[blockIdx.x] = total;
-}
-
-__global__ void scan_sums(int32_t* bsum, int nb) {  // one block; exclusive in place, bsum[nb] = total
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
+// One launch.  state[0] is the block ticket, state[1 + b] the (status | value) word of logical block
+// b; the caller zeroes state[0 .. nb] before the launch.  A block only ever waits for blocks with a
+// smaller ticket, which are running or done: no deadlock whatever the grid size.
+//   out[i] = min(sum(in[0..i)), clamp) for i <= n;  *total_out = sum(in) (unclamped);  *max_out =
+//   max(*max_out, max(in)).
+__global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const int32_t* __restrict__ in,
+                                                                     int32_t* __restrict__ out, int n,
+                                                                     unsigned long long* state, int clamp,
+                                                                     int32_t* total_out, int32_t* max_out) {
+  __shared__ int s_bid, s_excl;
+  if (threadIdx.x == 0) s_bid = (int)atomicAdd(state, 1ull);
   __syncthreads();
-  for (int base = 0; base < nb; base += kScanThreads) {
-    int i = base + threadIdx.x;
-    int v = i < nb ? bsum[i] : 0;
-    int total;
-    int inc = block_incl_scan(v, &total);
-    int c = carry;
-    if (i < nb) bsum[i] = c + inc - v;
-    __syncthreads();
-    if (threadIdx.x == 0) carry = c + total;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) bsum[nb] = carry;
-}
-
-__global__ void scan_final(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n,
-                           const int32_t* __restrict__ bsum, int nb) {
-  int base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
+  const int bid = s_bid;
+  const int base = bid * kScanBlock + threadIdx.x * kScanItems;
   int v[kScanItems];
-  int s = 0;
+  int s = 0, m = 0;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
     v[i] = base + i < n ? in[base + i] : 0;
     s += v[i];
+    m = max(m, v[i]);
   }
   int total;
-  int inc = block_incl_scan(s, &total);
-  int run = bsum[blockIdx.x] + inc - s;
+  const int inc = block_incl_scan(s, &total);
+  if (max_out != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_out, m);
+  }
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* st = state + 1;
+    int excl = 0;
+    if (bid > 0) {
+      st[bid] = kStAgg | (unsigned long long)total;
+      for (int p = bid - 1;; --p) {
+        unsigned long long w;
+        do {
+          w = st[p];
+        } while ((w >> 62) == 0);
+        excl += (int)(w & kStMask);
+        if ((w >> 62) == 2) break;
+      }
+    }
+    st[bid] = kStPrefix | (unsigned long long)(excl + total);
+    s_excl = excl;
+    if (bid == (int)gridDim.x - 1) {
+      out[n] = min(excl + total, clamp);
+      if (total_out != nullptr) *total_out = excl + total;
+    }
+  }
+  __syncthreads();
+  int run = s_excl + inc - s;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
-    if (base + i < n) out[base + i] = run;
+    if (base + i < n) out[base + i] = min(run, clamp);
     run += v[i];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = bsum[nb];
 }
 
-int exclusive_scan_i32(const int32_t* in, int32_t* out, int n, int32_t* scratch, cudaStream_t s) {
+static inline int64_t scan_state_words(int64_t n) { return (n + kScanBlock - 1) / kScanBlock + 2; }
+
+// state must have been zeroed (all of scan_state_words(n) words) on the same stream
+static int scan_lookback(const int32_t* in, int32_t* out, int n, unsigned long long* state, int clamp,
+                         int32_t* total_out, int32_t* max_out, cudaStream_t s) {
   int nb = cdiv(n, kScanBlock);
   if (nb == 0) nb = 1;
-  { scan_block_sums<<<nb, kScanThreads, 0, s>>>(in, n, scratch); LB_LAUNCHED(1); }
-  { scan_sums<<<1, kScanThreads, 0, s>>>(scratch, nb); LB_LAUNCHED(1); }
-  { scan_final<<<nb, kScanThreads, 0, s>>>(in, out, n, scratch, nb); LB_LAUNCHED(1); }
+  scan_lookback_kernel<<<nb, kScanThreads, 0, s>>>(in, out, n, state, clamp, total_out, max_out);
+  LB_LAUNCHED(1);
+  return 0;
+}
+
+// The generic helper other translation units use: zeroes its own state (one memset node).
+// scratch: scan_scratch_elems(n) int32.
+int exclusive_scan_i32(const int32_t* in, int32_t* out, int n, int32_t* scratch, cudaStream_t s) {
+  unsigned long long* state = reinterpret_cast<unsigned long long*>(scratch);
+  LB_CHECK(cudaMemsetAsync(state, 0, sizeof(unsigned long long) * scan_state_words(n), s));
+  int rc = scan_lookback(in, out, n, state, 0x7fffffff, nullptr, nullptr, s);
+  if (rc) return rc;
   LB_LAUNCH_CHECK();
   return 0;
 }
 
 // ------------------------------------------------------------------ grid parameters on device
 struct GridDev {
-  int n, dim, periodic, use_cells, n_cells, cap;
+  int n, n_valid, dim, periodic, use_cells, n_cells, cap;
   int nc[3];
   float cell_size[3];
   double box[3];
@@ -136,77 +164,64 @@ struct Geo {  // per-thread typed copy of the geometry
 };
 
 template <typename T, int DIM>
-__device__ __forceinline__ int cell_hash(const T* p, const Geo<T>& geo, const GridDev& g) {
+__device__ __forceinline__ int cell_hash(const T* p, const Geo<T>& geo, const GridDev& g, int* cc) {
   int h = 0, mult = 1;
 #pragma unroll
   for (int k = 0; k < DIM; ++k) {
     int c = (int)div_rn(p[k], geo.cs[k]);  // truncation toward zero, as jnp.array(..., dtype=i32)
     c = min(max(c, 0), g.nc[k] - 1);       // out-of-domain particles: clamp (documented deviation)
+    if (cc != nullptr) cc[k] = c;
     h += c * mult;
     mult *= g.nc[k];
   }
   return h;
 }
 
+// pos: particle i's coordinates are pos[i * stride + 0 .. DIM) (stride = DIM for a compact array,
+// t_window * DIM for the most recent frame of a position window)
 template <typename T, int DIM>
-__global__ void hash_kernel(const T* __restrict__ pos, GridDev g, int32_t* __restrict__ hash,
+__global__ void hash_kernel(const T* __restrict__ pos, int64_t stride, GridDev g, int32_t* __restrict__ hash,
                             int32_t* __restrict__ cell_count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.n) return;
+  if (i >= g.n_valid) return;
   Geo<T> geo(g);
   T p[DIM];
 #pragma unroll
-  for (int k = 0; k < DIM; ++k) p[k] = pos[(int64_t)i * DIM + k];
-  int h = cell_hash<T, DIM>(p, geo, g);
+  for (int k = 0; k < DIM; ++k) p[k] = pos[(int64_t)i * stride + k];
+  int h = cell_hash<T, DIM>(p, geo, g, nullptr);
   hash[i] = h;
   atomicAdd(&cell_count[h], 1);
 }
 
-__global__ void stats_init_kernel(int32_t* stats) {
-  stats[0] = 0;
-  stats[1] = 0;
-}
-
-__global__ void max_occ_kernel(const int32_t* __restrict__ cell_count, int n_cells, int32_t* stats) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  int v = c < n_cells ? cell_count[c] : 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(&stats[1], v);
-}
-
-__global__ void cell_scatter_kernel(const int32_t* __restrict__ hash, int n,
-                                    const int32_t* __restrict__ cell_start, int32_t* __restrict__ cursor,
-                                    int32_t* __restrict__ order) {
+// cell_count returns to zero: the slot of a particle is cell_start + (remaining count - 1)
+__global__ void cell_scatter_kernel(const int32_t* __restrict__ hash, int n, const int32_t* __restrict__ cell_start,
+                                    int32_t* __restrict__ cell_count, int32_t* __restrict__ sid) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int h = hash[i];
-  order[cell_start[h] + atomicAdd(&cursor[h], 1)] = i;
+  sid[cell_start[h] + atomicSub(&cell_count[h], 1) - 1] = i;
 }
 
-// stable argsort by hash == ascending particle id within each cell
-__global__ void cell_sort_kernel(const int32_t* __restrict__ cell_start, int n_cells, int32_t* __restrict__ order) {
+// stable argsort by hash == ascending particle id within each cell; then the cell-ordered positions
+template <typename T, int DIM>
+__global__ void cell_sort_gather_kernel(const int32_t* __restrict__ cell_start, int n_cells, int32_t* __restrict__ sid,
+                                        const T* __restrict__ pos, int64_t stride, T* __restrict__ spos) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_cells) return;
   int a = cell_start[c], b = cell_start[c + 1];
   for (int i = a + 1; i < b; ++i) {
-    int v = order[i], j = i - 1;
-    while (j >= a && order[j] > v) {
-      order[j + 1] = order[j];
+    int v = sid[i], j = i - 1;
+    while (j >= a && sid[j] > v) {
+      sid[j + 1] = sid[j];
       --j;
     }
-    order[j + 1] = v;
+    sid[j + 1] = v;
   }
-}
-
-template <typename T, int DIM>
-__global__ void gather_sorted_kernel(const T* __restrict__ pos, const int32_t* __restrict__ order, int n,
-                                     T* __restrict__ spos) {
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
-  int i = order[q];
+  for (int i = a; i < b; ++i) {
+    const int64_t p = (int64_t)sid[i] * stride;
 #pragma unroll
-  for (int k = 0; k < DIM; ++k) spos[(int64_t)q * DIM + k] = pos[(int64_t)i * DIM + k];
+    for (int k = 0; k < DIM; ++k) spos[(int64_t)i * DIM + k] = pos[p + k];
+  }
 }
 
 template <typename T, int DIM>
@@ -222,31 +237,29 @@ __device__ __forceinline__ bool within(const T* pi, const T* pj, const Geo<T>& g
   return acc < geo.cutoff_sq;
 }
 
-// Visit the candidates of the particle of sorted rank q in jax-md's order and call
-// f(particle id j) for every candidate within the cutoff.
+// ------------------------------------------------------------------ ordered sweep (the jax-md list)
+// One WARP per particle (sorted rank q), candidate cells visited one after the other in jax-md's
+// order: own cell, then ndindex(3,..,3)-1 (last component fastest) skipping 0, component 0 acting on
+// the slowest spatial axis, neighbour = coord - offset (wrap-around); inside a cell the slot of
+// sorted rank k is k mod cap, so ascending-slot order is a rotation.  f(accepted, qq) is called by
+// every lane for every 32-slot batch (warp-uniform trip count): lane `lane` holds candidate qq.
 template <typename T, int DIM, typename F>
-__device__ __forceinline__ void for_each_neighbor(int q, const GridDev& g, const Geo<T>& geo,
-                                                  const T* __restrict__ spos, const int32_t* __restrict__ order,
-                                                  const int32_t* __restrict__ cell_start, F f) {
+__device__ __forceinline__ void sweep_ordered(int q, int lane, const GridDev& g, const Geo<T>& geo,
+                                              const T* __restrict__ spos, const int32_t* __restrict__ cell_start,
+                                              F f) {
   T pi[DIM];
 #pragma unroll
   for (int k = 0; k < DIM; ++k) pi[k] = spos[(int64_t)q * DIM + k];
-  int h = cell_hash<T, DIM>(pi, geo, g);
   int cc[3] = {0, 0, 0};
-  {
-    int r = h;
-#pragma unroll
-    for (int k = 0; k < DIM; ++k) {
-      cc[k] = r % g.nc[k];
-      r /= g.nc[k];
-    }
-  }
+  cell_hash<T, DIM>(pi, geo, g, cc);
   constexpr int NOFF = DIM == 2 ? 9 : 27;
-  // candidate cells: own cell, then ndindex(3,..,3)-1 (last component fastest) skipping 0;
-  // component 0 acts on the slowest spatial axis; neighbour = coord - offset (wrap-around)
-  for (int o = -1; o < NOFF; ++o) {
+  // lane c < NOFF + 1 prepares candidate cell number c: c == 0 own cell, else offset o = c - 1
+  int my_r0 = 0, my_m = 0;
+  if (lane <= NOFF) {
     int off[3] = {0, 0, 0};
-    if (o >= 0) {
+    bool skip = false;
+    if (lane > 0) {
+      const int o = lane - 1;
       if (DIM == 2) {
         off[1] = o / 3 - 1;  // slowest axis: y
         off[0] = o % 3 - 1;  // x
@@ -255,95 +268,124 @@ __device__ __forceinline__ void for_each_neighbor(int q, const GridDev& g, const
         off[1] = (o / 3) % 3 - 1;  // y
         off[0] = o % 3 - 1;        // x
       }
-      if (off[0] == 0 && off[1] == 0 && off[2] == 0) continue;
+      skip = off[0] == 0 && off[1] == 0 && off[2] == 0;
     }
-    int c = 0, mult = 1;
+    if (!skip) {
+      int c = 0, mult = 1;
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) {
-      int v = cc[k] - off[k];
-      v = v < 0 ? v + g.nc[k] : (v >= g.nc[k] ? v - g.nc[k] : v);
-      c += v * mult;
-      mult *= g.nc[k];
+      for (int k = 0; k < DIM; ++k) {
+        int v = cc[k] - off[k];
+        v = v < 0 ? v + g.nc[k] : (v >= g.nc[k] ? v - g.nc[k] : v);
+        c += v * mult;
+        mult *= g.nc[k];
+      }
+      my_r0 = cell_start[c];
+      my_m = cell_start[c + 1] - my_r0;
     }
-    int r0 = cell_start[c], m = cell_start[c + 1] - r0;
+  }
+  for (int c = 0; c <= NOFF; ++c) {
+    const int r0 = __shfl_sync(0xffffffffu, my_r0, c), m = __shfl_sync(0xffffffffu, my_m, c);
     if (m == 0) continue;
-    // slot of sorted rank k inside its cell is k mod cap: ascending-slot order is a rotation
     int t0 = (g.cap - r0 % g.cap) % g.cap;
     if (t0 >= m) t0 = 0;
-    for (int u = 0; u < m; ++u) {
+    for (int u0 = 0; u0 < m; u0 += 32) {
+      const int u = u0 + lane;
       int t = t0 + u;
       if (t >= m) t -= m;
-      int qq = r0 + t;
-      T pj[DIM];
+      const int qq = r0 + t;
+      bool ok = false;
+      if (u < m) {
+        T pj[DIM];
 #pragma unroll
-      for (int k = 0; k < DIM; ++k) pj[k] = spos[(int64_t)qq * DIM + k];
-      if (within<T, DIM>(pi, pj, geo)) f(order[qq]);
+        for (int k = 0; k < DIM; ++k) pj[k] = spos[(int64_t)qq * DIM + k];
+        ok = within<T, DIM>(pi, pj, geo);
+      }
+      f(ok, qq);
     }
   }
 }
 
+constexpr int kSweepThreads = 256;  // 8 warps = 8 particles per block
+
 template <typename T, int DIM>
-__global__ void count_kernel(GridDev g, const T* __restrict__ spos, const int32_t* __restrict__ order,
-                             const int32_t* __restrict__ cell_start, int32_t* __restrict__ cnt) {
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= g.n) return;
+__global__ void __launch_bounds__(kSweepThreads) count_kernel(GridDev g, const T* __restrict__ spos,
+                                                              const int32_t* __restrict__ sid,
+                                                              const int32_t* __restrict__ cell_start,
+                                                              int32_t* __restrict__ cnt) {
+  const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (q >= g.n_valid) return;
   Geo<T> geo(g);
   int c = 0;
-  for_each_neighbor<T, DIM>(q, g, geo, spos, order, cell_start, [&](int) { ++c; });
-  cnt[order[q]] = c;
+  sweep_ordered<T, DIM>(q, lane, g, geo, spos, cell_start,
+                        [&](bool ok, int) { c += __popc(__ballot_sync(0xffffffffu, ok)); });
+  if (lane == 0) cnt[sid[q]] = c;
 }
 
 template <typename T, int DIM>
-__global__ void fill_kernel(GridDev g, const T* __restrict__ spos, const int32_t* __restrict__ order,
-                            const int32_t* __restrict__ cell_start, const int32_t* __restrict__ off,
-                            int32_t* __restrict__ idx, int e_cap) {
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= g.n) return;
+__global__ void __launch_bounds__(kSweepThreads) fill_kernel(GridDev g, const T* __restrict__ spos,
+                                                             const int32_t* __restrict__ sid,
+                                                             const int32_t* __restrict__ cell_start,
+                                                             const int32_t* __restrict__ off, int32_t* __restrict__ idx,
+                                                             int e_cap) {
+  const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (q >= g.n_valid) return;
   Geo<T> geo(g);
-  int i = order[q];
+  const int i = sid[q];
   int w = off[i];
-  for_each_neighbor<T, DIM>(q, g, geo, spos, order, cell_start, [&](int j) {
-    if (w < e_cap) {
-      idx[w] = j;          // row 0: receivers (candidate)
-      idx[e_cap + w] = i;  // row 1: senders (center)
+  sweep_ordered<T, DIM>(q, lane, g, geo, spos, cell_start, [&](bool ok, int qq) {
+    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const int k = w + __popc(m & ((1u << lane) - 1u));
+      if (k < e_cap) {
+        idx[k] = sid[qq];    // row 0: receivers (candidate)
+        idx[e_cap + k] = i;  // row 1: senders (center)
+      }
     }
-    ++w;
+    w += __popc(m);
   });
+}
+
+// particles without a cell (index >= n_valid: padding, utils.py NodeType.PAD_VALUE) own no edges
+__global__ void zero_tail_kernel(int32_t* __restrict__ cnt, int from, int n) {
+  int i = from + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cnt[i] = 0;
 }
 
 // all-pairs path (box smaller than 3 cutoffs): candidates 0..N-1 ascending
 template <typename T, int DIM>
-__global__ void count_allpairs_kernel(GridDev g, const T* __restrict__ pos, int32_t* __restrict__ cnt) {
+__global__ void count_allpairs_kernel(GridDev g, const T* __restrict__ pos, int64_t stride, int32_t* __restrict__ cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
-  Geo<T> geo(g);
-  T pi[DIM];
-#pragma unroll
-  for (int k = 0; k < DIM; ++k) pi[k] = pos[(int64_t)i * DIM + k];
   int c = 0;
-  for (int j = 0; j < g.n; ++j) {
-    T pj[DIM];
+  if (i < g.n_valid) {
+    Geo<T> geo(g);
+    T pi[DIM];
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) pj[k] = pos[(int64_t)j * DIM + k];
-    c += within<T, DIM>(pi, pj, geo) ? 1 : 0;
+    for (int k = 0; k < DIM; ++k) pi[k] = pos[(int64_t)i * stride + k];
+    for (int j = 0; j < g.n_valid; ++j) {
+      T pj[DIM];
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) pj[k] = pos[(int64_t)j * stride + k];
+      c += within<T, DIM>(pi, pj, geo) ? 1 : 0;
+    }
   }
   cnt[i] = c;
 }
 
 template <typename T, int DIM>
-__global__ void fill_allpairs_kernel(GridDev g, const T* __restrict__ pos, const int32_t* __restrict__ off,
-                                     int32_t* __restrict__ idx, int e_cap) {
+__global__ void fill_allpairs_kernel(GridDev g, const T* __restrict__ pos, int64_t stride,
+                                     const int32_t* __restrict__ off, int32_t* __restrict__ idx, int e_cap) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.n) return;
+  if (i >= g.n_valid) return;
   Geo<T> geo(g);
   T pi[DIM];
 #pragma unroll
-  for (int k = 0; k < DIM; ++k) pi[k] = pos[(int64_t)i * DIM + k];
+  for (int k = 0; k < DIM; ++k) pi[k] = pos[(int64_t)i * stride + k];
   int w = off[i];
-  for (int j = 0; j < g.n; ++j) {
+  for (int j = 0; j < g.n_valid; ++j) {
     T pj[DIM];
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) pj[k] = pos[(int64_t)j * DIM + k];
+    for (int k = 0; k < DIM; ++k) pj[k] = pos[(int64_t)j * stride + k];
     if (within<T, DIM>(pi, pj, geo)) {
       if (w < e_cap) {
         idx[w] = j;
@@ -354,9 +396,10 @@ __global__ void fill_allpairs_kernel(GridDev g, const T* __restrict__ pos, const
   }
 }
 
-__global__ void nbr_finalize_kernel(const int32_t* __restrict__ off, int n, int cap, int e_cap, int have_list,
+// stats: [0] E, [1] max cell occupancy, [2] overflow bits (sticky), [3] reserved; tot = unclamped E
+__global__ void nbr_finalize_kernel(const int32_t* __restrict__ tot, int cap, int e_cap, int have_list,
                                     int32_t* stats) {
-  int e = off[n];
+  int e = *tot;
   stats[0] = e;
   int bits = 0;
   if (have_list && e > e_cap) bits |= LB200_OVF_NEIGHBOR_LIST;
@@ -373,12 +416,43 @@ __global__ void nbr_pad_kernel(int32_t* __restrict__ idx, int e_cap, int n, cons
   }
 }
 
-template <typename T, int DIM>
-static int nbr_build_t(const lb200_grid* gr, const T* pos, int cap, int32_t* idx, int e_cap, int32_t* stats,
-                       void* scratch, int64_t scratch_bytes, cudaStream_t s) {
-  const int n = gr->n;
+// ------------------------------------------------------------------ scratch layout of one build
+template <typename T>
+struct NbrBufs {
+  int32_t *cnt, *off, *tot, *hash, *sid, *cell_start;
+  T* spos;
+  // zeroed by ONE memset per build: cell_count | scan state (cells) | scan state (particles)
+  char* zero;
+  int64_t zero_bytes;
+  int32_t* cell_count;
+  unsigned long long *st_cells, *st_part;
+};
+
+template <typename T>
+static bool nbr_carve(const lb200_grid* gr, void* scratch, int64_t bytes, NbrBufs<T>* b, int64_t* need) {
+  const int64_t n = gr->n, nc = gr->use_cells ? gr->n_cells : 0;
+  Arena ar(scratch, bytes);
+  b->cnt = ar.take<int32_t>(n + 1);
+  b->off = ar.take<int32_t>(n + 1);
+  b->tot = ar.take<int32_t>(4);
+  b->hash = ar.take<int32_t>(n);
+  b->sid = ar.take<int32_t>(n);
+  b->cell_start = ar.take<int32_t>(nc + 1);
+  b->spos = ar.take<T>(n * 3);
+  const int64_t w_cells = scan_state_words(nc), w_part = scan_state_words(n);
+  b->zero = ar.take<char>((nc + 1) * 4 + 256 + (w_cells + w_part) * 8 + 256);
+  b->cell_count = reinterpret_cast<int32_t*>(b->zero);
+  b->st_cells = reinterpret_cast<unsigned long long*>(b->zero + align_up((nc + 1) * 4, 256));
+  b->st_part = b->st_cells + w_cells;
+  b->zero_bytes = (char*)(b->st_part + w_part) - b->zero;
+  if (need) *need = ar.off + 4096;
+  return scratch == nullptr ? true : ar.ok();
+}
+
+static GridDev grid_dev(const lb200_grid* gr, int cap) {
   GridDev g;
-  g.n = n;
+  g.n = gr->n;
+  g.n_valid = gr->n_valid > 0 && gr->n_valid < gr->n ? gr->n_valid : gr->n;
   g.dim = gr->dim;
   g.periodic = gr->periodic;
   g.use_cells = gr->use_cells;
@@ -390,51 +464,240 @@ static int nbr_build_t(const lb200_grid* gr, const T* pos, int cap, int32_t* idx
     g.box[k] = gr->box[k];
   }
   g.cutoff = gr->r_cutoff;
+  return g;
+}
 
-  Arena ar(scratch, scratch_bytes);
-  int32_t* cnt = ar.take<int32_t>(n + 1);
-  int32_t* off = ar.take<int32_t>(n + 1);
-  int32_t* scan_tmp = ar.take<int32_t>(scan_scratch_elems(n > gr->n_cells ? n : gr->n_cells) + 1);
-  const int tb = 128;
-  { stats_init_kernel<<<1, 1, 0, s>>>(stats); LB_LAUNCHED(1); }
-  if (gr->use_cells) {
-    const int nc = gr->n_cells;
-    int32_t* hash = ar.take<int32_t>(n);
-    int32_t* order = ar.take<int32_t>(n);
-    int32_t* cell_count = ar.take<int32_t>(2 * (nc + 1));
-    int32_t* cursor = cell_count + (nc + 1);
-    int32_t* cell_start = ar.take<int32_t>(nc + 1);
-    T* spos = ar.take<T>((int64_t)n * DIM);
-    if (!ar.ok()) return LB200_EINVAL;
-    LB_CHECK(cudaMemsetAsync(cell_count, 0, sizeof(int32_t) * 2 * (nc + 1), s));
-    { hash_kernel<T, DIM><<<cdiv(n, tb), tb, 0, s>>>(pos, g, hash, cell_count); LB_LAUNCHED(1); }
-    { max_occ_kernel<<<cdiv(nc, 256), 256, 0, s>>>(cell_count, nc, stats); LB_LAUNCHED(1); }
-    int rc = exclusive_scan_i32(cell_count, cell_start, nc, scan_tmp, s);
-    if (rc) return rc;
-    { cell_scatter_kernel<<<cdiv(n, tb), tb, 0, s>>>(hash, n, cell_start, cursor, order); LB_LAUNCHED(1); }
-    { cell_sort_kernel<<<cdiv(nc, tb), tb, 0, s>>>(cell_start, nc, order); LB_LAUNCHED(1); }
-    { gather_sorted_kernel<T, DIM><<<cdiv(n, tb), tb, 0, s>>>(pos, order, n, spos); LB_LAUNCHED(1); }
-    { count_kernel<T, DIM><<<cdiv(n, tb), tb, 0, s>>>(g, spos, order, cell_start, cnt); LB_LAUNCHED(1); }
-    rc = exclusive_scan_i32(cnt, off, n, scan_tmp, s);
-    if (rc) return rc;
-    if (idx != nullptr && e_cap > 0)
-      { fill_kernel<T, DIM><<<cdiv(n, tb), tb, 0, s>>>(g, spos, order, cell_start, off, idx, e_cap); LB_LAUNCHED(1); }
-  } else {
-    if (!ar.ok()) return LB200_EINVAL;
-    { count_allpairs_kernel<T, DIM><<<cdiv(n, tb), tb, 0, s>>>(g, pos, cnt); LB_LAUNCHED(1); }
-    int rc = exclusive_scan_i32(cnt, off, n, scan_tmp, s);
-    if (rc) return rc;
-    if (idx != nullptr && e_cap > 0)
-      { fill_allpairs_kernel<T, DIM><<<cdiv(n, tb), tb, 0, s>>>(g, pos, off, idx, e_cap); LB_LAUNCHED(1); }
-  }
+// hash -> cell scan (+ max occupancy into stats[1]) -> scatter -> per-cell sort + cell-ordered positions
+template <typename T, int DIM>
+static int build_cells(const GridDev& g, const T* pos, int64_t stride, const NbrBufs<T>& b, int32_t* stats,
+                       cudaStream_t s) {
+  const int tb = 128, nv = g.n_valid, nc = g.n_cells;
+  LB_CHECK(cudaMemsetAsync(b.zero, 0, b.zero_bytes, s));
+  LB_CHECK(cudaMemsetAsync(stats, 0, 2 * sizeof(int32_t), s));
+  { hash_kernel<T, DIM><<<cdiv(nv, tb), tb, 0, s>>>(pos, stride, g, b.hash, b.cell_count); LB_LAUNCHED(1); }
+  int rc = scan_lookback(b.cell_count, b.cell_start, nc, b.st_cells, 0x7fffffff, nullptr, stats + 1, s);
+  if (rc) return rc;
+  { cell_scatter_kernel<<<cdiv(nv, tb), tb, 0, s>>>(b.hash, nv, b.cell_start, b.cell_count, b.sid); LB_LAUNCHED(1); }
+  { cell_sort_gather_kernel<T, DIM><<<cdiv(nc, tb), tb, 0, s>>>(b.cell_start, nc, b.sid, pos, stride, b.spos); LB_LAUNCHED(1); }
+  return 0;
+}
+
+template <typename T, int DIM>
+static int nbr_build_t(const lb200_grid* gr, const T* pos, int cap, int32_t* idx, int e_cap, int32_t* stats,
+                       void* scratch, int64_t scratch_bytes, cudaStream_t s) {
+  const int n = gr->n;
+  const GridDev g = grid_dev(gr, cap);
+  NbrBufs<T> b;
+  if (!nbr_carve<T>(gr, scratch, scratch_bytes, &b, nullptr)) return LB200_EINVAL;
   const int have_list = idx != nullptr && e_cap > 0;
-  { nbr_finalize_kernel<<<1, 1, 0, s>>>(off, n, gr->use_cells ? cap : 0, e_cap, have_list, stats); LB_LAUNCHED(1); }
+  const int tb = 128;
+  if (gr->use_cells) {
+    int rc = build_cells<T, DIM>(g, pos, DIM, b, stats, s);
+    if (rc) return rc;
+    const int grid = cdiv((int64_t)g.n_valid * 32, kSweepThreads);
+    { count_kernel<T, DIM><<<grid, kSweepThreads, 0, s>>>(g, b.spos, b.sid, b.cell_start, b.cnt); LB_LAUNCHED(1); }
+    if (g.n_valid < n) { zero_tail_kernel<<<cdiv(n - g.n_valid, 256), 256, 0, s>>>(b.cnt, g.n_valid, n); LB_LAUNCHED(1); }
+    rc = scan_lookback(b.cnt, b.off, n, b.st_part, 0x7fffffff, b.tot, nullptr, s);
+    if (rc) return rc;
+    if (have_list)
+      { fill_kernel<T, DIM><<<grid, kSweepThreads, 0, s>>>(g, b.spos, b.sid, b.cell_start, b.off, idx, e_cap); LB_LAUNCHED(1); }
+  } else {
+    LB_CHECK(cudaMemsetAsync(b.zero, 0, b.zero_bytes, s));
+    LB_CHECK(cudaMemsetAsync(stats, 0, 2 * sizeof(int32_t), s));
+    { count_allpairs_kernel<T, DIM><<<cdiv(n, tb), tb, 0, s>>>(g, pos, DIM, b.cnt); LB_LAUNCHED(1); }
+    int rc = scan_lookback(b.cnt, b.off, n, b.st_part, 0x7fffffff, b.tot, nullptr, s);
+    if (rc) return rc;
+    if (have_list)
+      { fill_allpairs_kernel<T, DIM><<<cdiv(g.n_valid, tb), tb, 0, s>>>(g, pos, DIM, b.off, idx, e_cap); LB_LAUNCHED(1); }
+  }
+  { nbr_finalize_kernel<<<1, 1, 0, s>>>(b.tot, gr->use_cells ? cap : 0, e_cap, have_list, stats); LB_LAUNCHED(1); }
   if (have_list) { nbr_pad_kernel<<<cdiv(e_cap, 256), 256, 0, s>>>(idx, e_cap, n, stats); LB_LAUNCHED(1); }
   LB_LAUNCH_CHECK();
   return 0;
 }
 
-// ------------------------------------------------------------------ receiver-major CSR
+// ------------------------------------------------------------------ unordered sweep (receiver-major view)
+// One WARP per receiver v (sorted rank q).  The 3^d candidate cells are 3^(d-1) rows of three
+// x-adjacent cells, contiguous in the cell-ordered arrays (two pieces when the row wraps).  Lane r
+// prepares row r; then the warp walks each row 32 candidates at a time.  The predicate is the one
+// the LIST applies to the reverse pair -- metric(sender = center, receiver = candidate) -- so the
+// set of accepted senders is exactly the set of list entries whose receiver is v.
+template <typename T, int DIM, typename F>
+__device__ __forceinline__ void sweep_rows(int lane, const T* pv, const GridDev& g, const Geo<T>& geo,
+                                           const T* __restrict__ spos, const int32_t* __restrict__ cell_start, F f) {
+  int cc[3] = {0, 0, 0};
+  cell_hash<T, DIM>(pv, geo, g, cc);
+  constexpr int NROWS = DIM == 2 ? 3 : 9;
+  int a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+  if (lane < NROWS) {
+    int rowbase = 0;
+    {
+      int cy = cc[1] - (lane % 3 - 1);
+      cy = cy < 0 ? cy + g.nc[1] : (cy >= g.nc[1] ? cy - g.nc[1] : cy);
+      rowbase = cy * g.nc[0];
+      if (DIM == 3) {
+        int cz = cc[2] - (lane / 3 - 1);
+        cz = cz < 0 ? cz + g.nc[2] : (cz >= g.nc[2] ? cz - g.nc[2] : cz);
+        rowbase += cz * g.nc[0] * g.nc[1];
+      }
+    }
+    const int nx = g.nc[0], cx = cc[0];
+    if (cx > 0 && cx < nx - 1) {
+      a0 = cell_start[rowbase + cx - 1];
+      b0 = cell_start[rowbase + cx + 2];
+    } else if (cx == 0) {  // cells 0, 1 and the wrapped nx - 1 (nx >= 3)
+      a0 = cell_start[rowbase];
+      b0 = cell_start[rowbase + 2];
+      a1 = cell_start[rowbase + nx - 1];
+      b1 = cell_start[rowbase + nx];
+    } else {               // cells nx - 2, nx - 1 and the wrapped 0
+      a0 = cell_start[rowbase + nx - 2];
+      b0 = cell_start[rowbase + nx];
+      a1 = cell_start[rowbase];
+      b1 = cell_start[rowbase + 1];
+    }
+  }
+  for (int r = 0; r < NROWS; ++r) {
+#pragma unroll
+    for (int piece = 0; piece < 2; ++piece) {
+      const int a = __shfl_sync(0xffffffffu, piece ? a1 : a0, r), b = __shfl_sync(0xffffffffu, piece ? b1 : b0, r);
+      for (int t0 = a; t0 < b; t0 += 32) {
+        const int t = t0 + lane;
+        bool ok = false;
+        if (t < b) {
+          T pj[DIM];
+#pragma unroll
+          for (int k = 0; k < DIM; ++k) pj[k] = spos[(int64_t)t * DIM + k];
+          ok = within<T, DIM>(pj, pv, geo);
+        }
+        f(ok, t);
+      }
+    }
+  }
+}
+
+template <typename T, int DIM>
+__global__ void __launch_bounds__(kSweepThreads) count_in_kernel(GridDev g, int n_recv, const T* __restrict__ spos,
+                                                                 const int32_t* __restrict__ sid,
+                                                                 const int32_t* __restrict__ cell_start,
+                                                                 int32_t* __restrict__ cnt) {
+  const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (q >= g.n_valid) return;
+  const int v = sid[q];
+  int c = 0;
+  if (v < n_recv) {
+    Geo<T> geo(g);
+    T pv[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) pv[k] = spos[(int64_t)q * DIM + k];
+    sweep_rows<T, DIM>(lane, pv, g, geo, spos, cell_start,
+                       [&](bool ok, int) { c += __popc(__ballot_sync(0xffffffffu, ok)); });
+  }
+  if (lane == 0) cnt[v] = c;
+}
+
+// rel_disp = disp(p_receiver, p_sender) / r, rel_dist = |rel_disp|  (features.py:115-124), the
+// arithmetic of edge_feature_kernel (features.cu) in the position dtype, stored as float32
+template <typename T, int DIM>
+__device__ __forceinline__ float4 edge_feature(const T* pr, const T* ps, const Geo<T>& geo, T radius) {
+  float f[4] = {0.f, 0.f, 0.f, 0.f};
+  T ss = T(0);
+#pragma unroll
+  for (int k = 0; k < DIM; ++k) {
+    T d = disp1(pr[k], ps[k], geo.side[k], geo.half[k], geo.periodic[k]);
+    T nd = div_rn(d, radius);
+    f[k] = (float)nd;
+    ss = k == 0 ? mul_rn(nd, nd) : add_rn(ss, mul_rn(nd, nd));
+  }
+  f[DIM] = ss > T(0) ? (float)sqrt_rn(ss) : 0.f;
+  return make_float4(f[0], f[1], f[2], f[3]);
+}
+
+constexpr int kFastDeg = 64;  // in-degrees up to this are ranked in shared memory
+
+// rowptr holds CLAMPED offsets (<= e_cap): slots past the capacity are dropped (the step is then
+// flagged as overflowed and repeated by the caller).  tmp: int32[e_cap] scratch for in-degrees
+// beyond kFastDeg (the cell-ordered ranks of the bucket's senders are parked there before ranking).
+template <typename T, int DIM>
+__global__ void __launch_bounds__(kSweepThreads) fill_csr_kernel(
+    GridDev g, int n_recv, const T* __restrict__ spos, const int32_t* __restrict__ sid,
+    const int32_t* __restrict__ cell_start, const int32_t* __restrict__ rowptr, int32_t* __restrict__ snd,
+    int32_t* __restrict__ rcv, float4* __restrict__ edge_feat, int32_t* __restrict__ tmp, int e_cap) {
+  __shared__ int s_id[kSweepThreads / 32][kFastDeg];
+  __shared__ int s_t[kSweepThreads / 32][kFastDeg];
+  const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (q >= g.n_valid) return;
+  const int v = sid[q];
+  if (v >= n_recv) return;
+  const int base = rowptr[v], end = rowptr[v + 1];
+  if (end <= base) return;
+  int* ids = s_id[threadIdx.x >> 5];
+  int* ts = s_t[threadIdx.x >> 5];
+  Geo<T> geo(g);
+  const T radius = (T)g.cutoff;
+  T pv[DIM];
+#pragma unroll
+  for (int k = 0; k < DIM; ++k) pv[k] = spos[(int64_t)q * DIM + k];
+  int deg = 0;
+  sweep_rows<T, DIM>(lane, pv, g, geo, spos, cell_start, [&](bool ok, int t) {
+    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const int k = deg + __popc(m & ((1u << lane) - 1u));
+      if (k < kFastDeg) {
+        ids[k] = sid[t];
+        ts[k] = t;
+      } else if (base + k < e_cap) {
+        tmp[base + k] = t;
+      }
+    }
+    deg += __popc(m);
+  });
+  __syncwarp();
+  const int n_fast = min(deg, kFastDeg);
+  const int n_all = min(deg, e_cap - base);  // entries that were recorded (fast ones always are)
+  for (int k = lane; k < n_all; k += 32) {
+    const int t = k < kFastDeg ? ts[k] : tmp[base + k];
+    const int id = k < kFastDeg ? ids[k] : sid[t];
+    int rank = 0;
+    for (int j = 0; j < n_fast; ++j) rank += ids[j] < id ? 1 : 0;
+    for (int j = kFastDeg; j < n_all; ++j) rank += sid[tmp[base + j]] < id ? 1 : 0;
+    const int slot = base + rank;
+    if (slot < end) {
+      snd[slot] = id;
+      rcv[slot] = v;
+      if (edge_feat != nullptr) {
+        T ps[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) ps[d] = spos[(int64_t)t * DIM + d];
+        edge_feat[slot] = edge_feature<T, DIM>(pv, ps, geo, radius);
+      }
+    }
+  }
+}
+
+template <typename T, int DIM>
+static int nbr_csr_build_t(const lb200_grid* gr, const T* pos, int64_t stride, int cap, int n_recv, int32_t* rowptr,
+                           int32_t* snd, int32_t* rcv, float* edge_feat, int32_t* tmp, int e_cap, int32_t* stats,
+                           void* scratch, int64_t scratch_bytes, cudaStream_t s) {
+  const int n = gr->n;
+  const GridDev g = grid_dev(gr, cap);
+  NbrBufs<T> b;
+  if (!nbr_carve<T>(gr, scratch, scratch_bytes, &b, nullptr)) return LB200_EINVAL;
+  int rc = build_cells<T, DIM>(g, pos, stride, b, stats, s);
+  if (rc) return rc;
+  const int grid = cdiv((int64_t)g.n_valid * 32, kSweepThreads);
+  { count_in_kernel<T, DIM><<<grid, kSweepThreads, 0, s>>>(g, n_recv, b.spos, b.sid, b.cell_start, b.cnt); LB_LAUNCHED(1); }
+  if (g.n_valid < n) { zero_tail_kernel<<<cdiv(n - g.n_valid, 256), 256, 0, s>>>(b.cnt, g.n_valid, n); LB_LAUNCHED(1); }
+  rc = scan_lookback(b.cnt, rowptr, n, b.st_part, e_cap, b.tot, nullptr, s);
+  if (rc) return rc;
+  { fill_csr_kernel<T, DIM><<<grid, kSweepThreads, 0, s>>>(g, n_recv, b.spos, b.sid, b.cell_start, rowptr, snd, rcv,
+                                                           reinterpret_cast<float4*>(edge_feat), tmp, e_cap); LB_LAUNCHED(1); }
+  { nbr_finalize_kernel<<<1, 1, 0, s>>>(b.tot, cap, e_cap, 1, stats); LB_LAUNCHED(1); }
+  LB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ receiver-major CSR of ANY list
 __global__ void csr_degree_kernel(const int32_t* __restrict__ idx, int n, int e_cap, int32_t* __restrict__ deg) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= e_cap) return;
@@ -491,6 +754,7 @@ extern "C" int lb200_grid_init(lb200_grid* g, int32_t n, int32_t dim, int32_t po
                                const double* box, double r_cutoff) {
   if (!g || !box || (dim != 2 && dim != 3) || n < 1 || !(r_cutoff > 0)) return LB200_EINVAL;
   g->n = n;
+  g->n_valid = n;
   g->dim = dim;
   g->pos_f64 = pos_f64 ? 1 : 0;
   g->periodic = periodic;  // bit k: dimension k is periodic (the reference uses all-or-none, case.py:104)
@@ -527,14 +791,10 @@ extern "C" int lb200_grid_init(lb200_grid* g, int32_t n, int32_t dim, int32_t po
 }
 
 extern "C" int64_t lb200_nbr_scratch_bytes(const lb200_grid* g) {
-  int64_t n = g->n, nc = g->n_cells;
-  int64_t b = 0;
-  b += 2 * align_up((n + 1) * 4, 256);
-  b += align_up((scan_scratch_elems(n > nc ? n : nc) + 1) * 4, 256);
-  b += 2 * align_up(n * 4, 256);
-  b += align_up(2 * (nc + 1) * 4, 256) + align_up((nc + 1) * 4, 256);
-  b += align_up(n * 3 * 8, 256);
-  return b + 4096;
+  NbrBufs<double> b;
+  int64_t need = 0;
+  nbr_carve<double>(g, nullptr, 0, &b, &need);
+  return need;
 }
 
 extern "C" int lb200_nbr_build(const lb200_grid* g, const void* pos_dev, int32_t cell_capacity, int32_t* idx_dev,
@@ -556,6 +816,28 @@ extern "C" int lb200_nbr_build(const lb200_grid* g, const void* pos_dev, int32_t
                                scratch_bytes, s);
 }
 
+extern "C" int lb200_nbr_csr_build(const lb200_grid* g, const void* pos_dev, int64_t pos_stride,
+                                   int32_t cell_capacity, int32_t n_receivers, int32_t* rowptr_dev, int32_t* snd_dev,
+                                   int32_t* rcv_dev, float* edge_feat_dev, int32_t* tmp_dev, int32_t e_cap,
+                                   int32_t* stats_dev, void* scratch_dev, int64_t scratch_bytes, void* stream) {
+  if (!g || !pos_dev || !rowptr_dev || !snd_dev || !rcv_dev || !tmp_dev || !stats_dev || !scratch_dev || e_cap < 1 ||
+      cell_capacity < 1 || pos_stride < g->dim)
+    return LB200_EINVAL;
+  if (!g->use_cells) return LB200_EUNSUPPORTED;  // all-pairs boxes go through lb200_nbr_build + lb200_csr_build
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n_recv = n_receivers > 0 && n_receivers < g->n ? n_receivers : g->n;
+#define LB_CSR(T, D)                                                                                              \
+  return nbr_csr_build_t<T, D>(g, (const T*)pos_dev, pos_stride, cell_capacity, n_recv, rowptr_dev, snd_dev, rcv_dev, \
+                               edge_feat_dev, tmp_dev, e_cap, stats_dev, scratch_dev, scratch_bytes, s)
+  if (g->pos_f64) {
+    if (g->dim == 2) LB_CSR(double, 2);
+    LB_CSR(double, 3);
+  }
+  if (g->dim == 2) LB_CSR(float, 2);
+  LB_CSR(float, 3);
+#undef LB_CSR
+}
+
 extern "C" int64_t lb200_csr_scratch_bytes(int32_t n, int32_t e_cap) {
   (void)e_cap;
   return 2 * align_up(((int64_t)n + 1) * 4, 256) + align_up((scan_scratch_elems(n) + 1) * 4, 256) + 4096;
@@ -568,12 +850,11 @@ extern "C" int lb200_csr_build(const int32_t* idx_dev, int32_t n, int32_t e_cap,
     return LB200_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   Arena ar(scratch_dev, scratch_bytes);
-  int32_t* deg = ar.take<int32_t>(n + 1);
-  int32_t* cursor = ar.take<int32_t>(n + 1);
+  int32_t* deg = ar.take<int32_t>(2 * ((int64_t)n + 1));  // degree | cursor, zeroed together
+  int32_t* cursor = deg + (n + 1);
   int32_t* scan_tmp = ar.take<int32_t>(scan_scratch_elems(n) + 1);
   if (!ar.ok()) return LB200_EINVAL;
-  LB_CHECK(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (n + 1), s));
-  LB_CHECK(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (n + 1), s));
+  LB_CHECK(cudaMemsetAsync(deg, 0, sizeof(int32_t) * 2 * ((int64_t)n + 1), s));
   { csr_degree_kernel<<<cdiv(e_cap, 256), 256, 0, s>>>(idx_dev, n, e_cap, deg); LB_LAUNCHED(1); }
   int rc = exclusive_scan_i32(deg, rowptr_dev, n, scan_tmp, s);
   if (rc) return rc;

@@ -63,9 +63,10 @@ __global__ void rollout_step_done_kernel(const int32_t* __restrict__ nbr_stats, 
   if (nbr_stats[2] == 0) status[0] += 1;
 }
 
-__global__ void rollout_init_kernel(int32_t* nbr_stats, int32_t* status) {
+__global__ void rollout_init_kernel(int32_t* nbr_stats, int32_t* status, int first_frame) {
   nbr_stats[0] = nbr_stats[1] = nbr_stats[2] = nbr_stats[3] = 0;
-  status[0] = status[1] = status[2] = status[3] = 0;
+  status[0] = status[1] = status[2] = 0;
+  status[3] = first_frame;
 }
 
 
@@ -168,7 +169,7 @@ static GraphEntry* graph_capture(const std::string& key, cudaStream_t s, Step& o
 
 struct RolloutBufs {
   void* pos;
-  int32_t *stats, *rowptr, *perm, *snd, *rcv;
+  int32_t *stats, *rowptr, *perm, *snd, *rcv, *idx;
   float *node_feat, *edge_feat, *out;
   void *nbr_scratch, *csr_scratch, *gns_scratch;
   int64_t nbr_bytes, csr_bytes, gns_bytes;
@@ -180,9 +181,10 @@ static bool carve(const lb200_rollout_cfg* c, void* scratch, int64_t bytes, Roll
   b->pos = ar.take<double>(n * 3);
   b->stats = ar.take<int32_t>(8);
   b->rowptr = ar.take<int32_t>(n + 1);
-  b->perm = ar.take<int32_t>(e_cap);
+  b->perm = ar.take<int32_t>(e_cap);  // cell-list grids: scratch of the direct CSR build
   b->snd = ar.take<int32_t>(e_cap);
   b->rcv = ar.take<int32_t>(e_cap);
+  b->idx = c->grid.use_cells ? nullptr : ar.take<int32_t>(2 * e_cap);  // all-pairs grids go through the list
   b->node_feat = ar.take<float>(n * c->feat.node_stride);
   b->edge_feat = ar.take<float>(e_cap * 4);
   b->out = ar.take<float>(n * 3);
@@ -243,31 +245,46 @@ extern "C" int64_t lb200_rollout_scratch_bytes(const lb200_rollout_cfg* c) {
 
 extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, const float* weights_dev,
                                    void* window_dev, const int32_t* ptype_dev, const float* force_dev,
-                                   const void* targets_dev, void* preds_dev, int32_t* idx_dev,
+                                   const void* targets_dev, void* preds_dev, int32_t first_frame, int32_t* idx_dev,
                                    int32_t* status_dev, void* scratch_dev, int64_t scratch_bytes, void* stream) {
-  if (!c || !weights_dev || !window_dev || !ptype_dev || !idx_dev || !status_dev || !scratch_dev || n_steps < 0)
+  if (!c || !weights_dev || !window_dev || !ptype_dev || !status_dev || !scratch_dev || n_steps < 0 || first_frame < 0)
     return LB200_EINVAL;
   RolloutBufs b;
   if (!carve(c, scratch_dev, scratch_bytes, &b, nullptr)) return LB200_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   const int n = c->grid.n, dim = c->grid.dim, tw = c->feat.t_window;
   const int64_t esz = c->grid.pos_f64 ? 8 : 4;
-  { rollout_init_kernel<<<1, 1, 0, s>>>(b.stats, status_dev); LB_LAUNCHED(1); }
+  { rollout_init_kernel<<<1, 1, 0, s>>>(b.stats, status_dev, first_frame); LB_LAUNCHED(1); }
   // One step; targets / predictions are indexed on the device by status[0] (steps completed in this
   // call), so the very same launches serve every step -- and can be replayed from a CUDA graph.
+  const bool direct = c->grid.use_cells != 0;  // cell-list grids: receiver-major view straight from the cells
+  int32_t* const list = idx_dev != nullptr ? idx_dev : b.idx;
   auto one_step = [&]() -> int {
-    if (c->grid.pos_f64)
-      { extract_last_kernel<double><<<cdiv(n * dim, 256), 256, 0, s>>>((const double*)window_dev, n, tw, dim, (double*)b.pos); LB_LAUNCHED(1); }
-    else
-      { extract_last_kernel<float><<<cdiv(n * dim, 256), 256, 0, s>>>((const float*)window_dev, n, tw, dim, (float*)b.pos); LB_LAUNCHED(1); }
-    int rc = lb200_nbr_build(&c->grid, b.pos, c->cell_capacity, idx_dev, c->e_cap, b.stats, b.nbr_scratch,
-                             b.nbr_bytes, stream);
-    if (rc) return rc;
-    rc = lb200_csr_build(idx_dev, n, c->e_cap, b.rowptr, b.perm, b.snd, b.rcv, b.csr_scratch, b.csr_bytes, stream);
-    if (rc) return rc;
-    rc = lb200_features(&c->feat, window_dev, force_dev, idx_dev, c->e_cap, b.node_feat, b.edge_feat, stream);
-    if (rc) return rc;
-    rc = lb200_gns_forward(&c->gns, weights_dev, b.node_feat, b.edge_feat, ptype_dev, b.rowptr, b.perm, b.snd, b.rcv,
+    int rc;
+    if (!direct || idx_dev != nullptr) {  // the jax-md ordered list: all-pairs grids, or a caller that asked for it
+      if (c->grid.pos_f64)
+        { extract_last_kernel<double><<<cdiv(n * dim, 256), 256, 0, s>>>((const double*)window_dev, n, tw, dim, (double*)b.pos); LB_LAUNCHED(1); }
+      else
+        { extract_last_kernel<float><<<cdiv(n * dim, 256), 256, 0, s>>>((const float*)window_dev, n, tw, dim, (float*)b.pos); LB_LAUNCHED(1); }
+      rc = lb200_nbr_build(&c->grid, b.pos, c->cell_capacity, list, c->e_cap, b.stats, b.nbr_scratch, b.nbr_bytes, stream);
+      if (rc) return rc;
+    }
+    const int32_t* perm = nullptr;
+    if (direct) {
+      const char* last = (const char*)window_dev + (int64_t)(tw - 1) * dim * esz;
+      rc = lb200_nbr_csr_build(&c->grid, last, (int64_t)tw * dim, c->cell_capacity, 0, b.rowptr, b.snd, b.rcv,
+                               b.edge_feat, b.perm, c->e_cap, b.stats, b.nbr_scratch, b.nbr_bytes, stream);
+      if (rc) return rc;
+      rc = lb200_features(&c->feat, window_dev, force_dev, nullptr, 0, b.node_feat, nullptr, stream);
+      if (rc) return rc;
+    } else {
+      rc = lb200_csr_build(list, n, c->e_cap, b.rowptr, b.perm, b.snd, b.rcv, b.csr_scratch, b.csr_bytes, stream);
+      if (rc) return rc;
+      rc = lb200_features(&c->feat, window_dev, force_dev, list, c->e_cap, b.node_feat, b.edge_feat, stream);
+      if (rc) return rc;
+      perm = b.perm;
+    }
+    rc = lb200_gns_forward(&c->gns, weights_dev, b.node_feat, b.edge_feat, ptype_dev, b.rowptr, perm, b.snd, b.rcv,
                            b.out, b.gns_scratch, b.gns_bytes, stream);
     if (rc) return rc;
     rc = integrate_indexed(&c->integ, b.out, window_dev, ptype_dev, targets_dev, preds_dev, b.stats + 2, status_dev, s);

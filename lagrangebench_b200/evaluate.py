@@ -19,6 +19,7 @@ import torch
 
 from . import _cabi
 from .defaults import merged
+from .case_setup import NeighborList, num_real_particles
 from .models import GNS, gns_cfg
 from .utils import broadcast_from_batch, get_kinematic_mask, load_haiku, set_seed
 
@@ -95,20 +96,25 @@ class RolloutEngine:
         self.packed = model.packed_params(params)
         self.steps_per_sync = int(steps_per_sync)
         self._cfg = None
+        self._cfg_key = None
         self._scratch = None
         self._stream = None  # non-default stream: lets lb200_rollout_steps replay steps from a CUDA graph
         # persistent small buffers: stable device pointers let the library reuse its captured graph
         self._status = None
-        self._ptype = (None, None)  # (source tensor, int32 device copy)
+        self._ptype = (None, None, 0)  # (source, int32 device copy, number of real particles)
         self.n_reallocations = 0
         self.n_launch_calls = 0
 
-    def _configure(self, neighbors):
+    def _configure(self, neighbors, n_valid):
         lib = _cabi.load()
         h = self.h
         n = neighbors._grid.n
+        key = (id(neighbors._grid), n, n_valid, neighbors.max_occupancy, neighbors.cell_list_capacity)
+        if self._cfg is not None and self._cfg_key == key:
+            return
         cfg = _cabi.RolloutCfg()
         cfg.grid = neighbors._grid
+        cfg.grid.n_valid = n_valid
         cfg.feat = h["feature_cfg"](n)
         cfg.gns = gns_cfg(self.packed, n, neighbors.max_occupancy, cfg.feat.node_stride, cfg.feat.node_stride,
                           self.model.edge_impl)
@@ -117,8 +123,8 @@ class RolloutEngine:
         cfg.e_cap = neighbors.max_occupancy
         nbytes = lib.lb200_rollout_scratch_bytes(C.byref(cfg))
         if self._scratch is None or self._scratch.numel() < nbytes:
-            self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=neighbors.idx.device)
-        self._cfg = cfg
+            self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=neighbors.reference_position.device)
+        self._cfg, self._cfg_key, self._grid_ref = cfg, key, neighbors._grid
 
     def run(self, window, particle_type, targets, n_steps, neighbors=None, out=None):
         """Advance ``window`` (N, isl, d) in place by ``n_steps``.
@@ -126,20 +132,27 @@ class RolloutEngine:
         ``targets`` (n_steps, N, d) or None supplies the positions of kinematic particles.
         ``out``: optional preallocated ``(n_steps, N, d)`` tensor for the predictions (a caller that
         repeats a call with the very same buffers lets the library replay its captured step graph
-        from the first step on).  Returns ``(predictions (n_steps, N, d), neighbors)``."""
+        from the first step on).  Returns ``(predictions (n_steps, N, d), neighbors)``; the returned
+        list carries the capacities and builds its ``idx`` array on first access (the step loop
+        itself works on the receiver-major view of the graph)."""
         lib = _cabi.load()
         h = self.h
         assert window.is_cuda and window.is_contiguous() and window.dtype == h["dtype"]
         n, isl, dim = window.shape
         dev = window.device
         if self._ptype[0] is particle_type and self._ptype[1].device == dev:
-            ptype = self._ptype[1]
+            ptype, n_valid = self._ptype[1], self._ptype[2]
         else:
             ptype = torch.as_tensor(particle_type).to(dev, torch.int32).contiguous()
-            self._ptype = (particle_type, ptype)
-        if neighbors is None:
-            neighbors = h["neighbor_fn"].allocate(window[:, -1].contiguous())
-        self._configure(neighbors)
+            n_valid = num_real_particles(particle_type)
+            self._ptype = (particle_type, ptype, n_valid)
+        if ptype.shape[0] != n:
+            raise ValueError(f"particle_type has {ptype.shape[0]} rows, the position window {n}")
+        nfn = h["neighbor_fn"]
+        if neighbors is None or neighbors._grid is None or neighbors._grid.n != n:
+            # also a trajectory with another particle count than the list was allocated for (rollout.py:383)
+            neighbors = nfn.allocate(window[:, -1].contiguous(), num_particles=n_valid)
+        self._configure(neighbors, n_valid)
         if out is not None:
             assert out.shape == (n_steps, n, dim) and out.dtype == window.dtype and out.device == dev \
                 and out.is_contiguous()
@@ -158,22 +171,31 @@ class RolloutEngine:
         done = 0
         while done < n_steps:
             chunk = min(self.steps_per_sync, n_steps - done)
-            tgt = _cabi.ptr(targets[done:done + chunk]) if targets is not None else None
             self._stream.wait_stream(caller)
             with torch.cuda.stream(self._stream):
+                # base pointers + first frame: every chunk of a long rollout replays the same cached step graph
                 _cabi.check(lib.lb200_rollout_steps(
                     C.byref(self._cfg), chunk, _cabi.ptr(self.packed.blob), _cabi.ptr(window), _cabi.ptr(ptype), None,
-                    tgt, _cabi.ptr(preds[done:done + chunk]), _cabi.ptr(neighbors.idx), _cabi.ptr(status),
+                    _cabi.ptr(targets), _cabi.ptr(preds), done, None, _cabi.ptr(status),
                     _cabi.ptr(self._scratch), self._scratch.numel(), _cabi.stream()))
             caller.wait_stream(self._stream)
             self.n_launch_calls += 1
-            completed, overflow, _, _ = status.tolist()  # the one host sync per chunk
+            completed, overflow, n_edges, _ = status.tolist()  # the one host sync per chunk
             done += completed
             if overflow:  # rollout.py:135-151: re-allocate from the current state, retry the step
                 self.n_reallocations += 1
-                neighbors = h["neighbor_fn"].allocate(window[:, -1].contiguous())
-                self._configure(neighbors)
-        return preds, neighbors
+                neighbors = nfn.allocate(window[:, -1].contiguous(), num_particles=n_valid)
+                self._configure(neighbors, n_valid)
+        # the list a per-step caller would hold now: built (lazily) on the positions the last step started from
+        ref = window[:, -2] if (n_steps > 0 and isl > 1) else window[:, -1]
+        if n_steps > 0:
+            stats = torch.zeros(4, dtype=torch.int32, device=dev)
+            stats[0] = status[2]  # edges of the last step; the overflow bits are clear (the loop retried them away)
+        else:
+            stats = neighbors._stats
+        out_nl = NeighborList(nfn, None, stats, ref.clone(), neighbors.cell_list_capacity, neighbors.max_occupancy,
+                              neighbors._scratch, neighbors._grid)
+        return preds, out_nl
 
 
 # ----------------------------------------------------------------------------- reference loop

@@ -48,10 +48,11 @@ def case_builder(box, metadata, input_seq_length, cfg_neighbors=None, cfg_model=
     def _preprocess(sample, neighbors=None, is_allocate=False, mode="train", unroll_steps=0):
         pos_input = np.asarray(sample[0], dtype=dtype)
         most_recent_position = pos_input[:, input_seq_length - 1]
+        num_particles = int((np.asarray(sample[1]) != -1).sum())  # case.py:182
         if is_allocate:
-            neighbors = neighbor_fn.allocate(most_recent_position)
+            neighbors = neighbor_fn.allocate(most_recent_position, num_particles=num_particles)
         else:
-            neighbors = neighbors.update(most_recent_position)
+            neighbors = neighbors.update(most_recent_position, num_particles=num_particles)
         feats = feature_transform(pos_input[:, :input_seq_length], neighbors)
         if mode == "train":
             begin = input_seq_length - 2 + unroll_steps

@@ -61,8 +61,8 @@ class NeighborList:
         self.n_edges = n_edges  # un-truncated true edge count (oracle extra)
         self.update_fn = update_fn
 
-    def update(self, position, **kwargs):
-        return self.update_fn(position, self)
+    def update(self, position, num_particles=None, **kwargs):
+        return self.update_fn(position, self, num_particles=num_particles)
 
 
 class NeighborListFns:
@@ -130,9 +130,14 @@ def neighbor_list(displacement_fn, box, r_cutoff, capacity_multiplier=1.25, dtyp
             c = (coords - off[None, :]) % np.array(dims_rev)[None, :]
             nbr_cells[:, o] = np.ravel_multi_index(tuple(c.T), dims_rev)
 
-    def _build(position, nbrs):
+    def _build(position, nbrs, num_particles=None):
         position = np.asarray(position, dtype=dtype)
-        n = position.shape[0]
+        n_rows = position.shape[0]  # the pad value of the list
+        # ``num_particles`` (case.py:182-190): the first rows are real particles, the rest padding
+        # (``data.py:183-197``, particle type -1) that stays out of the search -- what the reference's
+        # matscipy backend, the only one that pads, does with it (jax-sph 0.0.3, unvendored)
+        n = n_rows if num_particles is None else int(num_particles)
+        position = position[:n]
         cell_overflow = False
         if with_cells:
             hashes = cell_hashes(position, cell_size, cells_per_side)
@@ -173,10 +178,10 @@ def neighbor_list(displacement_fn, box, r_cutoff, capacity_multiplier=1.25, dtyp
         n_edges = int(recv.shape[0])
         if nbrs is None:
             e_cap = int(n_edges * capacity_multiplier)
-            e_cap = min(e_cap, n * n_cand, n * n)
+            e_cap = min(e_cap, n_rows * n_cand if with_cells else n_rows * n_rows, n_rows * n_rows)
         else:
             e_cap = nbrs.max_occupancy
-        idx = np.full((2, e_cap), n, dtype=np.int32)
+        idx = np.full((2, e_cap), n_rows, dtype=np.int32)
         m = min(e_cap, n_edges)
         idx[0, :m] = recv[:m]
         idx[1, :m] = send[:m]
@@ -187,10 +192,10 @@ def neighbor_list(displacement_fn, box, r_cutoff, capacity_multiplier=1.25, dtyp
         out.cell_overflow = cell_overflow  # oracle extra: list contents are unspecified when set
         return out
 
-    def allocate(position, **kwargs):
-        return _build(position, None)
+    def allocate(position, num_particles=None, **kwargs):
+        return _build(position, None, num_particles)
 
-    def update(position, nbrs, **kwargs):
-        return _build(position, nbrs)
+    def update(position, nbrs, num_particles=None, **kwargs):
+        return _build(position, nbrs, num_particles)
 
     return NeighborListFns(allocate, update)

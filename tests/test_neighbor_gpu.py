@@ -141,3 +141,113 @@ def test_integrate_matches_oracle():
     assert np.array_equal(got, ref)
     got_v = ours.integrate({"vel": acc}, c["positions"]).cpu().numpy()
     assert np.array_equal(got_v, orac.integrate({"vel": acc}, c["positions"]))
+
+
+# ---- the receiver-major view built straight from the cells (lb200_nbr_csr_build) vs list -> csr_build
+def _csr_both_ways(ours, window, nbrs, n_receivers=0):
+    """-> (rowptr, snd, rcv, edge_feat[perm]) of the list path and of the direct build, as numpy."""
+    import ctypes as C
+
+    from lagrangebench_b200 import _cabi
+
+    lib = _cabi.load()
+    n, e_cap = window.shape[0], nbrs.max_occupancy
+    dev = window.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    st = _cabi.stream()
+    rowptr, perm, snd, rcv = torch.empty(n + 1, **i32), torch.empty(e_cap, **i32), torch.empty(e_cap, **i32), \
+        torch.empty(e_cap, **i32)
+    scratch = torch.empty(lib.lb200_csr_scratch_bytes(n, e_cap), dtype=torch.uint8, device=dev)
+    _cabi.check(lib.lb200_csr_build(_cabi.ptr(nbrs.idx), n, e_cap, _cabi.ptr(rowptr), _cabi.ptr(perm), _cabi.ptr(snd),
+                                    _cabi.ptr(rcv), _cabi.ptr(scratch), scratch.numel(), st))
+    fc = ours._lb200["feature_cfg"](n)
+    ef_list = torch.empty((e_cap, 4), dtype=torch.float32, device=dev)
+    _cabi.check(lib.lb200_features(C.byref(fc), _cabi.ptr(window), None, _cabi.ptr(nbrs.idx), e_cap, None,
+                                   _cabi.ptr(ef_list), st))
+    rowptr2, tmp, snd2, rcv2 = torch.empty(n + 1, **i32), torch.empty(e_cap, **i32), torch.full((e_cap,), -7, **i32), \
+        torch.full((e_cap,), -7, **i32)
+    ef2 = torch.zeros((e_cap, 4), dtype=torch.float32, device=dev)
+    stats = torch.zeros(4, **i32)
+    tw, dim = window.shape[1], window.shape[2]
+    last = window.data_ptr() + (tw - 1) * dim * window.element_size()
+    _cabi.check(lib.lb200_nbr_csr_build(C.byref(nbrs._grid), C.c_void_p(last), tw * dim, nbrs.cell_list_capacity,
+                                        n_receivers, _cabi.ptr(rowptr2), _cabi.ptr(snd2), _cabi.ptr(rcv2),
+                                        _cabi.ptr(ef2), _cabi.ptr(tmp), e_cap, _cabi.ptr(stats),
+                                        _cabi.ptr(nbrs._scratch), nbrs._scratch.numel(), st))
+    e = int(rowptr[n])
+    a = (rowptr.cpu().numpy(), snd[:e].cpu().numpy(), rcv[:e].cpu().numpy(), ef_list[perm[:e].long()].cpu().numpy())
+    e2 = int(rowptr2[n])
+    b = (rowptr2.cpu().numpy(), snd2[:e2].cpu().numpy(), rcv2[:e2].cpu().numpy(), ef2[:e2].cpu().numpy())
+    return a, b, stats.cpu().numpy()
+
+
+@pytest.mark.parametrize("name,dtype", [("tgv2d", "float32"), ("rpf2d", "float64"), ("dam2d", "float64"),
+                                        ("ldc3d", "float32"), ("rpf3d_8k", "float64"), ("ldc3d_28k", "float64")])
+def test_direct_csr_is_the_list_path_bit_for_bit(name, dtype):
+    c, ours, _ = build_pair(name, dtype)
+    window = torch.as_tensor(c["positions"][:, :6]).cuda().contiguous()
+    nbrs = ours._lb200["neighbor_fn"].allocate(window[:, -1].contiguous())
+    a, b, stats = _csr_both_ways(ours, window, nbrs)
+    assert stats[0] == nbrs.n_edges and stats[2] == 0
+    for x, y, what in zip(a, b, ("rowptr", "snd", "rcv", "edge features")):
+        assert np.array_equal(x, y), what
+    # domain decomposition: only the first n_receivers particles receive
+    n_recv = window.shape[0] // 3
+    a, b, _ = _csr_both_ways(ours, window, nbrs, n_receivers=n_recv)
+    e = a[0][n_recv]
+    assert b[0][-1] == e and np.array_equal(b[0][:n_recv + 1], a[0][:n_recv + 1])
+    for x, y in zip(a[1:], b[1:]):
+        assert np.array_equal(x[:e], y)
+
+
+def test_direct_csr_dense_bucket_and_capacity_clamp():
+    """In-degrees beyond the shared-memory fast path (a pile of particles), and a capacity smaller
+    than the edge count: the view is the truncated bucket structure, the flag is raised."""
+    c, ours, _ = build_pair("tgv2d", "float64")
+    pos = c["positions"][:, :6].copy()
+    rng = np.random.default_rng(5)
+    pile = rng.choice(pos.shape[0], 150, replace=False)
+    pos[pile] = pos[pile[0]] + 1e-4 * rng.standard_normal((150, 6, 2))
+    window = torch.as_tensor(pos).cuda().contiguous()
+    nbrs = ours._lb200["neighbor_fn"].allocate(window[:, -1].contiguous())
+    a, b, stats = _csr_both_ways(ours, window, nbrs)
+    assert np.diff(a[0]).max() >= 150 and stats[2] == 0
+    for x, y, what in zip(a, b, ("rowptr", "snd", "rcv", "edge features")):
+        assert np.array_equal(x, y), what
+    # shrink the capacity below the edge count
+    small = int(0.8 * nbrs.n_edges)
+    nbrs.max_occupancy, nbrs.idx = small, nbrs.idx[:, :small].contiguous()
+    _, b2, stats2 = _csr_both_ways(ours, window, nbrs)
+    assert stats2[2] & 1 and stats2[0] == stats[0]
+    assert b2[0][-1] == small and np.array_equal(b2[0], np.minimum(b[0], small))
+    full = b2[2] != -7  # slots of buckets cut by the capacity may stay unwritten
+    assert np.array_equal(b2[1][full], b[1][:small][full]) and np.array_equal(b2[2][full], b[2][:small][full])
+
+
+@pytest.mark.parametrize("name,dtype", [("tgv2d", "float32"), ("ldc3d", "float64")])
+def test_padding_particles_stay_out_of_the_search(name, dtype):
+    """``num_particles`` (case.py:182-190): rows of type PAD_VALUE appended by the loader
+    (data.py:183-197, all at the origin) are neither senders nor receivers."""
+    c, ours, orac = build_pair(name, dtype)
+    n_pad = 321
+    pos = np.concatenate([c["positions"][:, :6], np.zeros((n_pad,) + c["positions"][:, :6].shape[1:],
+                                                            c["positions"].dtype)])
+    ptype = np.concatenate([c["particle_type"], np.full(n_pad, -1, c["particle_type"].dtype)])
+    n_real = c["positions"].shape[0]
+    f_gpu, n_gpu = ours.allocate_eval((pos, ptype))
+    f_cpu, n_cpu = orac.allocate_eval((pos, ptype))
+    _, n_plain = orac.allocate_eval((c["positions"][:, :6], c["particle_type"]))
+    assert n_cpu.n_edges == n_plain.n_edges
+    idx = n_gpu.idx.cpu().numpy()
+    assert np.array_equal(idx, n_cpu.idx)
+    real = idx[0] < pos.shape[0]
+    assert real.sum() == n_plain.n_edges and idx[:, real].max() < n_real
+    assert np.array_equal(idx[:, real], n_plain.idx[:, :n_plain.n_edges])
+    _, u_gpu = ours.preprocess_eval((pos, ptype), n_gpu)
+    assert np.array_equal(u_gpu.idx.cpu().numpy(), n_cpu.idx)
+    # the direct view leaves the padding rows without buckets
+    window = torch.as_tensor(pos).cuda().to(f_gpu["abs_pos"].dtype).contiguous()
+    a, b, _ = _csr_both_ways(ours, window, n_gpu)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert b[0][n_real] == b[0][-1]

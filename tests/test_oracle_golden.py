@@ -140,3 +140,24 @@ def test_segment_sum_drops_pad():
     data = np.arange(12, dtype=np.float64).reshape(6, 2)
     out = gns.segment_sum(data, np.array([0, 2, 2, 3, 0, 3]), 3)
     assert np.array_equal(out, [[8, 10], [0, 0], [6, 8]])
+
+
+def test_num_particles_keeps_padding_out_of_the_search():
+    """``case.py:182-190`` + ``data.py:183-197``: trailing PAD_VALUE rows (all at the origin) are
+    neither senders nor receivers; the list of the real particles is unchanged, the pad value is
+    the padded row count."""
+    from lagrangebench_b200 import synthetic
+
+    c = synthetic.make_case("tgv2d", 6, 0, 0, np.float32)
+    orac = ocase.case_builder(c["box"], c["metadata"], 6, cfg_neighbors={"multiplier": 1.25}, dtype=np.float32)
+    n_pad = 77
+    pos = np.concatenate([c["positions"][:, :6], np.zeros((n_pad, 6, 2), np.float32)])
+    ptype = np.concatenate([c["particle_type"], np.full(n_pad, -1, np.int32)])
+    _, padded = orac.allocate_eval((pos, ptype))
+    _, plain = orac.allocate_eval((c["positions"][:, :6], c["particle_type"]))
+    e = plain.n_edges
+    assert padded.n_edges == e and padded.max_occupancy == plain.max_occupancy
+    assert np.array_equal(padded.idx[:, :e], plain.idx[:, :e])
+    assert (padded.idx[:, e:] == pos.shape[0]).all()
+    _, again = orac.preprocess_eval((pos, ptype), padded)
+    assert np.array_equal(again.idx, padded.idx) and not again.did_buffer_overflow
