@@ -432,22 +432,148 @@ def run_ours(args):
                 "value": n_cpu / t_cpu, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                 "sample": f"1 full rollout step of the NumPy oracle on a {args.workload} sub-lattice {dims} = "
                           f"{n_cpu} particles / {e_cpu} edges ({t_cpu:.1f} s)"}
+    # strong scaling of ONE sharded 1 M-particle cloud over the same ranks (every N, N = 1 included)
+    ss = None
+    if not args.no_strong_scaling:
+        del engine, engine_e, preds, preds_buf, targets_all, window, window_p, window_e
+        torch.cuda.empty_cache()
+        ss = strong_scaling_leg(args, world, rank, dev, max(K, 20), max(W, 3))
+    if rank == 0:
+        line["strong_scaling"] = ss
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_sharded(args):
-    """ONE cloud sharded over the ranks (slab decomposition + halo exchange, domain.py):
-    strong scaling of the periodic RPF-3D clouds (BASELINE.json configs[4])."""
+def strong_scaling_leg(args, world, rank, dev, K, W):
+    """ONE periodic cloud (BASELINE.json configs[4]: RPF-3D, 1 M particles) sharded over all ranks: slab
+    decomposition, peer-memory halo, device-resident step loop (domain.py).  Run at every N, N = 1 included,
+    so that the driver's per-N lines carry the strong-scaling series.  Returns the dict of the
+    ``strong_scaling`` key (rank 0) or None.
+
+    Correctness rides along: the first ``check_steps`` steps are compared with the single-GPU engine
+    (rank 0 rolls the whole cloud out alone) -- max |dpos| in units of dx -- plus position checksums."""
     import ctypes as C
 
     import torch
     import torch.distributed as dist
 
-    from lagrangebench_b200 import _cabi
+    from lagrangebench_b200 import GNS, RolloutEngine, _cabi, case_builder
     from lagrangebench_b200 import models as lbmodels
     from lagrangebench_b200.domain import DistributedRollout
+
+    lib = _cabi.load()
+    name = args.scaling_workload
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    spec = build_workload(name, 0, args.seed, "float32")
+    d = spec["metadata"]["dim"]
+    dx = spec["metadata"]["dx"]
+    n_total = spec["positions"].shape[0]
+    params = lbmodels.init_params(node_in_of(spec), d, 128, MP_STEPS, 16, seed=args.seed)
+    tdt = torch.float64 if args.dtype == "float64" else torch.float32
+    check_steps = args.check_steps
+    dr = DistributedRollout(spec["box"], spec["metadata"], params, MP_STEPS, force=spec["force"], dtype=tdt,
+                            multiplier=spec["multiplier"], noise_std=0.0, steps_per_sync=max(K, W, check_steps, 1))
+    dr.scatter(spec["positions"], spec["particle_type"])
+    # ---- correctness against the single-GPU trajectory
+    dr.run(check_steps)
+    pos_sharded = dr.gather_positions(n_total)
+    check = None
+    if rank == 0:
+        case = case_builder(spec["box"], spec["metadata"], 6, cfg_neighbors={"multiplier": spec["multiplier"]},
+                            external_force_fn=spec["force"], dtype=args.dtype, noise_std=0.0)
+        eng = RolloutEngine(case, GNS(d, 128, 2, MP_STEPS, 16), params, steps_per_sync=check_steps)
+        w1 = torch.as_tensor(spec["positions"][:, :6]).to(dev, tdt).contiguous()
+        ref, _ = eng.run(w1, spec["particle_type"], None, check_steps)
+        diff = case.displacement(pos_sharded, ref[-1]).abs().max().item()
+        check = {"steps": check_steps, "against": "single-GPU engine on rank 0, same initial cloud",
+                 "max_abs_dpos": diff, "max_dpos_over_dx": diff / dx,
+                 "checksum_sharded": float(pos_sharded.double().sum().item()),
+                 "checksum_single": float(ref[-1].double().sum().item())}
+        del eng, w1, ref
+    del pos_sharded
+    torch.cuda.empty_cache()
+    # ---- timing: W warm-up steps, then K steps = one call, one host synchronisation
+    dr.run(W)
+    barrier()
+    launches0 = lib.lb200_launch_count()
+    sel0, real0 = dr.n_selections, dr.n_reallocations
+    sampler = ClockSampler(dev.index, period_s=0.025)  # NVML queries share a driver lock with kernel launches
+    if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    dr.run(K)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.lb200_launch_count() - launches0
+    # ---- kernel leg: a few eager steps with an event pair around every message / node kernel launch
+    kp = min(K, 5)
+    lib.lb200_profile(1)
+    dr.run(kp)
+    torch.cuda.synchronize()
+    kms, kl = (C.c_double * 2)(), (C.c_int64 * 2)()
+    _cabi.check(lib.lb200_profile_read(kms, kl))
+    lib.lb200_profile(0)
+    n_own, n_edges = dr.window.shape[0], dr.edges_last
+    per_rank = {"particles": n_own, "ghosts": dr.n_ghost_left + dr.n_ghost_right, "edges": n_edges,
+                "halo_rows_sent": dr.halo_rows, "message_kernel_ms": kms[0] / max(kl[0], 1),
+                "node_kernel_ms": kms[1] / max(kl[1], 1)}
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        cnt = torch.tensor([float(launches), float(n_own)], device=dev, dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        launches, owned_total = int(cnt[0].item()), int(cnt[1].item())
+        tables = [None] * world
+        dist.all_gather_object(tables, per_rank)
+    else:
+        owned_total, tables = n_own, [per_rank]
+    out = None
+    if rank == 0:
+        assert owned_total == n_total, "particles lost in migration"
+        peaks, peak_kind = measured_peaks()
+        edge_ms = per_rank["message_kernel_ms"]
+        alg_bytes = EDGE_BYTES * n_edges + NODE_BYTES * n_own
+        achieved = alg_bytes / (edge_ms * 1e-3) / 1e9 if edge_ms > 0 else 0.0
+        out = {
+            "workload": name, "particles": n_total, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "value": n_total * K / (ms * 1e-3), "unit": UNIT, "scaling": "strong",
+            "positions": args.dtype, "mp_steps": MP_STEPS,
+            "multi_gpu": "slab decomposition along axis %d; ghost positions and the sender projections of boundary "
+                         "rows stored into the neighbours' peer-mapped heaps (node-kernel epilogue), one signal/wait "
+                         "kernel per exchange, status bits OR-ed over the ranks on the device; steps replayed from a "
+                         "CUDA graph, one host synchronisation per %d steps" % (dr.axis, K),
+            "halo_bytes_per_step_rank0": dr.halo_bytes + dr.halo_rows * d * (8 if args.dtype == "float64" else 4),
+            "halo_margin": dr.halo_margin, "ghost_selections_in_timed_region": dr.n_selections - sel0,
+            "reallocations_in_timed_region": dr.n_reallocations - real0,
+            "per_rank": tables, "gpu_launches": launches,
+            "roofline_rank0": {"kernel": "edge_mp_tc2_kernel", "bound": "hbm", "achieved": achieved,
+                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                               "peak_source": peak_kind, "avg_launch_ms": edge_ms, "algorithmic_bytes": alg_bytes},
+            "check": check, "clocks": clocks,
+        }
+    dr.close()
+    del dr
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_sharded(args):
+    """``--sharded``: only the strong-scaling leg, printed as the line's main value (manual runs)."""
+    import torch
+    import torch.distributed as dist
+
+    from lagrangebench_b200 import _cabi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -457,105 +583,14 @@ def run_sharded(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lib = _cabi.load()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    K, W = args.steps, args.warmup
-    spec = build_workload(args.workload, 0, args.seed, "float32")
-    d = spec["metadata"]["dim"]
-    n_total = spec["positions"].shape[0]
-    params = lbmodels.init_params(node_in_of(spec), d, 128, MP_STEPS, 16, seed=args.seed)
-    tdt = torch.float64 if args.dtype == "float64" else torch.float32
-    dr = DistributedRollout(spec["box"], spec["metadata"], params, MP_STEPS, force=spec["force"], dtype=tdt,
-                            multiplier=spec["multiplier"], noise_std=0.0, timing=True)
-    dr.scatter(spec["positions"], spec["particle_type"])
-    for _ in range(W):
-        dr.step()
-    barrier()
-    dr.read_phase_ms()  # drop the warm-up marks
-    launches0 = lib.lb200_launch_count()
-    lib.lb200_profile(1)
-    sampler = ClockSampler(local_rank, period_s=0.025)  # NVML queries share a driver lock with kernel launches
+    args.scaling_workload = args.workload if args.workload.startswith("rpf3d") else args.scaling_workload
+    ss = strong_scaling_leg(args, world, rank, dev, args.steps, args.warmup)
     if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    halo_bytes = 0
-    barrier()
-    ev0.record()
-    for _ in range(K):
-        dr.step()
-        halo_bytes += dr.halo_bytes
-    ev1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    phase_ms = {k: round(v, 3) for k, v in dr.read_phase_ms().items()}
-    phase_host_ms = {k: round(v, 3) for k, v in dr.phase_host_ms.items()}
-    dr.timing = False
-    if world > 1:  # every rank's table (device time between marks, host time enqueuing)
-        tables = [None] * world
-        dist.all_gather_object(tables, {"device": phase_ms, "host": phase_host_ms})
-    else:
-        tables = [{"device": phase_ms, "host": phase_host_ms}]
-    launches = lib.lb200_launch_count() - launches0
-    kms, kl = (C.c_double * 2)(), (C.c_int64 * 2)()
-    _cabi.check(lib.lb200_profile_read(kms, kl))
-    lib.lb200_profile(0)
-    n_own, n_edges = dr.window.shape[0], dr.edges_last
-    # end-to-end: every step also reads the rank's new positions back to pinned host memory
-    esz = 8 if args.dtype == "float64" else 4
-    h_out = torch.empty((int(n_own * 1.2) + 1024, d), dtype=tdt).pin_memory()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        dr.step()
-        cur = dr.window[:, -1]
-        h_out[:cur.shape[0]].copy_(cur, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
-        cnt = torch.tensor([float(launches), float(dr.window.shape[0])], device=dev, dtype=torch.float64)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        launches, owned_total = int(cnt[0].item()), int(cnt[1].item())
-    else:
-        owned_total = dr.window.shape[0]
-    if rank == 0:
-        assert owned_total == n_total, "particles lost in migration"
-        peaks, peak_kind = measured_peaks()
-        edge_ms_avg = kms[0] / max(kl[0], 1)
-        alg_bytes = EDGE_BYTES * n_edges + NODE_BYTES * n_own
-        achieved = alg_bytes / (edge_ms_avg * 1e-3) / 1e9 if edge_ms_avg > 0 else 0.0
-        line = {
-            "metric": METRIC.replace("LDC-3D", args.workload), "value": n_total * K / (ms * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "particles": n_total, "particles_rank0": n_own,
-                       "edges_rank0": n_edges, "ghosts_rank0": dr.n_ghost_left + dr.n_ghost_right,
-                       "mp_steps": MP_STEPS, "latent": 128, "positions": args.dtype,
-                       "multi_gpu": f"slab decomposition along axis {dr.axis}, halo exchange of P per MP step (NCCL)",
-                       "halo_bytes_per_step_rank0": halo_bytes // max(K, 1),
-                       "phase_ms_per_rank": tables, "reallocations_rank0": dr.n_reallocations,
-                       "dynamics": "quiet synthetic statistics (synthetic.py), noise_std 0",
-                       "l2": "inputs larger than L2 (edge latents %.0f MB per rank)" % (n_edges * 512 / 1e6)},
-            "roofline": {"bound": "hbm", "kernel": "edge_mp_tc2_kernel (rank 0)", "achieved": achieved,
-                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": None, "peak_source": peak_kind, "avg_launch_ms": edge_ms_avg,
-                         "launches": int(kl[0]), "share_of_step": kms[0] / ms,
-                         "node_kernel_share_of_step": kms[1] / ms},
-            "e2e": {"value": n_total * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": n_total * d * esz},
-            "gpu_launches": launches, "clocks": clocks,
-        }
+        line = {"metric": METRIC.replace("LDC-3D", ss["workload"]), "value": ss["value"], "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ss["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": ss["workload"], "particles": ss["particles"]}, "strong_scaling": ss,
+                "gpu_launches": ss["gpu_launches"], "clocks": ss["clocks"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -573,6 +608,11 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=12000, help="particles in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong-scaling", action="store_true",
+                    help="skip the sharded 1 M-particle leg (the strong_scaling key of the line)")
+    ap.add_argument("--scaling-workload", default="rpf3d_1m")
+    ap.add_argument("--check-steps", type=int, default=2,
+                    help="steps of the sharded cloud compared with the single-GPU engine before timing")
     ap.add_argument("--sharded", action="store_true",
                     help="shard ONE periodic cloud over the GPUs (slab decomposition, strong scaling) "
                          "instead of one replica per GPU")

@@ -34,6 +34,10 @@ extern "C" {
 /* overflow flag bits, mirroring jax-md's PartitionErrorCode */
 #define LB200_OVF_NEIGHBOR_LIST 1 /* E > E_cap: list truncated */
 #define LB200_OVF_CELL_LIST 2     /* a cell holds more particles than cell_capacity */
+/* status bits of a decomposed rollout (lb200_shard), OR-ed over all ranks before they take effect */
+#define LB200_OVF_DRIFT 4         /* a particle moved further than the halo margin covers: choose new ghost sets */
+#define LB200_OVF_PEER_TIMEOUT 8  /* a neighbour's signal did not arrive (a rank died): the rollout is void */
+#define LB200_MAX_RANKS 16
 
 int lb200_version(void);
 const char* lb200_error_string(int code);
@@ -173,6 +177,46 @@ typedef struct {
   int64_t tc_w, tc_vec;
 } lb200_mlp_off;
 
+/* ------------------------------------------------------------------------------------
+ * Domain decomposition of ONE cloud over the GPUs of a box (no reference counterpart: the reference
+ * is single-device).  One process per GPU; the box is cut into slabs along `axis`; a
+ * rank's local cloud is  [ owned | ghosts from the left neighbour | ghosts from the right neighbour ].
+ * Ghost sets are chosen on the host (halo = cutoff + margin) and stay FIXED until a particle has
+ * moved more than drift_limit along the cut axis (LB200_OVF_DRIFT), so that steps need no host
+ * round trip: every exchange is a store into peer-mapped memory plus a device-side signal.
+ *
+ * Peer heap: one cudaMalloc block per rank, identical layout everywhere (lb200_peer_heap_layout),
+ * shared with the other processes by CUDA IPC:  control words | positions of the local cloud
+ * [n_cap][3] double | two projection arrays [n_cap][256] float (alternating by message-passing step).
+ */
+typedef struct lb200_shard_s {
+  int32_t rank, world;
+  int32_t has_left, has_right;         /* 0: open boundary on that side (non-periodic cut axis) */
+  int32_t n_owned, n_ghost_left, n_ghost_right;
+  int32_t n_send_left, n_send_right;
+  const int32_t* push_left;            /* dev int32[n_owned]: k if row v is the k-th row the left neighbour holds */
+  const int32_t* push_right;           /*                     as a ghost (ascending v), -1 otherwise */
+  int32_t dst_row_left, dst_row_right; /* first row of my block inside the left / right neighbour's local cloud */
+  int32_t axis;
+  int32_t n_cap;                       /* rows per array of the heap layout (uniform across ranks) */
+  double shift_left, shift_right;      /* added to the cut-axis coordinate of rows sent left / right (periodic wrap) */
+  double axis_length;                  /* box length along the cut axis if it is periodic, else 0 */
+  const void* ref_coord;               /* dev T[n_owned]: cut-axis coordinate when the ghost sets were chosen */
+  double drift_limit;
+  void* heap;                          /* this rank's heap */
+  void* heap_left;                     /* the neighbours' heaps mapped into this process (or NULL) */
+  void* heap_right;
+  void* heap_all[LB200_MAX_RANKS];     /* every rank's heap ([rank] == heap): status bits go to all of them */
+} lb200_shard;
+
+/* bytes of a heap for n_cap rows, and the byte offsets of its parts */
+int64_t lb200_peer_heap_layout(int32_t n_cap, int64_t* off_pos, int64_t* off_p0, int64_t* off_p1);
+/* cudaMalloc + zeroed control words; handle64 receives the 64-byte CUDA IPC handle other processes open */
+int lb200_peer_heap_create(int64_t bytes, void** heap_out, void* handle64_out);
+int lb200_peer_heap_open(const void* handle64, void** heap_out);
+int lb200_peer_heap_close(void* peer_heap);   /* a mapping obtained from lb200_peer_heap_open */
+int lb200_peer_heap_destroy(void* heap);      /* a heap obtained from lb200_peer_heap_create */
+
 typedef struct {
   int32_t n, dim, num_mp_steps;
   int32_t node_in;          /* node feature columns (without embedding) */
@@ -188,15 +232,13 @@ typedef struct {
                                   pipelined tiles);
                                1: fp32 CUDA-core kernel (kept as the numerical cross-check);
                                2: first tensor-core kernel (weights in shared memory) */
-  /* Domain decomposition (0 / NULL on a single GPU): rows [0, n_owned) of the node arrays are
-   * this rank's particles, rows [n_owned, n) are ghosts whose projections P arrive from the
-   * neighbouring ranks.  Node kernels run over owned rows, edge kernels over edges whose
-   * receiver is owned.  halo_fn(halo_ctx, m) is called on the host after the node projections
-   * feeding message-passing step m have been enqueued (m = 0 .. num_mp_steps-1): it must enqueue,
-   * on the same stream, the exchange that fills the ghost rows of P (lb200_gns_scratch_layout). */
+  /* Domain decomposition (0 / NULL on a single GPU): rows [0, n_owned) of the node arrays are this
+   * rank's particles, rows [n_owned, n) ghosts.  Node kernels run over owned rows, edge kernels over
+   * the edges whose receiver is owned; the sender projections of the ghost rows arrive from the
+   * neighbouring ranks through peer-mapped memory (lb200_shard below): the node kernel's epilogue stores
+   * its boundary rows into the neighbours' arrays, one signal/wait kernel per message-passing step. */
   int32_t n_owned;
-  void (*halo_fn)(void* ctx, int32_t mp_step);
-  void* halo_ctx;
+  const struct lb200_shard_s* shard;
 } lb200_gns_cfg;
 
 /* device scratch the forward needs, in bytes (node latents, projections, edge latents ...) */
@@ -267,6 +309,9 @@ typedef struct {
   lb200_integrate_cfg integ;
   int32_t cell_capacity;
   int32_t e_cap;
+  /* decomposed cloud (NULL: single GPU): grid.n = gns.n = local cloud (owned + ghosts), feat.n = integ.n =
+   * gns.n_owned = owned rows; window / ptype / targets / preds hold the OWNED rows; gns.shard = this too */
+  const lb200_shard* shard;
 } lb200_rollout_cfg;
 
 int64_t lb200_rollout_scratch_bytes(const lb200_rollout_cfg* c);

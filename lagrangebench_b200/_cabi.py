@@ -46,10 +46,26 @@ class GnsCfg(C.Structure):
                 ("node_stride", C.c_int32), ("embed_size", C.c_int32), ("num_particle_types", C.c_int32),
                 ("e_cap", C.c_int32), ("embedding", C.c_int64), ("enc_node", MlpOff), ("enc_edge", MlpOff),
                 ("dec", MlpOff), ("proc_edge", C.POINTER(MlpOff)), ("proc_node", C.POINTER(MlpOff)),
-                ("edge_impl", C.c_int32), ("n_owned", C.c_int32), ("halo_fn", C.c_void_p), ("halo_ctx", C.c_void_p)]
+                ("edge_impl", C.c_int32), ("n_owned", C.c_int32), ("shard", C.c_void_p)]
 
 
-HALO_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int32)
+MAX_RANKS = 16
+OVF_DRIFT = 4
+OVF_PEER_TIMEOUT = 8
+
+
+class Shard(C.Structure):
+    """``lb200_shard``: one rank's view of a slab decomposition (include/lb200.h)."""
+
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("has_left", C.c_int32), ("has_right", C.c_int32),
+                ("n_owned", C.c_int32), ("n_ghost_left", C.c_int32), ("n_ghost_right", C.c_int32),
+                ("n_send_left", C.c_int32), ("n_send_right", C.c_int32),
+                ("push_left", C.c_void_p), ("push_right", C.c_void_p),
+                ("dst_row_left", C.c_int32), ("dst_row_right", C.c_int32), ("axis", C.c_int32), ("n_cap", C.c_int32),
+                ("shift_left", C.c_double), ("shift_right", C.c_double), ("axis_length", C.c_double),
+                ("ref_coord", C.c_void_p), ("drift_limit", C.c_double),
+                ("heap", C.c_void_p), ("heap_left", C.c_void_p), ("heap_right", C.c_void_p),
+                ("heap_all", C.c_void_p * MAX_RANKS)]
 
 
 class IntegrateCfg(C.Structure):
@@ -60,7 +76,7 @@ class IntegrateCfg(C.Structure):
 
 class RolloutCfg(C.Structure):
     _fields_ = [("grid", Grid), ("feat", FeatureCfg), ("gns", GnsCfg), ("integ", IntegrateCfg),
-                ("cell_capacity", C.c_int32), ("e_cap", C.c_int32)]
+                ("cell_capacity", C.c_int32), ("e_cap", C.c_int32), ("shard", C.c_void_p)]
 
 
 _VP, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64
@@ -83,6 +99,11 @@ _SIGNATURES = {
     "lb200_rollout_scratch_bytes": (_I64, [C.POINTER(RolloutCfg)]),
     "lb200_rollout_steps": (C.c_int, [C.POINTER(RolloutCfg), _I32, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _I64,
                                       _VP]),
+    "lb200_peer_heap_layout": (_I64, [_I32, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
+    "lb200_peer_heap_create": (C.c_int, [_I64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "lb200_peer_heap_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "lb200_peer_heap_close": (C.c_int, [_VP]),
+    "lb200_peer_heap_destroy": (C.c_int, [_VP]),
     "lb200_tc_selftest": (C.c_int, [_VP, _VP]),
     "lb200_launch_count": (_I64, []),
     "lb200_profile": (C.c_int, [_I32]),

@@ -37,6 +37,19 @@ int integrate_indexed(const lb200_integrate_cfg* c, const float* out_dev, void* 
                       const void* target_dev, void* pred_out_dev, const int32_t* skip_flag_dev,
                       const int32_t* step_counter_dev, cudaStream_t s);
 
+// decomposed rollout (peer.cu): views into the peer heaps and the exchange / status kernels
+float* shard_p_local(const lb200_shard* sh, int which);
+float* shard_p_left(const lb200_shard* sh, int which);
+float* shard_p_right(const lb200_shard* sh, int which);
+void* shard_pos_local(const lb200_shard* sh);
+const int32_t* shard_skip_flag(const lb200_shard* sh);
+int shard_exchange(const lb200_shard* sh, int k, int per_step, cudaStream_t s);
+int shard_push_positions(const lb200_shard* sh, const void* window, int tw, int dim, int pos_f64, cudaStream_t s);
+int shard_flag_bcast(const lb200_shard* sh, const int32_t* nbr_stats, cudaStream_t s);
+int shard_flag_wait(const lb200_shard* sh, cudaStream_t s);
+int shard_step_done(const lb200_shard* sh, const int32_t* nbr_stats, int32_t* status, cudaStream_t s);
+int shard_call_init(const lb200_shard* sh, cudaStream_t s);
+
 // optional CUDA-event timing of a kernel class on its launch stream (lb200_profile)
 void prof_begin(int cls, cudaStream_t s);
 void prof_end(int cls, cudaStream_t s);

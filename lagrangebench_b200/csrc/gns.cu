@@ -594,6 +594,32 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   float* cl = ar.take<float>((int64_t)(n_sub + 1) * kLatent);
   if (!ar.ok()) return LB200_EINVAL;
   const float* w = weights_dev;
+  // Decomposed cloud: the projections live in the peer heap, two arrays alternating by message-passing
+  // step (a neighbour's store for step m + 1 can then never race this rank's message kernel of step m);
+  // exchange 0 of a step is the ghost positions (rollout.cu), exchanges 1 .. num_mp_steps the projections.
+  const lb200_shard* sh = c->shard;
+  const int per_step = c->num_mp_steps + 1;
+  if (sh != nullptr) {
+    if (c->edge_impl == 1 || c->enc_node.tc_w < 0 || c->enc_node.tc_vec < 0) return LB200_EUNSUPPORTED;
+    if (n > sh->n_cap || n_own != sh->n_owned) return LB200_EINVAL;
+  }
+  auto p_of = [&](int m) -> float* { return sh != nullptr ? shard_p_local(sh, m) : P; };
+  auto set_push = [&](NodeTcArgs& na, int m_out) {  // the node kernel writing projection array m_out
+    na.P_left = na.P_right = nullptr;
+    na.push_left = na.push_right = nullptr;
+    na.dst_left = na.dst_right = 0;
+    if (sh == nullptr) return;
+    if (sh->has_left && sh->n_send_left > 0) {
+      na.P_left = shard_p_left(sh, m_out);
+      na.push_left = sh->push_left;
+      na.dst_left = sh->dst_row_left;
+    }
+    if (sh->has_right && sh->n_send_right > 0) {
+      na.P_right = shard_p_right(sh, m_out);
+      na.push_right = sh->push_right;
+      na.dst_right = sh->dst_row_right;
+    }
+  };
 
   NodeEncArgs ne;
   ne.n = n_own;
@@ -607,7 +633,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   ne.enc = mlp_ptrs(w, c->enc_node);
   ne.nxt = mlp_ptrs(w, c->proc_edge[0]);
   ne.h = h;
-  ne.P = P;
+  ne.P = p_of(0);
   if (c->edge_impl != 1 && c->enc_node.tc_w >= 0 && c->enc_node.tc_vec >= 0) {
     // tensor-core encoder: the node-update kernel in encoder mode over the zero-padded input features
     rc = launch_node_embed(node_feat_dev, c->node_in, c->node_stride, ptype_dev, w + c->embedding, c->embed_size,
@@ -625,10 +651,12 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     na.w_tc = w + c->enc_node.tc_w;
     na.vec_tc = w + c->enc_node.tc_vec;
     na.h = h;
-    na.P = P;
+    na.P = p_of(0);
     na.out = out_dev;
+    set_push(na, 0);
     rc = launch_node_mp_tc(na, s);
     if (rc) return rc;
+    if (sh != nullptr) shard_exchange(sh, 1, per_step, s);
   } else {
     node_encoder_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeEnc, s>>>(ne);
     LB_LAUNCHED(1);
@@ -666,7 +694,6 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   }
 
   for (int m = 0; m < c->num_mp_steps; ++m) {
-    if (c->halo_fn) c->halo_fn(c->halo_ctx, m);  // ghost rows of P for this step (enqueued on `s`)
     const lb200_mlp_off& eo = c->proc_edge[m];
     prof_begin(0, s);
     if (c->edge_impl != 1 && eo.tc_w >= 0 && eo.tc_vec >= 0) {
@@ -675,7 +702,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       et.rowptr = rowptr_dev;
       et.snd = snd_dev;
       et.rcv = rcv_dev;
-      et.P = P;
+      et.P = p_of(m);
       et.w_tc = w + eo.tc_w;
       et.vec_tc = w + eo.tc_vec;
       et.e = e;
@@ -694,7 +721,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       em.rowptr = rowptr_dev;
       em.snd = snd_dev;
       em.rcv = rcv_dev;
-      em.P = P;
+      em.P = p_of(m);
       em.mlp = mlp_ptrs(w, eo);
       em.e = e;
       em.agg = agg;
@@ -720,10 +747,12 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       nt_args.w_tc = w + no.tc_w;
       nt_args.vec_tc = w + no.tc_vec;
       nt_args.h = h;
-      nt_args.P = P;
+      nt_args.P = p_of(m + 1);
       nt_args.out = out_dev;
+      set_push(nt_args, m + 1);
       rc = launch_node_mp_tc(nt_args, s);
       if (rc) return rc;
+      if (sh != nullptr && !last) shard_exchange(sh, m + 2, per_step, s);
     } else {
       NodeMpArgs nm;
       nm.n = n_own;
@@ -736,7 +765,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       nm.mlp = mlp_ptrs(w, no);
       nm.nxt = last ? mlp_ptrs(w, c->dec) : mlp_ptrs(w, c->proc_edge[m + 1]);
       nm.h = h;
-      nm.P = P;
+      nm.P = p_of(m + 1);
       nm.out = out_dev;
       { node_mp_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeMp, s>>>(nm); LB_LAUNCHED(1); }
     }

@@ -559,14 +559,30 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
     if (!a.last) {
       if (warp == 0) load_w(kEnc ? 3 : 4);
       float* const prow = a.P + (row0 + g * 32) * (2 * kLatent) + f;
+      const bool push = a.P_left != nullptr || a.P_right != nullptr;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         float hh[16], xx[16];
         tmem_ld_pair16(acc_hh + t_addr + hf * 16, acc_x + t_addr + hf * 16, hh, xx);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (hf * 16 + j < valid) prow[(int64_t)(hf * 16 + j) * (2 * kLatent)] = fmaf(xx[j], kLoInv, hh[j]);
+          if (hf * 16 + j < valid) {
+            const float val = fmaf(xx[j], kLoInv, hh[j]);
+            prow[(int64_t)(hf * 16 + j) * (2 * kLatent)] = val;
+            if (push) {  // boundary rows: the same 128-byte segment goes into the neighbour's ghost row (NVLink store)
+              const int64_t v = row0 + g * 32 + hf * 16 + j;
+              if (a.P_left != nullptr) {
+                const int k = __ldg(a.push_left + v);
+                if (k >= 0) a.P_left[(int64_t)(a.dst_left + k) * (2 * kLatent) + f] = val;
+              }
+              if (a.P_right != nullptr) {
+                const int k = __ldg(a.push_right + v);
+                if (k >= 0) a.P_right[(int64_t)(a.dst_right + k) * (2 * kLatent) + f] = val;
+              }
+            }
+          }
       }
+      if (push) __threadfence_system();  // peer stores are performed before the kernel completes (exchange kernel follows)
       tc_fence_before();
       __syncthreads();  // every warp has drained the accumulators
       // ---- receiver projection P[:, 128:256] = h W1r + b1(next)

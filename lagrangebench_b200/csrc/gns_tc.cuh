@@ -36,6 +36,11 @@ struct NodeTcArgs {
   const void* w_tc;     // 5 (4 when last) streamed operands, each hi|lo = 64 KB, UMMA K-major layout
   const float* vec_tc;  // b1 | b2c | ln_scale | ln_offset | b_next | wd1[128][3] | bd1[4]
   float *h, *P, *out;
+  // decomposed cloud: the sender half of the projections of boundary rows also goes into the neighbours'
+  // arrays (peer-mapped): row v -> row dst_* + push_*[v] there.  NULL: no neighbour on that side.
+  float *P_left, *P_right;
+  const int32_t *push_left, *push_right;
+  int dst_left, dst_right;
 };
 
 int launch_node_mp_tc(const NodeTcArgs& a, cudaStream_t s);

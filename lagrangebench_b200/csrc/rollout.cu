@@ -98,10 +98,13 @@ static std::string graph_key(const lb200_rollout_cfg* c, const void* w, const vo
   const size_t off_gns = offsetof(lb200_rollout_cfg, gns);
   memset(&k[off_gns + offsetof(lb200_gns_cfg, proc_edge)], 0, sizeof(void*));
   memset(&k[off_gns + offsetof(lb200_gns_cfg, proc_node)], 0, sizeof(void*));
+  memset(&k[off_gns + offsetof(lb200_gns_cfg, shard)], 0, sizeof(void*));
+  memset(&k[offsetof(lb200_rollout_cfg, shard)], 0, sizeof(void*));
   for (int m = 0; m < c->gns.num_mp_steps; ++m) {
     key_put(k, c->gns.proc_edge[m]);
     key_put(k, c->gns.proc_node[m]);
   }
+  if (c->shard != nullptr) key_put(k, *c->shard);  // counts, tables and heap addresses of the decomposition
   const void* ptrs[] = {w, window, ptype, force, targets, preds, idx, status, scratch, stream};
   key_put(k, ptrs);
   key_put(k, scratch_bytes);
@@ -258,9 +261,42 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
   // One step; targets / predictions are indexed on the device by status[0] (steps completed in this
   // call), so the very same launches serve every step -- and can be replayed from a CUDA graph.
   const bool direct = c->grid.use_cells != 0;  // cell-list grids: receiver-major view straight from the cells
+  const lb200_shard* sh = c->shard;
+  if (sh != nullptr) {
+    if (!direct || c->gns.shard != sh || c->gns.n_owned != sh->n_owned || c->integ.n != sh->n_owned ||
+        c->feat.n != sh->n_owned || n != sh->n_owned + sh->n_ghost_left + sh->n_ghost_right || n > sh->n_cap ||
+        sh->world > LB200_MAX_RANKS)
+      return LB200_EINVAL;
+    int rc = shard_call_init(sh, s);
+    if (rc) return rc;
+  }
   int32_t* const list = idx_dev != nullptr ? idx_dev : b.idx;
   auto one_step = [&]() -> int {
     int rc;
+    if (sh != nullptr) {
+      // decomposed cloud: [owned | ghosts]; every exchange is a store into the neighbours' heaps + one
+      // signal/wait kernel; the status bits are OR-ed over all ranks before integrate takes effect
+      rc = shard_push_positions(sh, window_dev, tw, dim, c->grid.pos_f64, s);
+      if (rc) return rc;
+      rc = shard_exchange(sh, 0, c->gns.num_mp_steps + 1, s);
+      if (rc) return rc;
+      rc = lb200_nbr_csr_build(&c->grid, shard_pos_local(sh), dim, c->cell_capacity, sh->n_owned, b.rowptr, b.snd,
+                               b.rcv, b.edge_feat, b.perm, c->e_cap, b.stats, b.nbr_scratch, b.nbr_bytes, stream);
+      if (rc) return rc;
+      rc = shard_flag_bcast(sh, b.stats, s);
+      if (rc) return rc;
+      rc = lb200_features(&c->feat, window_dev, force_dev, nullptr, 0, b.node_feat, nullptr, stream);
+      if (rc) return rc;
+      rc = lb200_gns_forward(&c->gns, weights_dev, b.node_feat, b.edge_feat, ptype_dev, b.rowptr, nullptr, b.snd,
+                             b.rcv, b.out, b.gns_scratch, b.gns_bytes, stream);
+      if (rc) return rc;
+      rc = shard_flag_wait(sh, s);
+      if (rc) return rc;
+      rc = integrate_indexed(&c->integ, b.out, window_dev, ptype_dev, targets_dev, preds_dev, shard_skip_flag(sh),
+                             status_dev, s);
+      if (rc) return rc;
+      return shard_step_done(sh, b.stats, status_dev, s);
+    }
     if (!direct || idx_dev != nullptr) {  // the jax-md ordered list: all-pairs grids, or a caller that asked for it
       if (c->grid.pos_f64)
         { extract_last_kernel<double><<<cdiv(n * dim, 256), 256, 0, s>>>((const double*)window_dev, n, tw, dim, (double*)b.pos); LB_LAUNCHED(1); }
@@ -295,8 +331,8 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
   // Launch-bound inner loop (about 100 launches per step): steps are replayed from a CUDA graph, which is
   // kept across calls -- every argument a step depends on is part of the key, so a per-step caller
   // (steps_per_sync = 1) replays too.  Not on the legacy default stream (capture is unsupported there),
-  // not while per-kernel events are on, not with a host halo callback inside the forward.
-  const bool graph_ok = s != nullptr && s != cudaStreamLegacy && !prof_enabled() && c->gns.halo_fn == nullptr &&
+  // not while per-kernel events are on.
+  const bool graph_ok = s != nullptr && s != cudaStreamLegacy && !prof_enabled() &&
                         getenv("LB200_NO_GRAPH") == nullptr;
   int t = 0;
   if (graph_ok && n_steps > 0) {

@@ -24,7 +24,28 @@ def test_single_rank_domain_path_equals_engine():
     assert "max|dpos|=0.000e+00" in out  # world == 1: same kernels, same order -> bitwise
 
 
+def _torchrun(nproc, port, *args):
+    return [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+            "--master-addr", "127.0.0.1", "--master-port", str(port), TOOL, *args]
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_rank_decomposition_matches_single_gpu():
-    _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-          "--master-addr", "127.0.0.1", "--master-port", "29577", TOOL, "--case", "rpf3d_8k", "--steps", "3"])
+    _run(_torchrun(2, 29577, "--case", "rpf3d_8k", "--steps", "3"))
+
+
+def test_two_ranks_sharing_one_gpu_peer_memory_path():
+    """The peer-memory halo (IPC-mapped heaps, epilogue stores, signal/wait kernels, all-rank status OR)
+    with both ranks on cuda:0 -- their contexts time-slice, so it is slow but it is the very code path
+    of a multi-GPU box, on the one-GPU box the driver runs the tests on."""
+    out = _run(_torchrun(2, 29578, "--case", "rpf3d_8k", "--steps", "3", "--same-gpu"))
+    assert "world=2" in out
+
+
+def test_three_ranks_sharing_one_gpu_with_reselection_and_migration():
+    """Particles drift across the slab faces: the device-side drift bit stops the chunk, every rank
+    migrates / re-selects its ghosts, and the rollout still equals the single-GPU one."""
+    out = _run(_torchrun(3, 29579, "--case", "rpf3d_8k", "--steps", "6", "--same-gpu", "--spread", "0.12",
+                         "--mp", "3"))
+    sel = int(out.split("selections=")[1].split()[0])
+    assert sel >= 2, out

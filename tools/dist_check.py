@@ -23,26 +23,42 @@ def main():
     ap.add_argument("--case", default="rpf3d_8k")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--mp", type=int, default=10)
+    ap.add_argument("--same-gpu", action="store_true",
+                    help="all ranks on cuda:0 (time-sliced contexts), gloo for the host plumbing: the peer-memory "
+                         "path on a one-GPU box")
+    ap.add_argument("--spread", type=float, default=0.0,
+                    help="velocity scale in units of dx per step (0: the case's own statistics): makes particles "
+                         "cross slab faces, so ghost re-selection and migration run")
+    ap.add_argument("--sync", type=int, default=32, help="steps per host synchronisation")
+    ap.add_argument("--margin", type=float, default=0.25)
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
+    local = 0 if args.same_gpu else int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if args.same_gpu:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     c = synthetic.make_case(args.case, 6, 0, 0, np.float32)
+    if args.spread > 0:  # a coherent drift along every axis plus the case's jitter
+        dx = c["metadata"]["dx"]
+        drift = args.spread * dx * np.arange(6, dtype=np.float32)[None, :, None]
+        c["positions"] = np.mod(c["positions"][:, :6] + drift, c["box"].astype(np.float32)).astype(np.float32)
+        c["metadata"]["vel_mean"] = [args.spread * dx] * c["metadata"]["dim"]
     d = c["metadata"]["dim"]
     n = c["positions"].shape[0]
     params = lbmodels.init_params(5 * d + d, d, 128, args.mp, 16, seed=0)
     dr = DistributedRollout(c["box"], c["metadata"], params, args.mp, force=c["force"], dtype=torch.float32,
-                            multiplier=c["multiplier"]).scatter(c["positions"], c["particle_type"])
+                            multiplier=c["multiplier"], halo_margin=args.margin, steps_per_sync=args.sync)
+    dr.scatter(c["positions"], c["particle_type"])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        dr.step()
+    dr.run(args.steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     pos = dr.gather_positions(n)
-    owned = torch.tensor([dr.window.shape[0]], device="cuda")
+    owned = torch.tensor([dr.window.shape[0]], device="cpu" if args.same_gpu else "cuda")
     if world > 1:
         dist.all_reduce(owned)
     if rank == 0:
@@ -56,10 +72,12 @@ def main():
         dx = c["metadata"]["dx"]
         print(f"world={world} N={n} steps={args.steps} owned_total={int(owned)} edges_rank0={dr.edges_last} "
               f"ghosts_rank0={dr.n_ghost_left + dr.n_ghost_right} max|dpos|={diff:.3e} ({diff / dx:.2e} dx) "
-              f"{1e3 * dt / args.steps:.2f} ms/step reallocs={dr.n_reallocations}", flush=True)
+              f"{1e3 * dt / args.steps:.2f} ms/step reallocs={dr.n_reallocations} selections={dr.n_selections} "
+              f"migrations={dr.n_migrations}", flush=True)
         assert int(owned) == n, "particles lost or duplicated in migration"
         assert diff <= 1e-5 * dx + 8 * np.finfo(np.float32).eps * float(np.max(c["box"])), "decomposed rollout diverged"
         print("DIST_CHECK_OK", flush=True)
+    dr.close()
     if world > 1:
         dist.destroy_process_group()
 

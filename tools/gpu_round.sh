@@ -10,6 +10,6 @@ tail -5 gpurun_out/${tag}_tests.log
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 tail -c 1500 gpurun_out/${tag}_bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_launches.log 2>&1
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-strong-scaling > gpurun_out/${tag}_launches.log 2>&1
 python profiles/summarize_launches.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_launches.summary.txt 2>&1
 head -30 gpurun_out/${tag}_launches.summary.txt
