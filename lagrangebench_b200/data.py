@@ -7,11 +7,13 @@ reader of :mod:`lagrangebench_b200.h5lite` (h5py is not part of this image); the
 download path (no network) -- ``dataset_path`` must exist.
 
 The reference loads a JAX ``force_fn`` from the dataset's ``force.py`` (``data.py:87-101``).
-JAX is not available here and the feature kernel evaluates forces on the device, so the
-force fields of the shipped datasets are provided as :class:`PiecewiseForce` objects keyed
-by dataset name (``dataset_force``): reverse Poiseuille flow pushes ``+x`` in the lower
-half of the box and ``-x`` in the upper half, the dam break has constant gravity along
-``-y`` (``notebooks/data_gen.ipynb`` cells 11-19 of the reference).
+Here the file is executed too (``force_from_file``; with ``jax.numpy`` standing in as NumPy when
+JAX is not installed), probed over the domain and turned into the :class:`PiecewiseForce` the
+feature kernel evaluates on the device -- constant fields and ``jnp.where(r[axis] > t, a, b)``
+fields, which is what the shipped datasets contain; anything else stays a Python callable
+(evaluated on the host side of the per-step loop).  Only when a dataset has no ``force.py`` does
+the name-keyed ``dataset_force`` table apply (reverse Poiseuille flow: ``+x`` below ``y = 1``,
+``-x`` above, ``notebooks/data_gen.ipynb`` cells 11 / 13 of the reference).
 """
 
 import bisect
@@ -49,14 +51,97 @@ def get_dataset_name_from_path(path):
 def dataset_force(name, metadata):
     """External force of a shipped dataset as a device-evaluable :class:`PiecewiseForce`, or None."""
     d = int(metadata["dim"])
-    if name in ("rpf2d", "rpf3d"):
-        y_mid = 0.5 * (metadata["bounds"][1][0] + metadata["bounds"][1][1])
-        return PiecewiseForce(axis=1, threshold=y_mid, lo=[1.0] + [0.0] * (d - 1), hi=[-1.0] + [0.0] * (d - 1))
-    if name == "dam2d":
-        g = [0.0] * d
-        g[1] = -1.0
-        return PiecewiseForce.constant(g)
+    if name in ("rpf2d", "rpf3d"):  # jnp.where(r[:, 1] > 1.0, -1.0, 1.0) * e_x  (data_gen.ipynb cells 11, 13)
+        return PiecewiseForce(axis=1, threshold=1.0, lo=[1.0] + [0.0] * (d - 1), hi=[-1.0] + [0.0] * (d - 1))
     return None
+
+
+def _load_force_module(path):
+    """Execute a dataset's ``force.py`` (``data.py:87-95``).  Without JAX, ``jax`` / ``jax.numpy``
+    resolve to NumPy for the duration of the import (the files use a handful of array functions)."""
+    import importlib.util
+    import sys
+    import types
+
+    shims = {}
+    try:
+        import jax  # noqa: F401
+    except ImportError:
+        fake = types.ModuleType("jax")
+        fake.numpy = np
+        fake.vmap = lambda f, *a, **k: (lambda x: np.stack([np.asarray(f(row)) for row in x]))
+        fake.jit = lambda f, *a, **k: f
+        shims = {"jax": fake, "jax.numpy": np}
+    saved = {k: sys.modules.get(k) for k in shims}
+    sys.modules.update(shims)
+    try:
+        spec = importlib.util.spec_from_file_location("force_module", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod.force_fn
+
+
+def force_from_file(path, metadata, n_probe=4096, seed=0):
+    """``force.py`` -> :class:`PiecewiseForce` when the field is constant or switches once along one
+    axis (checked on probe points, threshold located by bisection, the side the threshold itself falls on
+    verified); otherwise the function itself, vectorised over ``(N, d)`` positions."""
+    fn = _load_force_module(path)
+    d = int(metadata["dim"])
+    bounds = np.asarray(metadata["bounds"], dtype=np.float64)
+    lo_b, hi_b = bounds[:, 0], bounds[:, 1]
+    rng = np.random.default_rng(seed)
+
+    def f(r):
+        return np.asarray(fn(np.asarray(r, dtype=np.float64)), dtype=np.float64).reshape(d)
+
+    def vectorised(pos):
+        import torch
+
+        p = torch.as_tensor(pos).detach().cpu().numpy()
+        out = np.stack([f(row) for row in p]) if len(p) else np.zeros((0, d))
+        return torch.as_tensor(out, dtype=torch.float32)
+
+    probes = lo_b + (hi_b - lo_b) * rng.random((n_probe, d))
+    vals = np.stack([f(p) for p in probes])
+    uniq = np.unique(vals, axis=0)
+    if len(uniq) == 1:
+        return PiecewiseForce.constant(uniq[0].tolist())
+    if len(uniq) == 2:
+        for axis in range(d):
+            is_a = np.all(vals == uniq[0], axis=1)
+            xa, xb = probes[is_a, axis], probes[~is_a, axis]
+            if xa.max() < xb.min():
+                lo_v, hi_v, left, right = uniq[0], uniq[1], xa.max(), xb.min()
+            elif xb.max() < xa.min():
+                lo_v, hi_v, left, right = uniq[1], uniq[0], xb.max(), xa.min()
+            else:
+                continue
+            base = 0.5 * (lo_b + hi_b)
+            for _ in range(200):  # bisection on the switching coordinate
+                mid = 0.5 * (left + right)
+                if mid == left or mid == right:
+                    break
+                q = base.copy()
+                q[axis] = mid
+                if np.array_equal(f(q), lo_v):
+                    left = mid
+                else:
+                    right = mid
+            # PiecewiseForce is hi for r[axis] > threshold: the threshold is the last coordinate with the low value
+            cand = PiecewiseForce(axis, left, lo_v.tolist(), hi_v.tolist())
+            check = np.concatenate([probes, [np.where(np.arange(d) == axis, left, base),
+                                             np.where(np.arange(d) == axis, right, base)]])
+            ok = all(np.array_equal(f(p), np.asarray(cand.hi if p[axis] > cand.threshold else cand.lo)) for p in check)
+            if ok:
+                return cand
+    warnings.warn(f"{path}: force field is not piecewise-constant along one axis; it stays a host callable")
+    return vectorised
 
 
 def numpy_collate(batch):
@@ -94,7 +179,13 @@ class H5Dataset:
         self.nl_backend = nl_backend
         with open(osp.join(dataset_path, "metadata.json")) as f:
             self.metadata = json.load(f)
-        self.external_force_fn = dataset_force(self.name, self.metadata)
+        force_fn_path = osp.join(dataset_path, "force.py")
+        if osp.exists(force_fn_path):  # data.py:87-95
+            self.external_force_fn = force_from_file(force_fn_path, self.metadata)
+        else:  # the reference raises for dam2d / rpf2d / rpf3d (data.py:96-101); RPF's field is known from its generator
+            if self.name == "dam2d":
+                raise FileNotFoundError(f"External force function not found in {dataset_path} (force.py).")
+            self.external_force_fn = dataset_force(self.name, self.metadata)
         self.db_hdf5 = None
         with H5File(self.file_path) as f:
             self.traj_keys = list(f.keys())

@@ -89,7 +89,44 @@ def test_dataset_names_and_forces():
     meta = {"dim": 2, "bounds": [[0.0, 1.0], [0.0, 2.0]]}
     f = dataset_force("rpf2d", meta)
     assert (f.axis, f.threshold, f.lo, f.hi) == (1, 1.0, [1.0, 0.0], [-1.0, 0.0])
-    assert dataset_force("dam2d", meta).lo == [0.0, -1.0] and dataset_force("tgv2d", meta) is None
+    assert dataset_force("dam2d", meta) is None and dataset_force("tgv2d", meta) is None  # dam2d: force.py or nothing
+
+
+FORCE_FILES = {
+    # the forms the reference's datasets ship (single-particle ``force_fn(r)``, vmapped in features.py:105-107)
+    "rpf": ("import jax.numpy as jnp\n\n\ndef force_fn(r):\n"
+            "    return jnp.where(r[1] > 1.0, jnp.array([-1.0, 0.0]), jnp.array([1.0, 0.0]))\n"),
+    "dam": "import jax.numpy as jnp\n\n\ndef force_fn(r):\n    return jnp.array([0.0, -1.0])\n",
+    "dam_up": "import jax.numpy as jnp\n\n\ndef force_fn(r):\n    return jnp.ones_like(r) * jnp.array([0.0, 1.0])\n",
+    "ge": ("import jax.numpy as jnp\n\n\ndef force_fn(r):\n"
+           "    return jnp.where(r[0] >= 0.25, jnp.array([0.0, 2.0]), jnp.array([0.0, -2.0]))\n"),
+    "smooth": "import jax.numpy as jnp\n\n\ndef force_fn(r):\n    return jnp.array([jnp.sin(r[1]), 0.0])\n",
+}
+
+
+def test_force_py_is_read_and_probed(tmp_path):
+    """``data.py:87-101``: the dataset's own ``force.py`` decides the force -- sign, threshold and the side
+    the threshold itself falls on -- not a name-keyed table."""
+    from lagrangebench_b200.case_setup import PiecewiseForce
+    from lagrangebench_b200.data import force_from_file
+
+    meta = {"dim": 2, "bounds": [[0.0, 1.0], [0.0, 2.0]]}
+    paths = {}
+    for k, src in FORCE_FILES.items():
+        paths[k] = tmp_path / f"force_{k}.py"
+        paths[k].write_text(src)
+    f = force_from_file(str(paths["rpf"]), meta)
+    assert isinstance(f, PiecewiseForce) and (f.axis, f.threshold, f.lo, f.hi) == (1, 1.0, [1.0, 0.0], [-1.0, 0.0])
+    f = force_from_file(str(paths["dam"]), meta)
+    assert isinstance(f, PiecewiseForce) and f.lo == f.hi == [0.0, -1.0]
+    assert force_from_file(str(paths["dam_up"]), meta).lo == [0.0, 1.0]  # the generator notebook's sign
+    f = force_from_file(str(paths["ge"]), meta)  # ">=": the threshold is the last double below 0.25
+    assert isinstance(f, PiecewiseForce) and f.axis == 0 and f.threshold == np.nextafter(0.25, 0.0)
+    assert f(np.array([[0.25, 1.0]])).tolist() == [[0.0, 2.0]] and f(np.array([[0.2, 1.0]])).tolist() == [[0.0, -2.0]]
+    with pytest.warns(UserWarning):
+        g = force_from_file(str(paths["smooth"]), meta)
+    assert not isinstance(g, PiecewiseForce)
+    assert np.allclose(np.asarray(g(np.array([[0.3, 0.5]]))), [[np.sin(0.5), 0.0]])
 
 
 @needs_ref
