@@ -119,14 +119,23 @@ def library_path():
 
 
 def load():
-    """Load (building first if the .so is absent and nvcc is available).  Raises otherwise."""
+    """Load the library, building it first when it is absent OR stale: the build stamp must equal the
+    digest of the current sources (``build.build`` recompiles only then).  Raises when the sources
+    changed and nvcc is not there to rebuild them -- a silently loaded old binary would void every test."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_SO):
-        from . import build as _build
+    from . import build as _build
 
+    try:
         _build.build()
+    except RuntimeError as exc:
+        if not os.path.exists(_SO):
+            raise
+        stamp = _SO + ".stamp"
+        fresh = os.path.exists(stamp) and open(stamp).read().strip() == _build._digest()
+        if not fresh:
+            raise RuntimeError(f"{_SO} is older than its sources and cannot be rebuilt: {exc}") from exc
     lib = C.CDLL(_SO)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export the symbol

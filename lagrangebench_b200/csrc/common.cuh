@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/lb200.h"
 
 #define LB_CHECK(expr)                            \
@@ -27,8 +29,22 @@ constexpr int kEdgeTile = 32;
 constexpr int kNodeTile = 64;
 
 // cumulative number of kernels launched by the library (lb200_launch_count)
-extern int64_t g_launches;
-#define LB_LAUNCHED(k) (::lb::g_launches += (k))
+extern std::atomic<int64_t> g_launches;
+#define LB_LAUNCHED(k) (::lb::g_launches.fetch_add((k), std::memory_order_relaxed))
+
+// One-time per-DEVICE setup (kernel attributes and the SM count belong to a device / context, not to
+// the process): slot of the current device, or -1 with *rc set.
+constexpr int kMaxDevices = 64;
+static inline int device_slot(int* rc) {
+  int dev = 0;
+  const cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+    *rc = e != cudaSuccess ? (int)e : LB200_EUNSUPPORTED;
+    return -1;
+  }
+  return dev;
+}
+int device_sm_count(int* rc);  // cached per device (rollout.cu)
 
 bool prof_enabled();
 

@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_encoder_kernel(NodeEncArgs a
         v = a.node_feat[(row0 + r) * a.node_stride + c];
       } else if (c < a.node_in + a.embed) {
         int t = a.ptype[row0 + r];
+        if (t < 0) t += a.n_types;  // hk.Embed indexes like NumPy: PAD_VALUE (-1) is the last row
         t = min(max(t, 0), a.n_types - 1);
         v = a.embedding[t * a.embed + (c - a.node_in)];
       }
@@ -524,9 +525,11 @@ constexpr int kSmemEdgeMp = (2 * kTM * kLdA + 2 * kWChunk * kLatent) * 4 + (2 * 
 constexpr int kSmemNodeMp = (kTM * (2 * kLatent + 4) + 2 * kWChunk * kLatent) * 4;
 
 static int set_smem_once() {
-  static int done = 0;
-  static int rc = 0;
-  if (done) return rc;
+  static int state[kMaxDevices];  // 0: not yet, 1: done, < 0 or > 1: the error it ended with (offset by 2)
+  int rc = 0;
+  const int dev = device_slot(&rc);
+  if (dev < 0) return rc;
+  if (state[dev] == 1) return 0;
   cudaError_t e;
   e = cudaFuncSetAttribute(node_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNodeEnc);
   if (e == cudaSuccess)
@@ -535,9 +538,8 @@ static int set_smem_once() {
     e = cudaFuncSetAttribute(edge_mp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEdgeMp);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(node_mp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNodeMp);
-  rc = (int)e;
-  done = 1;
-  return rc;
+  if (e == cudaSuccess) state[dev] = 1;
+  return (int)e;
 }
 
 }  // namespace lb

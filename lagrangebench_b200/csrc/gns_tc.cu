@@ -647,7 +647,9 @@ __global__ void node_embed_kernel(const float* __restrict__ node_feat, int node_
   if (c < node_in) {
     v = node_feat[r * node_stride + c];
   } else if (c < node_in + embed) {
-    const int t = min(max(ptype[r], 0), n_types - 1);
+    int t = ptype[r];
+    if (t < 0) t += n_types;  // hk.Embed indexes like NumPy: PAD_VALUE (-1) is the last row
+    t = min(max(t, 0), n_types - 1);
     v = embedding[t * embed + (c - node_in)];
   }
   h[i] = v;
@@ -661,21 +663,22 @@ int launch_node_embed(const float* node_feat, int node_in, int node_stride, cons
   return 0;
 }
 
-static int g_num_sms = 0;
-
 int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
-  static int attr_rc = -1;
-  if (attr_rc < 0) {
-    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc);
-    if (attr_rc == 0)
-      attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc);
-    int dev = 0;
-    if (attr_rc == 0) attr_rc = (int)cudaGetDevice(&dev);
-    if (attr_rc == 0) attr_rc = (int)cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  static int ready[kMaxDevices];
+  int rc = 0;
+  const int dev = device_slot(&rc);
+  if (dev < 0) return rc;
+  if (!ready[dev]) {
+    rc = (int)cudaFuncSetAttribute(edge_mp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc);
+    if (rc == 0)
+      rc = (int)cudaFuncSetAttribute(edge_mp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc);
+    if (rc) return rc;
+    ready[dev] = 1;
   }
-  if (attr_rc) return attr_rc;
+  const int sms = device_sm_count(&rc);
+  if (rc) return rc;
   const int n_groups = cdiv(cdiv(e_cap, kTcTile), kWorkers);  // kWorkers tiles in flight per CTA
-  const int grid = n_groups < g_num_sms ? n_groups : g_num_sms;
+  const int grid = n_groups < sms ? n_groups : sms;
   if (a.encoder) {
     edge_mp_tc_kernel<true><<<grid, kTcThreads, kSmemTc, s>>>(a);
   } else {
@@ -686,17 +689,19 @@ int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
 }
 
 int launch_node_mp_tc(const NodeTcArgs& a, cudaStream_t s) {
-  static int attr_rc = -1;
-  static int sms = 0;
-  if (attr_rc < 0) {
-    attr_rc = (int)cudaFuncSetAttribute(node_mp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNodeTc);
-    if (attr_rc == 0)
-      attr_rc = (int)cudaFuncSetAttribute(node_mp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNodeTc);
-    int dev = 0;
-    if (attr_rc == 0) attr_rc = (int)cudaGetDevice(&dev);
-    if (attr_rc == 0) attr_rc = (int)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int ready[kMaxDevices];
+  int rc = 0;
+  const int dev = device_slot(&rc);
+  if (dev < 0) return rc;
+  if (!ready[dev]) {
+    rc = (int)cudaFuncSetAttribute(node_mp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNodeTc);
+    if (rc == 0)
+      rc = (int)cudaFuncSetAttribute(node_mp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNodeTc);
+    if (rc) return rc;
+    ready[dev] = 1;
   }
-  if (attr_rc) return attr_rc;
+  const int sms = device_sm_count(&rc);
+  if (rc) return rc;
   const int n_tiles = cdiv(a.n, kNtTile);
   const int grid = n_tiles < sms ? n_tiles : sms;
   if (a.enc) {

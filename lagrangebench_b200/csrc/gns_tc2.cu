@@ -652,26 +652,30 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
 
 template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref>
 static int launch_variant(const EdgeTcArgs& a, int grid, cudaStream_t s) {
-  static int attr_rc = -1;
-  if (attr_rc < 0)
-    attr_rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem);
-  if (attr_rc) return attr_rc;
+  static int ready[kMaxDevices];
+  int rc = 0;
+  const int dev = device_slot(&rc);
+  if (dev < 0) return rc;
+  if (!ready[dev]) {
+    rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem);
+    if (rc) return rc;
+    ready[dev] = 1;
+  }
   edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref><<<grid, k2Threads, k2Smem, s>>>(a);
   LB_LAUNCHED(1);
   return 0;
 }
 
 int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
-  static int sms = 0, variant = -1;
+  static int variant = -1;
   if (variant < 0) {
-    int dev = 0;
-    int rc = (int)cudaGetDevice(&dev);
-    if (rc == 0) rc = (int)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (rc) return rc;
     const char* e = getenv("LB200_TC2_VARIANT");  // bit 0: kMn, bit 1: kNoScale, bit 2: kStage, bit 3: kPref
     variant = e ? (atoi(e) & 15) : k2DefaultVariant;
   }
+  int rc = 0;
+  const int sms = device_sm_count(&rc);
+  if (rc) return rc;
   const int n_groups = cdiv(cdiv(e_cap, k2Tile), k2Workers);
   const int grid = n_groups < sms ? n_groups : sms;
   if (a.encoder) return launch_variant<true, true, true, false, false>(a, grid, s);

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -14,7 +15,26 @@
 
 namespace lb {
 
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
+
+int device_sm_count(int* rc) {
+  static int sms[kMaxDevices];
+  const int dev = device_slot(rc);
+  if (dev < 0) return 0;
+  if (sms[dev] == 0) {
+    int v = 0;
+    const cudaError_t e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) {
+      *rc = (int)e;
+      return 0;
+    }
+    sms[dev] = v;
+  }
+  return sms[dev];
+}
+
+// the graph cache and the profiling state are process-wide: one lock around every entry point that touches them
+static std::mutex g_state_mutex;
 
 // ---- optional per-kernel-class CUDA-event timing (bench.py's roofline leg)
 struct ProfState {
@@ -145,10 +165,10 @@ static GraphEntry* graph_capture(const std::string& key, cudaStream_t s, Step& o
     cudaGetLastError();
     return nullptr;
   }
-  const int64_t launches0 = g_launches;
+  const int64_t launches0 = g_launches.load();
   const int rc = one_step();
-  const int64_t per_step = g_launches - launches0;
-  g_launches = launches0;  // the captured launches did not execute
+  const int64_t per_step = g_launches.load() - launches0;
+  g_launches.fetch_sub(per_step);  // the captured launches did not execute
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   const cudaError_t e = cudaStreamEndCapture(s, &graph);
@@ -207,9 +227,10 @@ using namespace lb;
 
 extern "C" int lb200_version(void) { return 100; }
 
-extern "C" int64_t lb200_launch_count(void) { return g_launches; }
+extern "C" int64_t lb200_launch_count(void) { return g_launches.load(); }
 
 extern "C" int lb200_profile(int32_t enable) {
+  std::lock_guard<std::mutex> lock(g_state_mutex);
   g_prof.on = enable != 0;
   g_prof.used = 0;
   return 0;
@@ -217,6 +238,7 @@ extern "C" int lb200_profile(int32_t enable) {
 
 extern "C" int lb200_profile_read(double* ms_out2, int64_t* launches_out2) {
   if (!ms_out2 || !launches_out2) return LB200_EINVAL;
+  std::lock_guard<std::mutex> lock(g_state_mutex);
   ms_out2[0] = ms_out2[1] = 0.0;
   launches_out2[0] = launches_out2[1] = 0;
   for (size_t i = 0; i < g_prof.used; ++i) {
@@ -254,6 +276,7 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
     return LB200_EINVAL;
   RolloutBufs b;
   if (!carve(c, scratch_dev, scratch_bytes, &b, nullptr)) return LB200_EINVAL;
+  std::lock_guard<std::mutex> lock(g_state_mutex);  // graph cache, profiling events
   cudaStream_t s = (cudaStream_t)stream;
   const int n = c->grid.n, dim = c->grid.dim, tw = c->feat.t_window;
   const int64_t esz = c->grid.pos_f64 ? 8 : 4;
@@ -353,7 +376,7 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
           cudaGetLastError();
           break;
         }
-        g_launches += hit->launches_per_step;
+        g_launches.fetch_add(hit->launches_per_step);
       }
     }
   }

@@ -71,15 +71,20 @@ class MetricsComputer:
 
 
 def averaged_metrics(eval_metrics):
-    """Trajectory-averaged scalars (``metrics.py:233-252``) for the supported metrics."""
-    out = {}
-    for m in eval_metrics.values():
-        for k, v in m.items():
+    """Rollout-averaged scalars, ``metrics.py:233-252``: ``mse`` and ``mae`` both feed ``val/loss``
+    (the key the trainer checkpoints on), ``e_kin`` contributes its ``mse``; every key also gets a
+    ``val/std<key>`` across rollouts."""
+    per_key = {}
+    for rollout in eval_metrics.values():
+        for k, v in rollout.items():
             if k == "e_kin":
-                out.setdefault("e_kin", []).append(float(v["mse"]))
-            elif k in ("mse", "mae") or k[:3] in ("mse", "mae"):
-                out.setdefault(k, []).append(float(torch.as_tensor(v).mean()))
-    return {f"val/{k}": float(np.mean(v)) for k, v in out.items()}
+                v = v["mse"]
+            if k in ("mse", "mae"):
+                k = "loss"
+            per_key.setdefault(k, []).append(float(torch.as_tensor(v, dtype=torch.float64).mean()))
+    out = {f"val/{k}": float(np.mean(v)) for k, v in per_key.items()}
+    out.update({f"val/std{k}": float(np.std(v)) for k, v in per_key.items()})
+    return out
 
 
 # ----------------------------------------------------------------------------- engine

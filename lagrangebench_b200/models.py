@@ -303,15 +303,28 @@ class GNS:
                              self._embedding_size, self._num_particle_types, seed)
         return params, {}
 
+    @staticmethod
+    def _fingerprint(params):
+        """Identity of every leaf plus a strided sample of its values: a params tree that was mutated in
+        place (same objects, new numbers) must not be served from the packed copy."""
+        parts = []
+        for mod in sorted(params):
+            for name in sorted(params[mod]):
+                a = np.asarray(params[mod][name])
+                flat = a.reshape(-1)
+                step = max(1, flat.size // 16)
+                parts.append((mod, name, a.shape, a.__array_interface__["data"][0], flat[::step][:17].tobytes()))
+        return hash(tuple(parts))
+
     def packed_params(self, params):
-        key = id(params)
+        key = self._fingerprint(params)
         hit = self._packed.get(key)
-        if hit is None or hit[0] is not params:
+        if hit is None:
             _cabi.require_cuda()
             pk = pack_params(params, self._mp_steps, self._output_size, self._latent_size)
-            self._packed = {key: (params, pk)}  # keep one (the reference re-uses one params tree)
-            hit = self._packed[key]
-        return hit[1]
+            self._packed = {key: pk}  # keep one (the reference re-uses one params tree)
+            hit = pk
+        return hit
 
     def _buffers(self, n, e_cap, device):
         key = (n, e_cap, str(device))

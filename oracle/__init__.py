@@ -22,4 +22,4 @@ Parity pin status (see DESIGN.md "Oracle"):
 All citations ``path:line`` are relative to the reference repository root.
 """
 
-from . import space, partition, features, gns, case, rollout  # noqa: F401
+from . import space, partition, features, gns, case, rollout, metrics  # noqa: F401

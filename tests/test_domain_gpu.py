@@ -20,7 +20,7 @@ def _run(cmd):
 
 
 def test_single_rank_domain_path_equals_engine():
-    out = _run([sys.executable, TOOL, "--case", "rpf3d_8k", "--steps", "2", "--mp", "2"])
+    out = _run([sys.executable, TOOL, "--case", "rpf3d_8k", "--steps", "2", "--mp", "2", "--dtype", "float32"])
     assert "max|dpos|=0.000e+00" in out  # world == 1: same kernels, same order -> bitwise
 
 

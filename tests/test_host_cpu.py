@@ -170,3 +170,112 @@ def test_no_cpu_path():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CPU path"):
         _cabi.require_cuda()
+
+
+def test_ctypes_structs_mirror_the_header():
+    """sizeof / offsetof of every struct that crosses the C ABI, from a C program compiled against
+    include/lb200.h, against the ctypes mirrors of _cabi.py."""
+    import subprocess
+    import tempfile
+
+    pairs = [("lb200_grid", _cabi.Grid), ("lb200_feature_cfg", _cabi.FeatureCfg), ("lb200_mlp_off", _cabi.MlpOff),
+             ("lb200_gns_cfg", _cabi.GnsCfg), ("lb200_integrate_cfg", _cabi.IntegrateCfg),
+             ("lb200_rollout_cfg", _cabi.RolloutCfg), ("lb200_shard", _cabi.Shard)]
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "lb200.h"', "int main(void) {"]
+    for cname, ct in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    with tempfile.TemporaryDirectory() as tmp:
+        src, exe = os.path.join(tmp, "layout.c"), os.path.join(tmp, "layout")
+        with open(src, "w") as f:
+            f.write("\n".join(lines))
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src])
+        got = dict(ln.split() for ln in subprocess.check_output([exe], text=True).splitlines())
+    for cname, ct in pairs:
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
+
+
+def test_metrics_computer_values_against_the_oracle():
+    """mse / mae with horizon slices, e_kin and the rollout averages (metrics.py:88-160,233-252) on a
+    non-trivial periodic rollout pair."""
+    from lagrangebench_b200 import MetricsComputer, averaged_metrics
+    from lagrangebench_b200.case_setup import _make_space
+    from oracle import metrics as ometrics
+    from oracle import space as ospace
+
+    rng = np.random.default_rng(3)
+    box = np.array([1.0, 2.0, 0.5])
+    meta = {"dt": 0.001, "write_every": 100, "dx": 0.05, "dim": 3}
+    disp_t, _ = _make_space(box.tolist(), True, torch.float64)
+    disp_np, _ = ospace.periodic(box)
+    evals_t, evals_np = {}, {}
+    for r in range(3):
+        target = rng.random((27, 40, 3)) * box
+        pred = np.mod(target + 0.3 * rng.standard_normal(target.shape) * np.linspace(0, 1, 27)[:, None, None], box)
+        mc = MetricsComputer(["mse", "mae", "e_kin"], disp_t, meta, 6, stride=5)
+        got = mc(torch.as_tensor(pred), torch.as_tensor(target))
+        ref = ometrics.compute(["mse", "mae", "e_kin"], disp_np, meta, pred, target, stride=5)
+        assert set(got) == set(ref) and {"mse5", "mse20", "mae10"} <= set(got) and "mse50" not in got
+        for k in ref:
+            if k == "e_kin":
+                for kk in ("predicted", "target", "mse"):
+                    np.testing.assert_allclose(np.asarray(got[k][kk]), ref[k][kk], rtol=1e-12)
+            else:
+                np.testing.assert_allclose(got[k].numpy(), ref[k], rtol=1e-12)
+        evals_t[f"rollout_{r}"], evals_np[f"rollout_{r}"] = got, ref
+    avg, avg_ref = averaged_metrics(evals_t), ometrics.averaged_metrics(evals_np)
+    assert set(avg) == set(avg_ref) and "val/loss" in avg and "val/stdloss" in avg and "val/e_kin" in avg
+    for k in avg_ref:
+        assert abs(avg[k] - avg_ref[k]) <= 1e-12 * max(1.0, abs(avg_ref[k]))
+
+
+def test_ghost_selection_bookkeeping():
+    """select_ghosts: who sends what where, for periodic and walled cut axes, from all ranks' counts."""
+    from lagrangebench_b200.domain import SlabDomain, select_ghosts
+
+    box, halo = [1.0, 4.0, 1.0], 0.1
+    rng = np.random.default_rng(0)
+    for periodic in (True, False):
+        world = 4
+        coords = [torch.as_tensor(r + rng.random(30 + 5 * r)) for r in range(world)]  # slab r = [r, r + 1)
+        doms = [SlabDomain(box, 1, world, r, halo, periodic=periodic) for r in range(world)]
+        counts = []
+        for r in range(world):
+            ml, mr = doms[r].halo_masks(coords[r])
+            counts.append([coords[r].numel(), int(ml.sum()) if doms[r].has_left else 0,
+                           int(mr.sum()) if doms[r].has_right else 0])
+        sels = [select_ghosts(doms[r], coords[r], counts_all=counts) for r in range(world)]
+        for r in range(world):
+            s, d = sels[r], doms[r]
+            assert d.has_left == (periodic or r > 0) and d.has_right == (periodic or r < world - 1)
+            assert s["send_left"].numel() == counts[r][1] and s["send_right"].numel() == counts[r][2]
+            if d.has_left:
+                assert bool((coords[r][s["send_left"]] < d.lo + halo).all())
+                left = sels[d.left]
+                # my left-going rows are the left neighbour's from-right block: behind its rows and its from-left block
+                assert s["dst_row_left"] == counts[d.left][0] + left["n_ghost_left"]
+                assert left["n_ghost_right"] == counts[r][1]
+            else:
+                assert s["n_ghost_left"] == 0 and s["send_left"].numel() == 0
+            if d.has_right:
+                assert s["dst_row_right"] == counts[d.right][0]
+                assert sels[d.right]["n_ghost_left"] == counts[r][2]
+            assert s["n_loc_max"] == max(c[0] + sels[i]["n_ghost_left"] + sels[i]["n_ghost_right"]
+                                         for i, c in enumerate(counts))
+
+
+def test_neighbor_list_survives_the_batch_round_trip():
+    """utils.broadcast_to_batch / broadcast_from_batch (rollout.py:122,178) keep the grid handle."""
+    from lagrangebench_b200.case_setup import NeighborList
+
+    g = _cabi.Grid()
+    g.n = g.n_valid = 5
+    nl = NeighborList(None, torch.arange(12, dtype=torch.int32).view(2, 6), torch.zeros(4, dtype=torch.int32),
+                      torch.zeros(5, 3), 3, 6, None, g)
+    back = utils.broadcast_from_batch(utils.broadcast_to_batch(nl, 2), 1)
+    assert back._grid is g and torch.equal(back.idx, nl.idx) and back.max_occupancy == 6
+    assert back.idx.shape == (2, 6) and not bool(back.did_buffer_overflow)

@@ -31,6 +31,10 @@ def main():
                          "cross slab faces, so ghost re-selection and migration run")
     ap.add_argument("--sync", type=int, default=32, help="steps per host synchronisation")
     ap.add_argument("--margin", type=float, default=0.25)
+    ap.add_argument("--dtype", default="float64", choices=["float32", "float64"],
+                    help="position dtype (reference default float64).  In float32 the open-axis displacement of a "
+                         "slab (a - b) and the periodic one of the whole box round differently, and a pair within "
+                         "1e-7 of the cutoff can be an edge in one cloud and not in the other")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = 0 if args.same_gpu else int(os.environ.get("LOCAL_RANK", 0))
@@ -40,16 +44,18 @@ def main():
             dist.init_process_group("gloo")
         else:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    c = synthetic.make_case(args.case, 6, 0, 0, np.float32)
+    npd = np.float64 if args.dtype == "float64" else np.float32
+    tdt = torch.float64 if args.dtype == "float64" else torch.float32
+    c = synthetic.make_case(args.case, 6, 0, 0, npd)
     if args.spread > 0:  # a coherent drift along every axis plus the case's jitter
         dx = c["metadata"]["dx"]
-        drift = args.spread * dx * np.arange(6, dtype=np.float32)[None, :, None]
-        c["positions"] = np.mod(c["positions"][:, :6] + drift, c["box"].astype(np.float32)).astype(np.float32)
+        drift = args.spread * dx * np.arange(6, dtype=npd)[None, :, None]
+        c["positions"] = np.mod(c["positions"][:, :6] + drift, c["box"].astype(npd)).astype(npd)
         c["metadata"]["vel_mean"] = [args.spread * dx] * c["metadata"]["dim"]
     d = c["metadata"]["dim"]
     n = c["positions"].shape[0]
     params = lbmodels.init_params(5 * d + d, d, 128, args.mp, 16, seed=0)
-    dr = DistributedRollout(c["box"], c["metadata"], params, args.mp, force=c["force"], dtype=torch.float32,
+    dr = DistributedRollout(c["box"], c["metadata"], params, args.mp, force=c["force"], dtype=tdt,
                             multiplier=c["multiplier"], halo_margin=args.margin, steps_per_sync=args.sync)
     dr.scatter(c["positions"], c["particle_type"])
     torch.cuda.synchronize()
@@ -63,7 +69,7 @@ def main():
         dist.all_reduce(owned)
     if rank == 0:
         case = case_builder(c["box"], c["metadata"], 6, cfg_neighbors={"multiplier": c["multiplier"]},
-                            external_force_fn=c["force"], dtype="float32")
+                            external_force_fn=c["force"], dtype=args.dtype)
         model = GNS(d, 128, 2, args.mp, 16)
         eng = RolloutEngine(case, model, params)
         window = torch.as_tensor(c["positions"][:, :6]).cuda().contiguous()
@@ -75,7 +81,7 @@ def main():
               f"{1e3 * dt / args.steps:.2f} ms/step reallocs={dr.n_reallocations} selections={dr.n_selections} "
               f"migrations={dr.n_migrations}", flush=True)
         assert int(owned) == n, "particles lost or duplicated in migration"
-        assert diff <= 1e-5 * dx + 8 * np.finfo(np.float32).eps * float(np.max(c["box"])), "decomposed rollout diverged"
+        assert diff <= 1e-5 * dx + 8 * np.finfo(npd).eps * float(np.max(c["box"])), "decomposed rollout diverged"
         print("DIST_CHECK_OK", flush=True)
     dr.close()
     if world > 1:
