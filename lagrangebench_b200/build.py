@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "_lb200.so")
 STAMP = SO_PATH + ".stamp"
-SOURCES = ["neighbor.cu", "features.cu", "gns.cu", "gns_tc.cu", "gns_tc2.cu", "peer.cu", "rollout.cu"]
+SOURCES = ["neighbor.cu", "features.cu", "gns.cu", "gns_tc.cu", "gns_tc2.cu", "node_tc2.cu", "peer.cu", "rollout.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

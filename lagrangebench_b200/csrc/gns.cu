@@ -508,6 +508,16 @@ static int edge_tc_version(int edge_impl) {
   return env ? env : 2;
 }
 
+// Which tensor-core node kernel runs: v2 (node_tc2.cu) unless LB200_NODE_TC=1 asks for v1 (A/B measurements).
+static int launch_node(const NodeTcArgs& a, cudaStream_t s) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("LB200_NODE_TC");
+    env = (e && e[0] == '1') ? 1 : 2;
+  }
+  return env == 1 ? launch_node_mp_tc(a, s) : launch_node_mp_tc2(a, s);
+}
+
 static MlpW mlp_ptrs(const float* w, const lb200_mlp_off& o) {
   MlpW m;
   m.w0 = w + o.w0;
@@ -656,7 +666,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     na.P = p_of(0);
     na.out = out_dev;
     set_push(na, 0);
-    rc = launch_node_mp_tc(na, s);
+    rc = launch_node(na, s);
     if (rc) return rc;
     if (sh != nullptr) shard_exchange(sh, 1, per_step, s);
   } else {
@@ -752,7 +762,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       nt_args.P = p_of(m + 1);
       nt_args.out = out_dev;
       set_push(nt_args, m + 1);
-      rc = launch_node_mp_tc(nt_args, s);
+      rc = launch_node(nt_args, s);
       if (rc) return rc;
       if (sh != nullptr && !last) shard_exchange(sh, m + 2, per_step, s);
     } else {

@@ -44,6 +44,8 @@ struct NodeTcArgs {
 };
 
 int launch_node_mp_tc(const NodeTcArgs& a, cudaStream_t s);
+// v2 (node_tc2.cu): weights resident in TMEM, four workers x 32-node tiles, two passes (update, projections)
+int launch_node_mp_tc2(const NodeTcArgs& a, cudaStream_t s);
 // h[i] = [node_feat[i] | embedding[ptype[i]] | 0 ...] (128 wide): the encoder's input operand
 int launch_node_embed(const float* node_feat, int node_in, int node_stride, const int32_t* ptype, const float* embedding,
                       int embed, int n_types, int n, float* h, cudaStream_t s);

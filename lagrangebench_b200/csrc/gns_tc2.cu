@@ -27,12 +27,7 @@ namespace lb {
 constexpr int k2Threads = 512;
 constexpr int k2Workers = 4;
 constexpr int k2DefaultVariant = 15;  // see launch_edge_mp_tc2
-constexpr int k2Tile = 32;  // edges per worker tile == one carry sub-tile (kEdgeTile)
 constexpr int k2WThreads = k2Threads / k2Workers;
-static_assert(k2Tile == kEdgeTile, "a tile is one carry sub-tile");
-// instruction descriptor: D=F32, A=B=F16, K-major, N=32, M=128
-constexpr uint32_t k2Idesc = (1u << 4) | ((uint32_t)(k2Tile >> 3) << 17) | (8u << 24);
-constexpr uint32_t k2IdescBMn = k2Idesc | (1u << 16);  // B operand MN-major (edge-contiguous core matrices)
 
 // TMEM columns: [0,256) weights (64 columns per 128x128 fp16 operand), [256,512) accumulators
 constexpr uint32_t k2ColW1Hi = 0, k2ColW1Lo = 64, k2ColW2Hi = 128, k2ColW2Lo = 192, k2ColAcc = 256;
@@ -51,155 +46,6 @@ constexpr uint32_t k2OffStage = ((k2OffState + 48 + 127) / 128) * 128;  // [work
 constexpr uint32_t k2StageBytes = k2Tile * kLatent * 4;
 constexpr uint32_t k2Smem = k2OffStage + k2Workers * k2StageBytes;
 
-// D[tmem] (+)= A[tmem] * B[smem desc]; call from ALL lanes of one warp
-__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate,
-                                        uint32_t idesc) {
-  if (elect_one())
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-// D = A * B + D * 2^-11 (scale-input-d)
-__device__ __forceinline__ void umma_ts_rescale11(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
-  if (elect_one()) {
-    const uint32_t zero = 0;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, 1, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%4, %4, %4, %4}, p, 11;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(zero)
-        : "memory");
-  }
-}
-
-// SS twin of the rescaling instruction (self-test only)
-__device__ __forceinline__ void umma_ss_rescale11(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  if (elect_one()) {
-    const uint32_t zero = 0;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, 1, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%4, %4, %4, %4}, p, 11;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(zero)
-        : "memory");
-  }
-}
-
-// split-precision GEMM (K = 128) into ONE accumulator.  Weights' low halves carry 2^11 (lo' = lo * 2^11).
-//   b_scaled:  acc = (A_hi B_lo' + A_lo' B_hi) * 2^-11 + A_hi B_hi
-//   !b_scaled: acc = (A_lo' B_hi) * 2^-11 + A_hi B_lo + A_hi B_hi        (activation lo unscaled)
-template <bool kBScaled>
-__device__ __forceinline__ void issue_gemm_ts(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t acc,
-                                              uint32_t idesc) {
-  if (kBScaled) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      umma_ts(acc, a_hi + j * 8, umma_desc(b_lo + j * 2 * kLboB, kLboB), j > 0 ? 1u : 0u, idesc);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) umma_ts(acc, a_lo + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
-    umma_ts_rescale11(acc, a_hi, umma_desc(b_hi, kLboB), idesc);
-#pragma unroll
-    for (int j = 1; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      umma_ts(acc, a_lo + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), j > 0 ? 1u : 0u, idesc);
-    umma_ts_rescale11(acc, a_hi, umma_desc(b_lo, kLboB), idesc);
-#pragma unroll
-    for (int j = 1; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_lo + j * 2 * kLboB, kLboB), 1u, idesc);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
-  }
-}
-
-// 16 columns of this warp's 32 TMEM lanes -> registers (thread == lane)
-__device__ __forceinline__ void tmem_ld16(uint32_t ta, float (&a)[16]) {
-  uint32_t x[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
-      "tcgen05.wait::ld.sync.aligned;\n"
-      : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(x[8]),
-        "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15])
-      : "r"(ta)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(x[i]);
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t ta, float (&a)[32]) {
-  uint32_t x[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;\n"
-      : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(x[8]),
-        "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15]), "=r"(x[16]),
-        "=r"(x[17]), "=r"(x[18]), "=r"(x[19]), "=r"(x[20]), "=r"(x[21]), "=r"(x[22]), "=r"(x[23]), "=r"(x[24]),
-        "=r"(x[25]), "=r"(x[26]), "=r"(x[27]), "=r"(x[28]), "=r"(x[29]), "=r"(x[30]), "=r"(x[31])
-      : "r"(ta)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(x[i]);
-}
-
-// registers -> 16 columns of this warp's 32 TMEM lanes (thread == lane)
-__device__ __forceinline__ void tmem_st16(uint32_t ta, const uint32_t (&x)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(ta),
-      "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(x[8]), "r"(x[9]),
-      "r"(x[10]), "r"(x[11]), "r"(x[12]), "r"(x[13]), "r"(x[14]), "r"(x[15])
-      : "memory");
-}
-
-__device__ __forceinline__ bool mbar_test(uint32_t mbar, uint32_t parity) {  // non-blocking
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(mbar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-
-__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// One 128x128 fp16 operand, stored in global memory in the UMMA K-major layout [k/8][m][k%8]
-// (models.py: umma_operand), -> 64 TMEM columns: lane m holds row m, column c holds k = 2c, 2c+1.
-// Called by a warp for its own lane quarter; `lane_row` = the thread's row m.
-__device__ __forceinline__ void weight_to_tmem(const uint4* op, int lane_row, uint32_t taddr) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    uint32_t x[16];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const uint4 v = __ldg(op + (g * 4 + s) * 128 + lane_row);
-      x[s * 4 + 0] = v.x;
-      x[s * 4 + 1] = v.y;
-      x[s * 4 + 2] = v.z;
-      x[s * 4 + 3] = v.w;
-    }
-    tmem_st16(taddr + g * 16, x);
-  }
-}
-
 // kMn:      the hidden operand of GEMM 2 is written edge-contiguous (MN-major core matrices): a thread
 //           packs 8 consecutive edges of its feature into ONE 16-byte store (fp16 pairs converted two
 //           at a time) instead of 8 two-byte stores; same bytes, LBO / SBO as the K-major edge operand.
@@ -217,7 +63,12 @@ __device__ __forceinline__ void weight_to_tmem(const uint4* op, int lane_row, ui
 // contiguous tile ranges per CTA; "last arriving warp issues the GEMM" instead of bar.sync (a dedicated
 // 17th MMA warp is worse still: 5 warps on one SM sub-partition cap every thread at 96 registers);
 // requesting the residual rows before phase A; ld.global.L1::no_allocate for the residual rows (slower).
-template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref>
+// kArrive:  at "operand complete" only the issuing warp waits (bar.sync); the worker's other three warps
+//           bar.arrive and run on into their next phase.  The two hand-offs of an iteration use two barrier
+//           ids; LayerNorm's full worker barrier between them keeps any warp from lapping the issuer.
+// kBucketR: P_r[rcv] is the same row for every edge of a receiver bucket: it is loaded at bucket starts only
+//           (a predicated load per edge instead of a load per edge: a third of the gather's L1 wavefronts).
+template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref, bool kArrive, bool kBucketR>
 __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -235,6 +86,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   const uint32_t bar_g1 = sbase + k2OffBar + 8 * wk, bar_g2 = bar_g1 + 32, bar_st = bar_g1 + 64;
   const uint32_t bar_worker = 1 + wk;            // named barriers: the worker's 128 threads
   const uint32_t bar_ln = 1 + k2Workers + wk;
+  const uint32_t bar_worker2 = 1 + 2 * k2Workers + wk;
 
   const int E = a.rowptr[a.n];
   const int n_tiles = (E + k2Tile - 1) / k2Tile;
@@ -293,8 +145,16 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
 
   // Every thread has written its part of an operand (and fenced it for the async proxy): a worker-wide
   // bar.sync, after which the worker's first warp issues the GEMM.  Returns true in that warp.
-  auto operand_ready = [&]() -> bool {
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(k2WThreads) : "memory");
+  auto operand_ready = [&](bool second = false) -> bool {
+    if (kArrive) {
+      const uint32_t id = second ? bar_worker2 : bar_worker;
+      if (q == 0)
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(k2WThreads) : "memory");
+      else
+        asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(k2WThreads) : "memory");
+    } else {
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(k2WThreads) : "memory");
+    }
     return q == 0;
   };
 
@@ -389,6 +249,8 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     const int* sp = idx_base + ib * k2IdxInts;
     const int* rp = sp + 32;
     float ps[32], pr[32];
+    // bucket starts of the tile: edge 0 and every edge after a bucket end (uniform across the worker)
+    const uint32_t smask = kBucketR ? ((endm[ib] << 1) | 1u) : 0xffffffffu;
 #pragma unroll
     for (int j0 = 0; j0 < 32; j0 += 4) {
       const int4 s4 = *reinterpret_cast<const int4*>(sp + j0);
@@ -397,10 +259,22 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       ps[j0 + 1] = __ldg(a.P + (int64_t)s4.y * (2 * kLatent) + f);
       ps[j0 + 2] = __ldg(a.P + (int64_t)s4.z * (2 * kLatent) + f);
       ps[j0 + 3] = __ldg(a.P + (int64_t)s4.w * (2 * kLatent) + f);
-      pr[j0 + 0] = __ldg(a.P + (int64_t)r4.x * (2 * kLatent) + kLatent + f);
-      pr[j0 + 1] = __ldg(a.P + (int64_t)r4.y * (2 * kLatent) + kLatent + f);
-      pr[j0 + 2] = __ldg(a.P + (int64_t)r4.z * (2 * kLatent) + kLatent + f);
-      pr[j0 + 3] = __ldg(a.P + (int64_t)r4.w * (2 * kLatent) + kLatent + f);
+      if (kBucketR) {
+        const int rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int j = j0 + t;
+          if ((smask >> j) & 1u)
+            pr[j] = __ldg(a.P + (int64_t)rr[t] * (2 * kLatent) + kLatent + f);
+          else
+            pr[j] = pr[j > 0 ? j - 1 : 0];
+        }
+      } else {
+        pr[j0 + 0] = __ldg(a.P + (int64_t)r4.x * (2 * kLatent) + kLatent + f);
+        pr[j0 + 1] = __ldg(a.P + (int64_t)r4.y * (2 * kLatent) + kLatent + f);
+        pr[j0 + 2] = __ldg(a.P + (int64_t)r4.z * (2 * kLatent) + kLatent + f);
+        pr[j0 + 3] = __ldg(a.P + (int64_t)r4.w * (2 * kLatent) + kLatent + f);
+      }
     }
     mbar_wait(bar_g1, ph1);
     ph1 ^= 1;
@@ -454,7 +328,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     }
     fence_async_smem();
     tc_fence_before();
-    if (operand_ready()) {
+    if (operand_ready(true)) {
       tc_fence_after();
       const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
       issue_gemm_ts<!kNoScale>(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, kMn ? k2IdescBMn : k2Idesc);
@@ -650,19 +524,19 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   }
 }
 
-template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref>
+template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref, bool kArrive = false, bool kBucketR = false>
 static int launch_variant(const EdgeTcArgs& a, int grid, cudaStream_t s) {
   static int ready[kMaxDevices];
   int rc = 0;
   const int dev = device_slot(&rc);
   if (dev < 0) return rc;
   if (!ready[dev]) {
-    rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref>,
+    rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref, kArrive, kBucketR>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem);
     if (rc) return rc;
     ready[dev] = 1;
   }
-  edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref><<<grid, k2Threads, k2Smem, s>>>(a);
+  edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref, kArrive, kBucketR><<<grid, k2Threads, k2Smem, s>>>(a);
   LB_LAUNCHED(1);
   return 0;
 }
@@ -670,8 +544,9 @@ static int launch_variant(const EdgeTcArgs& a, int grid, cudaStream_t s) {
 int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
   static int variant = -1;
   if (variant < 0) {
-    const char* e = getenv("LB200_TC2_VARIANT");  // bit 0: kMn, bit 1: kNoScale, bit 2: kStage, bit 3: kPref
-    variant = e ? (atoi(e) & 15) : k2DefaultVariant;
+    // bit 0: kMn, bit 1: kNoScale, bit 2: kStage, bit 3: kPref, bit 4: kArrive, bit 5: kBucketR
+    const char* e = getenv("LB200_TC2_VARIANT");
+    variant = e ? (atoi(e) & 63) : k2DefaultVariant;
   }
   int rc = 0;
   const int sms = device_sm_count(&rc);
@@ -684,6 +559,9 @@ int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
     case 1: return launch_variant<false, true, false, false, false>(a, grid, s);
     case 3: return launch_variant<false, true, true, false, false>(a, grid, s);
     case 7: return launch_variant<false, true, true, true, false>(a, grid, s);
+    case 31: return launch_variant<false, true, true, true, true, true, false>(a, grid, s);
+    case 47: return launch_variant<false, true, true, true, true, false, true>(a, grid, s);
+    case 63: return launch_variant<false, true, true, true, true, true, true>(a, grid, s);
     default: return launch_variant<false, true, true, true, true>(a, grid, s);
   }
 }

@@ -187,6 +187,162 @@ __device__ __forceinline__ void issue_gemm(uint32_t a_hi, uint32_t a_lo, uint32_
     umma_f16(acc_x, umma_desc(a_lo + j * 2 * kLboA, kLboA), umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
 }
 
+// ---- v2 kernels (gns_tc2.cu, node_tc2.cu): A operand in tensor memory, one rescaled accumulator, N = 32 tiles
+constexpr int k2Tile = 32;  // edges (nodes) per worker tile == one carry sub-tile (kEdgeTile)
+static_assert(k2Tile == kEdgeTile, "a tile is one carry sub-tile");
+// instruction descriptor: D=F32, A=B=F16, K-major, N=32, M=128
+constexpr uint32_t k2Idesc = (1u << 4) | ((uint32_t)(k2Tile >> 3) << 17) | (8u << 24);
+constexpr uint32_t k2IdescBMn = k2Idesc | (1u << 16);  // B operand MN-major (edge-contiguous core matrices)
+
+// D[tmem] (+)= A[tmem] * B[smem desc]; call from ALL lanes of one warp
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate,
+                                        uint32_t idesc) {
+  if (elect_one())
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// D = A * B + D * 2^-11 (scale-input-d)
+__device__ __forceinline__ void umma_ts_rescale11(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
+  if (elect_one()) {
+    const uint32_t zero = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%4, %4, %4, %4}, p, 11;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(zero)
+        : "memory");
+  }
+}
+
+// SS twin of the rescaling instruction (self-test only)
+__device__ __forceinline__ void umma_ss_rescale11(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if (elect_one()) {
+    const uint32_t zero = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%4, %4, %4, %4}, p, 11;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(zero)
+        : "memory");
+  }
+}
+
+// split-precision GEMM (K = 128) into ONE accumulator.  Weights' low halves carry 2^11 (lo' = lo * 2^11).
+//   b_scaled:  acc = (A_hi B_lo' + A_lo' B_hi) * 2^-11 + A_hi B_hi
+//   !b_scaled: acc = (A_lo' B_hi) * 2^-11 + A_hi B_lo + A_hi B_hi        (activation lo unscaled)
+template <bool kBScaled>
+__device__ __forceinline__ void issue_gemm_ts(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t acc,
+                                              uint32_t idesc) {
+  if (kBScaled) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      umma_ts(acc, a_hi + j * 8, umma_desc(b_lo + j * 2 * kLboB, kLboB), j > 0 ? 1u : 0u, idesc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) umma_ts(acc, a_lo + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
+    umma_ts_rescale11(acc, a_hi, umma_desc(b_hi, kLboB), idesc);
+#pragma unroll
+    for (int j = 1; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      umma_ts(acc, a_lo + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), j > 0 ? 1u : 0u, idesc);
+    umma_ts_rescale11(acc, a_hi, umma_desc(b_lo, kLboB), idesc);
+#pragma unroll
+    for (int j = 1; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_lo + j * 2 * kLboB, kLboB), 1u, idesc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
+  }
+}
+
+// 16 columns of this warp's 32 TMEM lanes -> registers (thread == lane)
+__device__ __forceinline__ void tmem_ld16(uint32_t ta, float (&a)[16]) {
+  uint32_t x[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(x[8]),
+        "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15])
+      : "r"(ta)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(x[i]);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t ta, float (&a)[32]) {
+  uint32_t x[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(x[8]),
+        "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15]), "=r"(x[16]),
+        "=r"(x[17]), "=r"(x[18]), "=r"(x[19]), "=r"(x[20]), "=r"(x[21]), "=r"(x[22]), "=r"(x[23]), "=r"(x[24]),
+        "=r"(x[25]), "=r"(x[26]), "=r"(x[27]), "=r"(x[28]), "=r"(x[29]), "=r"(x[30]), "=r"(x[31])
+      : "r"(ta)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(x[i]);
+}
+
+// registers -> 16 columns of this warp's 32 TMEM lanes (thread == lane)
+__device__ __forceinline__ void tmem_st16(uint32_t ta, const uint32_t (&x)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(ta),
+      "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(x[8]), "r"(x[9]),
+      "r"(x[10]), "r"(x[11]), "r"(x[12]), "r"(x[13]), "r"(x[14]), "r"(x[15])
+      : "memory");
+}
+
+__device__ __forceinline__ bool mbar_test(uint32_t mbar, uint32_t parity) {  // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(mbar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// One 128x128 fp16 operand, stored in global memory in the UMMA K-major layout [k/8][m][k%8]
+// (models.py: umma_operand), -> 64 TMEM columns: lane m holds row m, column c holds k = 2c, 2c+1.
+// Called by a warp for its own lane quarter; `lane_row` = the thread's row m.
+__device__ __forceinline__ void weight_to_tmem(const uint4* op, int lane_row, uint32_t taddr) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t x[16];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const uint4 v = __ldg(op + (g * 4 + s) * 128 + lane_row);
+      x[s * 4 + 0] = v.x;
+      x[s * 4 + 1] = v.y;
+      x[s * 4 + 2] = v.z;
+      x[s * 4 + 3] = v.w;
+    }
+    tmem_st16(taddr + g * 16, x);
+  }
+}
+
 // lane l ends with the sum over the warp's 32 lanes of v[l]   (31 shuffles, fixed order)
 __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32]) {
   const int lane = threadIdx.x & 31;
