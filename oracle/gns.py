@@ -118,7 +118,9 @@ def node_edge_inputs(features, particle_type, params, dtype):
     key = "gns/~/embed" if "gns/~/embed" in params else "gns/embed"
     emb = params[key]["embeddings"].astype(dtype)
     n_types = emb.shape[0]
-    nodes = np.concatenate([nodes, emb[np.clip(particle_type, 0, n_types - 1)]], axis=-1)
+    pt = np.asarray(particle_type)
+    pt = np.clip(np.where(pt < 0, pt + n_types, pt), 0, n_types - 1)  # hk.Embed indexes like NumPy: -1 is the last row
+    nodes = np.concatenate([nodes, emb[pt]], axis=-1)
     return nodes, edges
 
 

@@ -161,3 +161,23 @@ def test_num_particles_keeps_padding_out_of_the_search():
     assert (padded.idx[:, e:] == pos.shape[0]).all()
     _, again = orac.preprocess_eval((pos, ptype), padded)
     assert np.array_equal(again.idx, padded.idx) and not again.did_buffer_overflow
+
+
+def test_torch_twin_of_the_forward_agrees_with_the_numpy_oracle():
+    """oracle/gns_torch.py (the CPU baseline bench.py times) is the same restatement as oracle/gns.py."""
+    from lagrangebench_b200 import synthetic
+    from oracle import gns as ogns
+    from oracle import gns_torch
+
+    c = synthetic.make_case("ldc3d", 6, 0, 0, np.float32, dims=(10, 9, 8))
+    orac = ocase.case_builder(c["box"], c["metadata"], 6, cfg_neighbors={"multiplier": 2.0}, dtype=np.float32)
+    ptype = c["particle_type"].copy()
+    ptype[-3:] = -1  # padding rows: hk.Embed takes the last row of the table
+    feats, _ = orac.allocate_eval((c["positions"], ptype))
+    params = ogns.init_params(21, 4, 3, num_mp_steps=4, seed=2)
+    ref = ogns.forward(params, feats, ptype, 4, np.float64)["acc"]
+    f32 = ogns.forward(params, feats, ptype, 4, np.float32)["acc"]
+    twin = gns_torch.forward(gns_torch.pack(params), feats, ptype, 4)["acc"]
+    scale = np.abs(ref).max()
+    assert np.abs(twin - ref).max() <= 1e-5 * scale
+    assert np.abs(twin - f32).max() <= 1e-5 * scale
