@@ -37,6 +37,8 @@ extern "C" {
 /* status bits of a decomposed rollout (lb200_shard), OR-ed over all ranks before they take effect */
 #define LB200_OVF_DRIFT 4         /* a particle moved further than the halo margin covers: choose new ghost sets */
 #define LB200_OVF_PEER_TIMEOUT 8  /* a neighbour's signal did not arrive (a rank died): the rollout is void */
+#define LB200_ERR_NONFINITE 16     /* the network produced NaN / Inf: an activation left the range of the fp16 split
+                                      (|x| > 65504) -- rerun with edge_impl = 1 (float32 CUDA cores) */
 #define LB200_MAX_RANKS 16
 
 int lb200_version(void);
@@ -239,6 +241,8 @@ typedef struct {
    * its boundary rows into the neighbours' arrays, one signal/wait kernel per message-passing step. */
   int32_t n_owned;
   const struct lb200_shard_s* shard;
+  /* dev int32* or NULL: OR-ed with 1 when an output acceleration is NaN / Inf (see LB200_ERR_NONFINITE) */
+  int32_t* nonfinite_flag;
 } lb200_gns_cfg;
 
 /* device scratch the forward needs, in bytes (node latents, projections, edge latents ...) */

@@ -46,12 +46,14 @@ class GnsCfg(C.Structure):
                 ("node_stride", C.c_int32), ("embed_size", C.c_int32), ("num_particle_types", C.c_int32),
                 ("e_cap", C.c_int32), ("embedding", C.c_int64), ("enc_node", MlpOff), ("enc_edge", MlpOff),
                 ("dec", MlpOff), ("proc_edge", C.POINTER(MlpOff)), ("proc_node", C.POINTER(MlpOff)),
-                ("edge_impl", C.c_int32), ("n_owned", C.c_int32), ("shard", C.c_void_p)]
+                ("edge_impl", C.c_int32), ("n_owned", C.c_int32), ("shard", C.c_void_p),
+                ("nonfinite_flag", C.c_void_p)]
 
 
 MAX_RANKS = 16
 OVF_DRIFT = 4
 OVF_PEER_TIMEOUT = 8
+ERR_NONFINITE = 16
 
 
 class Shard(C.Structure):

@@ -415,6 +415,7 @@ struct NodeMpArgs {
   MlpW mlp;  // w0 = (256,128): rows 0..127 act on h, 128..255 on the aggregate
   MlpW nxt;  // next step's edge MLP (projection) or the decoder when last
   float *h, *P, *out;
+  int32_t* flag;  // OR-ed with 1 when a decoded output is NaN / Inf (or NULL)
 };
 
 __global__ void __launch_bounds__(kThreads, 2) node_mp_kernel(NodeMpArgs a) {
@@ -491,7 +492,10 @@ __global__ void __launch_bounds__(kThreads, 2) node_mp_kernel(NodeMpArgs a) {
       for (int j = 0; j < 8; ++j) p = fmaf(acc[i][j], wk[j], p);
       p = half_warp_sum(p);
       const int r = ty * 4 + i;
-      if (tx == 0 && r < rows) a.out[(row0 + r) * a.dim + k] = p + bk;
+      if (tx == 0 && r < rows) {
+        a.out[(row0 + r) * a.dim + k] = p + bk;
+        if (a.flag != nullptr && !isfinite(p + bk)) atomicOr(a.flag, 1);
+      }
     }
   }
 }
@@ -620,6 +624,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     na.P_left = na.P_right = nullptr;
     na.push_left = na.push_right = nullptr;
     na.dst_left = na.dst_right = 0;
+    na.flag = c->nonfinite_flag;
     if (sh == nullptr) return;
     if (sh->has_left && sh->n_send_left > 0) {
       na.P_left = shard_p_left(sh, m_out);
@@ -778,6 +783,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       nm.nxt = last ? mlp_ptrs(w, c->dec) : mlp_ptrs(w, c->proc_edge[m + 1]);
       nm.h = h;
       nm.P = p_of(m + 1);
+      nm.flag = c->nonfinite_flag;
       nm.out = out_dev;
       { node_mp_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeMp, s>>>(nm); LB_LAUNCHED(1); }
     }

@@ -623,7 +623,9 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
         asm volatile("bar.sync %0, 128;" ::"r"(bar_group) : "memory");
         if (q == 0 && lane < valid) {
           const float* rb = red + (1 + (k & 1)) * 512;
-          a.out[(row0 + g * 32 + lane) * a.dim + k] = rb[lane] + rb[32 + lane] + rb[64 + lane] + rb[96 + lane] + vec[640 + 384 + k];
+          const float o = rb[lane] + rb[32 + lane] + rb[64 + lane] + rb[96 + lane] + vec[640 + 384 + k];
+          a.out[(row0 + g * 32 + lane) * a.dim + k] = o;
+          if (a.flag != nullptr && !isfinite(o)) atomicOr(a.flag, 1);
         }
       }
     }

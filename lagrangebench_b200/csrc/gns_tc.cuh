@@ -41,6 +41,7 @@ struct NodeTcArgs {
   float *P_left, *P_right;
   const int32_t *push_left, *push_right;
   int dst_left, dst_right;
+  int32_t* flag;  // OR-ed with 1 when a decoded output is NaN / Inf (or NULL)
 };
 
 int launch_node_mp_tc(const NodeTcArgs& a, cudaStream_t s);

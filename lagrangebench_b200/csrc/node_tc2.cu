@@ -337,8 +337,11 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
         float* rb = red + (1 + (k & 1)) * 128;  // blocks 1 / 2 alternate over k
         rb[q * 32 + lane] = warp_transpose_reduce(t);
         asm volatile("bar.sync %0, %1;" ::"r"(bar_ln), "n"(kN2WThreads) : "memory");
-        if (q == 0 && lane < rows)
-          a.out[(row0 + lane) * a.dim + k] = rb[lane] + rb[32 + lane] + rb[64 + lane] + rb[96 + lane] + vec[640 + 384 + k];
+        if (q == 0 && lane < rows) {
+          const float o = rb[lane] + rb[32 + lane] + rb[64 + lane] + rb[96 + lane] + vec[640 + 384 + k];
+          a.out[(row0 + lane) * a.dim + k] = o;
+          if (a.flag != nullptr && !isfinite(o)) atomicOr(a.flag, 1);  // an activation left the fp16 split's range
+        }
       }
     }
     tc_fence_before();

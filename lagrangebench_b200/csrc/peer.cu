@@ -113,7 +113,7 @@ struct CtrlAll {
 __global__ void shard_flag_bcast_kernel(uint32_t* ctrl, const int32_t* __restrict__ nbr_stats, int rank, int world,
                                         CtrlAll ctrl_all) {
   const int r = threadIdx.x;
-  const uint32_t bits = (ctrl[kCtrlSticky] | (uint32_t)nbr_stats[2]) & 0xffu;
+  const uint32_t bits = (ctrl[kCtrlSticky] | (uint32_t)nbr_stats[2] | (nbr_stats[3] ? LB200_ERR_NONFINITE : 0u)) & 0xffu;
   const uint32_t word = ((ctrl[kCtrlEpoch] + 1u) << 8) | bits;
   if (r < world) st_release_sys(ctrl_all.p[r] + kCtrlFlags + rank, word);
 }
@@ -149,7 +149,7 @@ __global__ void shard_flag_wait_kernel(uint32_t* ctrl, int world) {
 __global__ void shard_step_done_kernel(uint32_t* ctrl, const int32_t* __restrict__ nbr_stats, int32_t* status) {
   const uint32_t bits = ctrl[kCtrlGlobal];
   status[2] = nbr_stats[0];
-  status[1] |= (int32_t)bits;
+  status[1] |= (int32_t)bits | (nbr_stats[3] ? LB200_ERR_NONFINITE : 0);
   if (bits == 0) status[0] += 1;
   ctrl[kCtrlEpoch] += 1;
 }

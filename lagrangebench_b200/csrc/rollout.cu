@@ -79,7 +79,7 @@ __global__ void extract_last_kernel(const T* __restrict__ window, int n, int tw,
 // status: [0] steps completed, [1] overflow bits, [2] last E
 __global__ void rollout_step_done_kernel(const int32_t* __restrict__ nbr_stats, int32_t* status) {
   status[2] = nbr_stats[0];
-  status[1] |= nbr_stats[2];
+  status[1] |= nbr_stats[2] | (nbr_stats[3] ? LB200_ERR_NONFINITE : 0);
   if (nbr_stats[2] == 0) status[0] += 1;
 }
 
@@ -285,6 +285,8 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
   // call), so the very same launches serve every step -- and can be replayed from a CUDA graph.
   const bool direct = c->grid.use_cells != 0;  // cell-list grids: receiver-major view straight from the cells
   const lb200_shard* sh = c->shard;
+  lb200_gns_cfg gns = c->gns;
+  gns.nonfinite_flag = b.stats + 3;  // NaN / Inf accelerations (fp16 split out of range) -> status bit
   if (sh != nullptr) {
     if (!direct || c->gns.shard != sh || c->gns.n_owned != sh->n_owned || c->integ.n != sh->n_owned ||
         c->feat.n != sh->n_owned || n != sh->n_owned + sh->n_ghost_left + sh->n_ghost_right || n > sh->n_cap ||
@@ -310,7 +312,7 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
       if (rc) return rc;
       rc = lb200_features(&c->feat, window_dev, force_dev, nullptr, 0, b.node_feat, nullptr, stream);
       if (rc) return rc;
-      rc = lb200_gns_forward(&c->gns, weights_dev, b.node_feat, b.edge_feat, ptype_dev, b.rowptr, nullptr, b.snd,
+      rc = lb200_gns_forward(&gns, weights_dev, b.node_feat, b.edge_feat, ptype_dev, b.rowptr, nullptr, b.snd,
                              b.rcv, b.out, b.gns_scratch, b.gns_bytes, stream);
       if (rc) return rc;
       rc = shard_flag_wait(sh, s);
@@ -343,7 +345,7 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
       if (rc) return rc;
       perm = b.perm;
     }
-    rc = lb200_gns_forward(&c->gns, weights_dev, b.node_feat, b.edge_feat, ptype_dev, b.rowptr, perm, b.snd, b.rcv,
+    rc = lb200_gns_forward(&gns, weights_dev, b.node_feat, b.edge_feat, ptype_dev, b.rowptr, perm, b.snd, b.rcv,
                            b.out, b.gns_scratch, b.gns_bytes, stream);
     if (rc) return rc;
     rc = integrate_indexed(&c->integ, b.out, window_dev, ptype_dev, targets_dev, preds_dev, b.stats + 2, status_dev, s);

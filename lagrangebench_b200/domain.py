@@ -580,6 +580,8 @@ class DistributedRollout:
             self.steps_done += completed
             self.edges_last = n_edges
             self.halo_bytes = self.halo_rows * 512 * self.num_mp_steps
+            if bits & _cabi.ERR_NONFINITE:
+                raise FloatingPointError("rollout produced NaN / Inf accelerations (fp16 split out of range)")
             if bits & _cabi.OVF_PEER_TIMEOUT:
                 raise RuntimeError("a neighbouring rank stopped answering (peer signal timeout)")
             if bits & (_cabi.OVF_NEIGHBOR_LIST | _cabi.OVF_CELL_LIST):

@@ -187,6 +187,10 @@ class RolloutEngine:
             self.n_launch_calls += 1
             completed, overflow, n_edges, _ = status.tolist()  # the one host sync per chunk
             done += completed
+            if overflow & _cabi.ERR_NONFINITE:
+                raise FloatingPointError(
+                    "rollout produced NaN / Inf accelerations: an activation left the range of the fp16 split of the "
+                    "tensor-core kernels (|x| > 65504).  Set model.edge_impl = 'simt' for the float32 CUDA-core kernels.")
             if overflow:  # rollout.py:135-151: re-allocate from the current state, retry the step
                 self.n_reallocations += 1
                 neighbors = nfn.allocate(window[:, -1].contiguous(), num_particles=n_valid)

@@ -291,6 +291,7 @@ class GNS:
         # "tc": tcgen05 tensor-core message kernel (product path); "simt": fp32 CUDA-core
         # kernel kept as the numerical cross-check of the split-precision scheme
         self.edge_impl = "tc"
+        self.check_finite = True  # apply() raises FloatingPointError when the device flags a non-finite output
 
     # -- hk.transform_with_state surface ---------------------------------------------
     def init(self, key, sample):
@@ -339,6 +340,7 @@ class GNS:
                 "snd": torch.empty(e_cap, **i32), "rcv": torch.empty(e_cap, **i32),
                 "csr": torch.empty(csr_bytes, dtype=torch.uint8, device=device),
                 "gns": torch.empty(gns_bytes, dtype=torch.uint8, device=device),
+                "flag": torch.zeros(1, dtype=torch.int32, device=device),
             }
             self._bufs = {key: b}
         return b
@@ -369,6 +371,7 @@ class GNS:
         e_cap = idx.shape[1]
         b = self._buffers(n, e_cap, dev)
         cfg = gns_cfg(pk, n, e_cap, node_feat.shape[1], node_feat.shape[1], self.edge_impl)
+        cfg.nonfinite_flag = b["flag"].data_ptr()
         out = torch.empty((n, self._output_size), dtype=torch.float32, device=dev)
         st = _cabi.stream()
         _cabi.check(lib.lb200_csr_build(_cabi.ptr(idx), n, e_cap, _cabi.ptr(b["rowptr"]), _cabi.ptr(b["perm"]),
@@ -378,4 +381,9 @@ class GNS:
                                           _cabi.ptr(edge_feat), _cabi.ptr(ptype), _cabi.ptr(b["rowptr"]),
                                           _cabi.ptr(b["perm"]), _cabi.ptr(b["snd"]), _cabi.ptr(b["rcv"]),
                                           _cabi.ptr(out), _cabi.ptr(b["gns"]), b["gns"].numel(), st))
+        if self.check_finite and int(b["flag"].item()):  # one 4-byte read per forward (the per-step loop syncs anyway)
+            b["flag"].zero_()
+            raise FloatingPointError(
+                "GNS forward produced NaN / Inf: an activation left the range of the fp16 split of the tensor-core "
+                "kernels (|x| > 65504).  Set model.edge_impl = 'simt' for the float32 CUDA-core kernels.")
         return {"acc": out}, state

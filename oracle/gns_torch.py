@@ -15,13 +15,14 @@ import torch
 from .gns import mlp_names
 
 
-def _t(a):
-    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32))
+def _t(a, dtype=np.float32):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=dtype))
 
 
-def pack(params):
-    """NumPy parameter tree -> the same tree of float32 torch tensors (done once, outside the timed loop)."""
-    return {mod: {k: _t(v) for k, v in leaves.items()} for mod, leaves in params.items()}
+def pack(params, dtype=np.float32):
+    """NumPy parameter tree -> the same tree of torch tensors (done once, outside the timed loop).
+    ``dtype=np.float64`` gives the double-precision ground truth of the large parity tests."""
+    return {mod: {k: _t(v, dtype) for k, v in leaves.items()} for mod, leaves in params.items()}
 
 
 def _mlp(tp, prefix, idx, x, ln=True):
@@ -34,13 +35,14 @@ def _mlp(tp, prefix, idx, x, ln=True):
 
 
 def forward(tp, features, particle_type, num_mp_steps=10):
-    """``GNS.__call__`` (``gns.py:159-171``) -> ``{"acc": (N, dim) float32 ndarray}``; ``tp = pack(params)``."""
+    """``GNS.__call__`` (``gns.py:159-171``) -> ``{"acc": (N, dim) ndarray}`` in the dtype of ``tp = pack(params)``."""
     n = features["vel_hist"].shape[0]
-    nodes = torch.cat([_t(features[k]).reshape(n, -1) for k in ("vel_hist", "vel_mag", "bound", "force")
-                       if k in features], dim=1)
-    edges = torch.cat([_t(features[k]) for k in ("rel_disp", "rel_dist")], dim=1)
     key = "gns/~/embed" if "gns/~/embed" in tp else "gns/embed"
     emb = tp[key]["embeddings"]
+    dt = np.float64 if emb.dtype == torch.float64 else np.float32
+    nodes = torch.cat([_t(features[k], dt).reshape(n, -1) for k in ("vel_hist", "vel_mag", "bound", "force")
+                       if k in features], dim=1)
+    edges = torch.cat([_t(features[k], dt) for k in ("rel_disp", "rel_dist")], dim=1)
     pt = torch.as_tensor(np.asarray(particle_type)).long()
     pt = torch.where(pt < 0, pt + emb.shape[0], pt).clamp_(0, emb.shape[0] - 1)
     nodes = torch.cat([nodes, emb[pt]], dim=1)

@@ -29,3 +29,12 @@ def rel_err(a, b):
     """max |a - b| / max |b| -- the scale-relative error the 1e-5 bar is stated in."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def elem_rel_err(a, b, floor=1e-2):
+    """Elementwise relative error |a - b| / |b| over the elements that carry signal (|b| above ``floor`` of
+    the largest): returns (max, 99.9th percentile).  Reported beside the scale-relative ``rel_err``."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    keep = np.abs(b) > floor * np.abs(b).max()
+    r = np.abs(a - b)[keep] / np.abs(b)[keep]
+    return float(r.max()), float(np.percentile(r, 99.9))
