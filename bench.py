@@ -574,6 +574,7 @@ def strong_scaling_leg(args, world, rank, dev, K, W):
         del eng, w1, ref
     del pos_sharded
     torch.cuda.empty_cache()
+    barrier()  # rank 0 rolled the whole cloud out alone: nobody spins on its signals meanwhile
     # ---- timing: W warm-up steps, then K steps = one call, one host synchronisation
     dr.run(W)
     barrier()

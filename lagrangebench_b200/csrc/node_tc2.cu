@@ -126,32 +126,62 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
     const int64_t row0 = (int64_t)tile * k2Tile;
     const int rows = min(k2Tile, a.n - (int)row0);
     const uint32_t acc = tmem + kN2ColAccA + (uint32_t)wk * 32;
-    // ---- A0: h rows and aggregate rows (bucket carries resolved) -> operands, 8 rows per warp; GEMM 1
+    // ---- A0: h rows and aggregate rows (bucket carries resolved) -> operands, 8 rows per warp; GEMM 1.
+    //      Loads are issued in three independent batches (rows + bucket bounds, aggregates, then the rare
+    //      partial sums of buckets that straddle carry sub-tiles), not row after row.
+    {
+      float4 hv[8], av[8];
+      int e0[8], e1[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = r0 + i;
-      float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), av = hv;
-      if (r < rows) {
-        const int64_t v = row0 + r;
-        hv = reinterpret_cast<const float4*>(a.h + v * kLatent)[lane];
-        if (!kEnc) {
-          const int e0 = a.rowptr[v], e1 = a.rowptr[v + 1];
-          if (e1 > e0) {
-            const int ta = e0 / kEdgeTile, tb = (e1 - 1) / kEdgeTile;
-            if (ta == tb) {
-              av = reinterpret_cast<const float4*>(a.agg + v * kLatent)[lane];
-            } else {  // bucket straddles carry sub-tiles: partial sums in slot order
-              av = reinterpret_cast<const float4*>(a.carry_last + (int64_t)ta * kLatent)[lane];
-              for (int t = ta + 1; t <= tb; ++t) {
-                const float4 p = reinterpret_cast<const float4*>(a.carry_first + (int64_t)t * kLatent)[lane];
-                av.x += p.x; av.y += p.y; av.z += p.z; av.w += p.w;
-              }
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + i;
+        hv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        e0[i] = e1[i] = 0;
+        if (r < rows) {
+          const int64_t v = row0 + r;
+          hv[i] = reinterpret_cast<const float4*>(a.h + v * kLatent)[lane];
+          if (!kEnc) {
+            e0[i] = __ldg(a.rowptr + v);
+            e1[i] = __ldg(a.rowptr + v + 1);
+          }
+        }
+      }
+      if (!kEnc) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e1[i] > e0[i]) {
+            const int ta = e0[i] / kEdgeTile, tb = (e1[i] - 1) / kEdgeTile;
+            const float* src = ta == tb ? a.agg + (row0 + r0 + i) * kLatent : a.carry_last + (int64_t)ta * kLatent;
+            av[i] = reinterpret_cast<const float4*>(src)[lane];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (e1[i] > e0[i]) {
+            const int ta = e0[i] / kEdgeTile, tb = (e1[i] - 1) / kEdgeTile;
+            for (int t = ta + 1; t <= tb; ++t) {  // bucket straddles carry sub-tiles: partial sums in slot order
+              const float4 p = reinterpret_cast<const float4*>(a.carry_first + (int64_t)t * kLatent)[lane];
+              av[i].x += p.x; av[i].y += p.y; av[i].z += p.z; av[i].w += p.w;
             }
           }
         }
       }
-      put_row4(x_hi_p, x_lo_p, r, hv);
-      if (!kEnc) put_row4(y_hi_p, y_lo_p, r, av);
+      // range guard of the fp16 split (|x| <= 65504): the aggregate is a data-dependent sum, the encoder's input
+      // is raw data; everything else is bounded by the weights (checked on the host when they are packed)
+      bool bad = false;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 g = kEnc ? hv[i] : av[i];
+        bad = bad || !(fabsf(g.x) <= 65504.f) || !(fabsf(g.y) <= 65504.f) || !(fabsf(g.z) <= 65504.f) ||
+              !(fabsf(g.w) <= 65504.f);
+      }
+      if (bad && a.flag != nullptr) atomicOr(a.flag, 1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        put_row4(x_hi_p, x_lo_p, r0 + i, hv[i]);
+        if (!kEnc) put_row4(y_hi_p, y_lo_p, r0 + i, av[i]);
+      }
     }
     if (operand_ready()) {
       tc_fence_after();
@@ -184,6 +214,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
     {
       unsigned char* hi_p = y_hi_p + (uint32_t)(f >> 3) * kLboB + (uint32_t)(f & 7) * 16;
       unsigned char* lo_p = hi_p + kBBytes;
+      bool hid_bad = false;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float av[16];
@@ -195,6 +226,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
           for (int p2 = 0; p2 < 4; ++p2) {
             const int j = g * 8 + p2 * 2;
             const float x0 = fmaxf(av[j] + b1, 0.f), x1 = fmaxf(av[j + 1] + b1, 0.f);
+            hid_bad = hid_bad || !(x0 <= 65504.f) || !(x1 <= 65504.f);  // range guard of the split (data-dependent here)
             const __half2 hh = __floats2half2_rn(x0, x1);
             const float2 hf = __half22float2(hh);
             const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
@@ -206,6 +238,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
           *reinterpret_cast<uint4*>(lo_p + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
       }
+      if (hid_bad && a.flag != nullptr) atomicOr(a.flag, 1);
     }
     if (operand_ready()) {
       tc_fence_after();

@@ -35,8 +35,44 @@ def _mlp_modules(params, scope, idx, layer_norm=True):
     return l0, l1, ln
 
 
+FP16_MAX = 65504.0
+
+
+def fp16_range_bounds(params, num_mp_steps, latent=128):
+    """Worst-case magnitudes of everything the tensor-core kernels split into fp16 hi/lo halves that is
+    bounded by the WEIGHTS alone (float64): a LayerNorm output obeys ``|y_i| <= sqrt(L-1) |scale_i| +
+    |offset_i|``, latents are sums of such outputs over the residual steps, a hidden layer is bounded
+    through the column 1-norms of its matrix.  The data-dependent operands (the aggregate, the node
+    MLP's hidden layer, the encoder's raw inputs) are guarded on the device instead
+    (``LB200_ERR_NONFINITE``).  Returns ``{name: bound}``."""
+    root = np.sqrt(latent - 1.0)
+
+    def ln_bound(ln):
+        return float(np.max(root * np.abs(np.asarray(ln["scale"], np.float64)) +
+                            np.abs(np.asarray(ln["offset"], np.float64))))
+
+    def hidden_bound(l0, in_bounds):
+        w = np.abs(np.asarray(l0["w"], np.float64))
+        b = np.abs(np.asarray(l0["b"], np.float64))
+        return float(np.max(in_bounds @ w + b))
+
+    enc_n, enc_e = _mlp_modules(params, "_encoder", 0), _mlp_modules(params, "_encoder", 1)
+    h_bound, e_bound = ln_bound(enc_n[2]), ln_bound(enc_e[2])
+    out = {"edge encoder hidden": hidden_bound(enc_e[0], np.ones(np.asarray(enc_e[0]["w"]).shape[0]))}
+    for m in range(num_mp_steps):
+        edge, node = _mlp_modules(params, "_processor", 2 * m), _mlp_modules(params, "_processor", 2 * m + 1)
+        in_b = np.concatenate([np.full(2 * latent, h_bound), np.full(latent, e_bound)])
+        out[f"edge MLP {m} hidden"] = hidden_bound(edge[0], in_b)
+        e_bound += ln_bound(edge[2])
+        h_bound += ln_bound(node[2])
+    out["edge latents"], out["node latents"] = e_bound, h_bound
+    return out
+
+
 class PackedParams:
     """One contiguous float32 device blob + the offset table ``lb200_gns_cfg`` expects."""
+
+    fp16_safe, fp16_report = True, ""
 
     def __init__(self, blob, embedding, enc_node, enc_edge, dec, proc_edge, proc_node, node_in_total, embed_size,
                  num_types, dim, num_mp_steps):
@@ -209,15 +245,33 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
         proc_node[m] = on
     dec = put_mlp(_mlp_modules(params, "_decoder", 0, layer_norm=False), latent, dim)
     blob = torch.from_numpy(np.concatenate(chunks)).to(device)
-    return PackedParams(blob, embedding, enc_node, enc_edge, dec, proc_edge, proc_node, node_in_total, embed_size,
-                        num_types, dim, num_mp_steps)
+    pk = PackedParams(blob, embedding, enc_node, enc_edge, dec, proc_edge, proc_node, node_in_total, embed_size,
+                      num_types, dim, num_mp_steps)
+    over = {k: v for k, v in fp16_range_bounds(params, num_mp_steps, latent).items() if not v <= FP16_MAX}
+    if over:
+        pk.fp16_safe = False
+        pk.fp16_report = ", ".join(f"{k} <= {v:.3g}" for k, v in over.items())
+    return pk
 
 
 EDGE_IMPL = {"tc": 0, "simt": 1, "tc1": 2}
 
 
+_warned_fp16 = set()
+
+
 def gns_cfg(packed, n, e_cap, node_in, node_stride, edge_impl="tc"):
     c = _cabi.GnsCfg()
+    if edge_impl != "simt" and not packed.fp16_safe:
+        # these weights can drive an activation beyond the fp16 range of the split-precision tensor-core
+        # kernels: the float32 CUDA-core kernels take over (slower, always exact in range)
+        if packed.fp16_report not in _warned_fp16:
+            _warned_fp16.add(packed.fp16_report)
+            import warnings
+
+            warnings.warn("GNS weights exceed the range of the fp16 split (" + packed.fp16_report +
+                          " > 65504): running the float32 CUDA-core kernels instead of the tensor-core ones")
+        edge_impl = "simt"
     c.edge_impl = EDGE_IMPL[edge_impl]
     c.n, c.dim, c.num_mp_steps = n, packed.dim, packed.num_mp_steps
     c.node_in, c.node_stride = node_in, node_stride

@@ -279,3 +279,18 @@ def test_neighbor_list_survives_the_batch_round_trip():
     back = utils.broadcast_from_batch(utils.broadcast_to_batch(nl, 2), 1)
     assert back._grid is g and torch.equal(back.idx, nl.idx) and back.max_occupancy == 6
     assert back.idx.shape == (2, 6) and not bool(back.did_buffer_overflow)
+
+
+def test_fp16_range_bounds_of_the_weights():
+    """Static guard of the split-precision kernels: haiku-initialised weights sit far inside the fp16 range,
+    a LayerNorm scale of 1e4 does not -- that model is routed to the float32 kernels."""
+    params = models.init_params(15, 3, 128, 10, 16, seed=0)
+    b = models.fp16_range_bounds(params, 10)
+    assert max(b.values()) < 5000 and abs(b["edge latents"] - 11 * np.sqrt(127.0)) < 1e-6
+    assert models.pack_params(params, 10, 3, device="cpu").fp16_safe
+    params["gns/~_processor/layer_norm_4"]["scale"] = params["gns/~_processor/layer_norm_4"]["scale"] * 1.0e4
+    pk = models.pack_params(params, 10, 3, device="cpu")
+    assert not pk.fp16_safe and "edge latents" in pk.fp16_report
+    with pytest.warns(UserWarning, match="fp16 split"):
+        cfg = models.gns_cfg(pk, 100, 1000, 15, 15)
+    assert cfg.edge_impl == models.EDGE_IMPL["simt"]
