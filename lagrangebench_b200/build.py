@@ -24,6 +24,13 @@ NVCC_FLAGS = [
 ]
 
 
+def _flags():
+    """LB200_BUILD_CROSSCHECK=1 also compiles the superseded first-generation tensor-core kernels and the A/B
+    variants of the message kernel (tests then compare the product kernels against them)."""
+    extra = ["-DLB200_CROSSCHECK"] if os.environ.get("LB200_BUILD_CROSSCHECK") == "1" else []
+    return NVCC_FLAGS + extra
+
+
 def _nvcc():
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -33,7 +40,7 @@ def _nvcc():
 
 def _digest():
     h = hashlib.sha256()
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for name in sorted(os.listdir(root)):
             if name.endswith((".cu", ".cuh", ".h")):
@@ -50,7 +57,7 @@ def build(force=False, verbose=False):
         with open(STAMP) as f:
             if f.read().strip() == digest:
                 return SO_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    cmd = [_nvcc()] + _flags() + (["-Xptxas", "-v"] if verbose else []) + \
         ["-o", SO_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -29,6 +29,10 @@
 
 namespace lb {
 
+// The first-generation tensor-core kernels (message kernel with the weights in shared memory, node update with
+// five streamed operands) are superseded by gns_tc2.cu / node_tc2.cu.  They are compiled only into a
+// cross-check build (LB200_BUILD_CROSSCHECK=1 -> -DLB200_CROSSCHECK), where the tests compare v2 against them.
+#ifdef LB200_CROSSCHECK
 template <bool kEnc>
 __global__ void __launch_bounds__(kTcThreads, 1) edge_mp_tc_kernel(EdgeTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -638,6 +642,8 @@ __global__ void __launch_bounds__(kNtThreads, 1) node_mp_tc_kernel(NodeTcArgs a)
   }
 }
 
+#endif  // LB200_CROSSCHECK
+
 __global__ void node_embed_kernel(const float* __restrict__ node_feat, int node_in, int node_stride,
                                   const int32_t* __restrict__ ptype, const float* __restrict__ embedding, int embed,
                                   int n_types, int n, float* __restrict__ h) {
@@ -665,6 +671,7 @@ int launch_node_embed(const float* node_feat, int node_in, int node_stride, cons
   return 0;
 }
 
+#ifdef LB200_CROSSCHECK
 int launch_edge_mp_tc(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
   static int ready[kMaxDevices];
   int rc = 0;
@@ -714,5 +721,10 @@ int launch_node_mp_tc(const NodeTcArgs& a, cudaStream_t s) {
   LB_LAUNCHED(1);
   return 0;
 }
+
+#else
+int launch_edge_mp_tc(const EdgeTcArgs&, int, cudaStream_t) { return LB200_EUNSUPPORTED; }
+int launch_node_mp_tc(const NodeTcArgs&, cudaStream_t) { return LB200_EUNSUPPORTED; }
+#endif  // LB200_CROSSCHECK
 
 }  // namespace lb

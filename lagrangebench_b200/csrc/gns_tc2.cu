@@ -63,12 +63,10 @@ constexpr uint32_t k2Smem = k2OffStage + k2Workers * k2StageBytes;
 // contiguous tile ranges per CTA; "last arriving warp issues the GEMM" instead of bar.sync (a dedicated
 // 17th MMA warp is worse still: 5 warps on one SM sub-partition cap every thread at 96 registers);
 // requesting the residual rows before phase A; ld.global.L1::no_allocate for the residual rows (slower).
-// kArrive:  at "operand complete" only the issuing warp waits (bar.sync); the worker's other three warps
-//           bar.arrive and run on into their next phase.  The two hand-offs of an iteration use two barrier
-//           ids; LayerNorm's full worker barrier between them keeps any warp from lapping the issuer.
-// kBucketR: P_r[rcv] is the same row for every edge of a receiver bucket: it is loaded at bucket starts only
-//           (a predicated load per edge instead of a load per edge: a third of the gather's L1 wavefronts).
-template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref, bool kArrive, bool kBucketR>
+// Round 2, measured and dropped as well (LDC-3D 28k, 132.1 us base): bar.arrive for the three non-issuing warps
+// at "operand complete" with two alternating barrier ids (133.1 us); loading P_r[rcv] only at bucket starts
+// through predicated loads (143.5 us: the select chain costs more issue slots than the L1 wavefronts it saves).
+template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref>
 __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -86,7 +84,6 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   const uint32_t bar_g1 = sbase + k2OffBar + 8 * wk, bar_g2 = bar_g1 + 32, bar_st = bar_g1 + 64;
   const uint32_t bar_worker = 1 + wk;            // named barriers: the worker's 128 threads
   const uint32_t bar_ln = 1 + k2Workers + wk;
-  const uint32_t bar_worker2 = 1 + 2 * k2Workers + wk;
 
   const int E = a.rowptr[a.n];
   const int n_tiles = (E + k2Tile - 1) / k2Tile;
@@ -145,16 +142,8 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
 
   // Every thread has written its part of an operand (and fenced it for the async proxy): a worker-wide
   // bar.sync, after which the worker's first warp issues the GEMM.  Returns true in that warp.
-  auto operand_ready = [&](bool second = false) -> bool {
-    if (kArrive) {
-      const uint32_t id = second ? bar_worker2 : bar_worker;
-      if (q == 0)
-        asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(k2WThreads) : "memory");
-      else
-        asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(k2WThreads) : "memory");
-    } else {
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(k2WThreads) : "memory");
-    }
+  auto operand_ready = [&]() -> bool {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(k2WThreads) : "memory");
     return q == 0;
   };
 
@@ -249,8 +238,6 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     const int* sp = idx_base + ib * k2IdxInts;
     const int* rp = sp + 32;
     float ps[32], pr[32];
-    // bucket starts of the tile: edge 0 and every edge after a bucket end (uniform across the worker)
-    const uint32_t smask = kBucketR ? ((endm[ib] << 1) | 1u) : 0xffffffffu;
 #pragma unroll
     for (int j0 = 0; j0 < 32; j0 += 4) {
       const int4 s4 = *reinterpret_cast<const int4*>(sp + j0);
@@ -259,22 +246,10 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       ps[j0 + 1] = __ldg(a.P + (int64_t)s4.y * (2 * kLatent) + f);
       ps[j0 + 2] = __ldg(a.P + (int64_t)s4.z * (2 * kLatent) + f);
       ps[j0 + 3] = __ldg(a.P + (int64_t)s4.w * (2 * kLatent) + f);
-      if (kBucketR) {
-        const int rr[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int j = j0 + t;
-          if ((smask >> j) & 1u)
-            pr[j] = __ldg(a.P + (int64_t)rr[t] * (2 * kLatent) + kLatent + f);
-          else
-            pr[j] = pr[j > 0 ? j - 1 : 0];
-        }
-      } else {
-        pr[j0 + 0] = __ldg(a.P + (int64_t)r4.x * (2 * kLatent) + kLatent + f);
-        pr[j0 + 1] = __ldg(a.P + (int64_t)r4.y * (2 * kLatent) + kLatent + f);
-        pr[j0 + 2] = __ldg(a.P + (int64_t)r4.z * (2 * kLatent) + kLatent + f);
-        pr[j0 + 3] = __ldg(a.P + (int64_t)r4.w * (2 * kLatent) + kLatent + f);
-      }
+      pr[j0 + 0] = __ldg(a.P + (int64_t)r4.x * (2 * kLatent) + kLatent + f);
+      pr[j0 + 1] = __ldg(a.P + (int64_t)r4.y * (2 * kLatent) + kLatent + f);
+      pr[j0 + 2] = __ldg(a.P + (int64_t)r4.z * (2 * kLatent) + kLatent + f);
+      pr[j0 + 3] = __ldg(a.P + (int64_t)r4.w * (2 * kLatent) + kLatent + f);
     }
     mbar_wait(bar_g1, ph1);
     ph1 ^= 1;
@@ -328,7 +303,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     }
     fence_async_smem();
     tc_fence_before();
-    if (operand_ready(true)) {
+    if (operand_ready()) {
       tc_fence_after();
       const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
       issue_gemm_ts<!kNoScale>(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, kMn ? k2IdescBMn : k2Idesc);
@@ -524,19 +499,19 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   }
 }
 
-template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref, bool kArrive = false, bool kBucketR = false>
+template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref>
 static int launch_variant(const EdgeTcArgs& a, int grid, cudaStream_t s) {
   static int ready[kMaxDevices];
   int rc = 0;
   const int dev = device_slot(&rc);
   if (dev < 0) return rc;
   if (!ready[dev]) {
-    rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref, kArrive, kBucketR>,
+    rc = (int)cudaFuncSetAttribute(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem);
     if (rc) return rc;
     ready[dev] = 1;
   }
-  edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref, kArrive, kBucketR><<<grid, k2Threads, k2Smem, s>>>(a);
+  edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref><<<grid, k2Threads, k2Smem, s>>>(a);
   LB_LAUNCHED(1);
   return 0;
 }
@@ -544,9 +519,8 @@ static int launch_variant(const EdgeTcArgs& a, int grid, cudaStream_t s) {
 int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
   static int variant = -1;
   if (variant < 0) {
-    // bit 0: kMn, bit 1: kNoScale, bit 2: kStage, bit 3: kPref, bit 4: kArrive, bit 5: kBucketR
-    const char* e = getenv("LB200_TC2_VARIANT");
-    variant = e ? (atoi(e) & 63) : k2DefaultVariant;
+    const char* e = getenv("LB200_TC2_VARIANT");  // bit 0: kMn, bit 1: kNoScale, bit 2: kStage, bit 3: kPref
+    variant = e ? (atoi(e) & 15) : k2DefaultVariant;
   }
   int rc = 0;
   const int sms = device_sm_count(&rc);
@@ -554,16 +528,16 @@ int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
   const int n_groups = cdiv(cdiv(e_cap, k2Tile), k2Workers);
   const int grid = n_groups < sms ? n_groups : sms;
   if (a.encoder) return launch_variant<true, true, true, false, false>(a, grid, s);
-  switch (variant) {  // the measured ladder, kept for A/B runs
+#ifdef LB200_CROSSCHECK
+  switch (variant) {  // the measured ladder, cross-check builds only
     case 0: return launch_variant<false, false, false, false, false>(a, grid, s);
     case 1: return launch_variant<false, true, false, false, false>(a, grid, s);
     case 3: return launch_variant<false, true, true, false, false>(a, grid, s);
     case 7: return launch_variant<false, true, true, true, false>(a, grid, s);
-    case 31: return launch_variant<false, true, true, true, true, true, false>(a, grid, s);
-    case 47: return launch_variant<false, true, true, true, true, false, true>(a, grid, s);
-    case 63: return launch_variant<false, true, true, true, true, true, true>(a, grid, s);
-    default: return launch_variant<false, true, true, true, true>(a, grid, s);
+    default: break;
   }
+#endif
+  return launch_variant<false, true, true, true, true>(a, grid, s);
 }
 
 // =====================================================================================

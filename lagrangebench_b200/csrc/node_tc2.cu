@@ -147,20 +147,27 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
         }
       }
       if (!kEnc) {
+        // a bucket inside one carry sub-tile: its aggregate; a bucket that straddles sub-tiles (about every second
+        // one at 14 in-edges per node): carry_last of its first sub-tile + carry_first of the following ones,
+        // in slot order.  The first two terms of all 8 rows are requested together.
+        float4 cv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          cv[i] = av[i];
           if (e1[i] > e0[i]) {
             const int ta = e0[i] / kEdgeTile, tb = (e1[i] - 1) / kEdgeTile;
             const float* src = ta == tb ? a.agg + (row0 + r0 + i) * kLatent : a.carry_last + (int64_t)ta * kLatent;
             av[i] = reinterpret_cast<const float4*>(src)[lane];
+            if (tb > ta) cv[i] = reinterpret_cast<const float4*>(a.carry_first + (int64_t)(ta + 1) * kLatent)[lane];
           }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+          av[i].x += cv[i].x; av[i].y += cv[i].y; av[i].z += cv[i].z; av[i].w += cv[i].w;
           if (e1[i] > e0[i]) {
             const int ta = e0[i] / kEdgeTile, tb = (e1[i] - 1) / kEdgeTile;
-            for (int t = ta + 1; t <= tb; ++t) {  // bucket straddles carry sub-tiles: partial sums in slot order
+            for (int t = ta + 2; t <= tb; ++t) {  // in-degree beyond 32: further sub-tiles
               const float4 p = reinterpret_cast<const float4*>(a.carry_first + (int64_t)t * kLatent)[lane];
               av[i].x += p.x; av[i].y += p.y; av[i].z += p.z; av[i].w += p.w;
             }

@@ -225,7 +225,14 @@ static bool carve(const lb200_rollout_cfg* c, void* scratch, int64_t bytes, Roll
 
 using namespace lb;
 
-extern "C" int lb200_version(void) { return 100; }
+// 200: round-2 ABI; odd: a cross-check build that also carries the first-generation tensor-core kernels
+extern "C" int lb200_version(void) {
+#ifdef LB200_CROSSCHECK
+  return 201;
+#else
+  return 200;
+#endif
+}
 
 extern "C" int64_t lb200_launch_count(void) { return g_launches.load(); }
 

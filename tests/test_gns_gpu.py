@@ -198,6 +198,10 @@ def test_pipelined_message_kernel_matches_first_tensor_core_kernel():
     """v2 (weights in TMEM, one rescaled accumulator, two-tile pipeline) against v1 (weights in
     shared memory, two accumulators): same split-precision scheme, same summation order of
     the segmented sum -- they may differ in the last float32 bits of the GEMMs only."""
+    from lagrangebench_b200 import _cabi
+
+    if _cabi.load().lb200_version() % 2 == 0:
+        pytest.skip("product build: the first-generation kernels are compiled with LB200_BUILD_CROSSCHECK=1 only")
     got_v2, ref64, _, (c, ours, f_gpu, params, model) = _forward_both("ldc3d", "float64")
     model.edge_impl = "tc1"
     out, _ = model.apply(params, {}, (f_gpu, c["particle_type"]))
