@@ -98,7 +98,7 @@ struct GraphEntry {
 };
 static std::vector<GraphEntry> g_graphs;       // small LRU (front = oldest)
 static std::vector<std::string> g_seen_once;   // keys of single-step calls seen once, not yet captured
-constexpr size_t kMaxGraphs = 8, kMaxSeen = 32;
+constexpr size_t kMaxGraphs = 64, kMaxSeen = 128;  // one graph per engine of a trajectory batch and per chunk shape
 
 template <typename T>
 static void key_put(std::string& k, const T& v) {

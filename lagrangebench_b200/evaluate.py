@@ -99,6 +99,8 @@ class RolloutEngine:
         if self.h["force_mode"] == 2:
             raise NotImplementedError("a generic Python force callable needs the per-step loop")
         self.packed = model.packed_params(params)
+        self._params = params
+        self._siblings = []  # engines for the other trajectories of a batch (evaluate._eval_batched_rollout)
         self.steps_per_sync = int(steps_per_sync)
         self._cfg = None
         self._cfg_key = None
@@ -140,24 +142,39 @@ class RolloutEngine:
         from the first step on).  Returns ``(predictions (n_steps, N, d), neighbors)``; the returned
         list carries the capacities and builds its ``idx`` array on first access (the step loop
         itself works on the receiver-major view of the graph)."""
-        lib = _cabi.load()
-        h = self.h
+        job = self.start(window, particle_type, targets, n_steps, neighbors, out)
+        while not job.finished:
+            job.enqueue()
+            job.collect()
+        return job.result()
+
+    def start(self, window, particle_type, targets, n_steps, neighbors=None, out=None):
+        """A rollout as a job: ``enqueue()`` puts the next chunk of steps on this engine's stream without
+        waiting, ``collect()`` reads the chunk's status (the host synchronisation).  Several engines can
+        have their chunks in flight at once (``run_batched``)."""
+        return _RolloutJob(self, window, particle_type, targets, n_steps, neighbors, out)
+
+
+class _RolloutJob:
+    def __init__(self, engine, window, particle_type, targets, n_steps, neighbors, out):
+        self.engine = eng = engine
+        h = eng.h
         assert window.is_cuda and window.is_contiguous() and window.dtype == h["dtype"]
         n, isl, dim = window.shape
         dev = window.device
-        if self._ptype[0] is particle_type and self._ptype[1].device == dev:
-            ptype, n_valid = self._ptype[1], self._ptype[2]
+        if eng._ptype[0] is particle_type and eng._ptype[1].device == dev:
+            ptype, n_valid = eng._ptype[1], eng._ptype[2]
         else:
             ptype = torch.as_tensor(particle_type).to(dev, torch.int32).contiguous()
             n_valid = num_real_particles(particle_type)
-            self._ptype = (particle_type, ptype, n_valid)
+            eng._ptype = (particle_type, ptype, n_valid)
         if ptype.shape[0] != n:
             raise ValueError(f"particle_type has {ptype.shape[0]} rows, the position window {n}")
         nfn = h["neighbor_fn"]
         if neighbors is None or neighbors._grid is None or neighbors._grid.n != n:
             # also a trajectory with another particle count than the list was allocated for (rollout.py:383)
             neighbors = nfn.allocate(window[:, -1].contiguous(), num_particles=n_valid)
-        self._configure(neighbors, n_valid)
+        eng._configure(neighbors, n_valid)
         if out is not None:
             assert out.shape == (n_steps, n, dim) and out.dtype == window.dtype and out.device == dev \
                 and out.is_contiguous()
@@ -167,44 +184,74 @@ class RolloutEngine:
         if targets is not None:
             targets = targets.to(dev, window.dtype).contiguous()
             assert targets.shape == (n_steps, n, dim)
-        if self._status is None or self._status.device != dev:
-            self._status = torch.zeros(4, dtype=torch.int32, device=dev)
-        status = self._status  # reset on the device at the start of every lb200_rollout_steps call
-        if self._stream is None:
-            self._stream = torch.cuda.Stream(device=dev)
-        caller = torch.cuda.current_stream(dev)
-        done = 0
-        while done < n_steps:
-            chunk = min(self.steps_per_sync, n_steps - done)
-            self._stream.wait_stream(caller)
-            with torch.cuda.stream(self._stream):
-                # base pointers + first frame: every chunk of a long rollout replays the same cached step graph
-                _cabi.check(lib.lb200_rollout_steps(
-                    C.byref(self._cfg), chunk, _cabi.ptr(self.packed.blob), _cabi.ptr(window), _cabi.ptr(ptype), None,
-                    _cabi.ptr(targets), _cabi.ptr(preds), done, None, _cabi.ptr(status),
-                    _cabi.ptr(self._scratch), self._scratch.numel(), _cabi.stream()))
-            caller.wait_stream(self._stream)
-            self.n_launch_calls += 1
-            completed, overflow, n_edges, _ = status.tolist()  # the one host sync per chunk
-            done += completed
-            if overflow & _cabi.ERR_NONFINITE:
-                raise FloatingPointError(
-                    "rollout produced NaN / Inf accelerations: an activation left the range of the fp16 split of the "
-                    "tensor-core kernels (|x| > 65504).  Set model.edge_impl = 'simt' for the float32 CUDA-core kernels.")
-            if overflow:  # rollout.py:135-151: re-allocate from the current state, retry the step
-                self.n_reallocations += 1
-                neighbors = nfn.allocate(window[:, -1].contiguous(), num_particles=n_valid)
-                self._configure(neighbors, n_valid)
+        if eng._status is None or eng._status.device != dev:
+            eng._status = torch.zeros(4, dtype=torch.int32, device=dev)
+        if eng._stream is None:
+            eng._stream = torch.cuda.Stream(device=dev)
+        self.window, self.ptype, self.n_valid, self.targets, self.preds = window, ptype, n_valid, targets, preds
+        self.neighbors, self.n_steps, self.done, self.n_edges = neighbors, n_steps, 0, 0
+        self.dev = dev
+
+    @property
+    def finished(self):
+        return self.done >= self.n_steps
+
+    def enqueue(self):
+        eng, lib = self.engine, _cabi.load()
+        chunk = min(eng.steps_per_sync, self.n_steps - self.done)
+        eng._stream.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(eng._stream):
+            # base pointers + first frame: every chunk of a long rollout replays the same cached step graph;
+            # status is reset on the device at the start of every lb200_rollout_steps call
+            _cabi.check(lib.lb200_rollout_steps(
+                C.byref(eng._cfg), chunk, _cabi.ptr(eng.packed.blob), _cabi.ptr(self.window), _cabi.ptr(self.ptype), None,
+                _cabi.ptr(self.targets), _cabi.ptr(self.preds), self.done, None, _cabi.ptr(eng._status),
+                _cabi.ptr(eng._scratch), eng._scratch.numel(), _cabi.stream()))
+        eng.n_launch_calls += 1
+
+    def collect(self):
+        eng = self.engine
+        torch.cuda.current_stream(self.dev).wait_stream(eng._stream)
+        completed, overflow, n_edges, _ = eng._status.tolist()  # the one host sync per chunk
+        self.done += completed
+        self.n_edges = n_edges
+        if overflow & _cabi.ERR_NONFINITE:
+            raise FloatingPointError(
+                "rollout produced NaN / Inf accelerations: an activation left the range of the fp16 split of the "
+                "tensor-core kernels (|x| > 65504).  Set model.edge_impl = 'simt' for the float32 CUDA-core kernels.")
+        if overflow:  # rollout.py:135-151: re-allocate from the current state, retry the step
+            eng.n_reallocations += 1
+            self.neighbors = eng.h["neighbor_fn"].allocate(self.window[:, -1].contiguous(), num_particles=self.n_valid)
+            eng._configure(self.neighbors, self.n_valid)
+
+    def result(self):
         # the list a per-step caller would hold now: built (lazily) on the positions the last step started from
-        ref = window[:, -2] if (n_steps > 0 and isl > 1) else window[:, -1]
-        if n_steps > 0:
-            stats = torch.zeros(4, dtype=torch.int32, device=dev)
-            stats[0] = status[2]  # edges of the last step; the overflow bits are clear (the loop retried them away)
+        eng, window, nbrs = self.engine, self.window, self.neighbors
+        ref = window[:, -2] if (self.n_steps > 0 and window.shape[1] > 1) else window[:, -1]
+        if self.n_steps > 0:
+            stats = torch.zeros(4, dtype=torch.int32, device=self.dev)
+            stats[0] = eng._status[2]  # edges of the last step; the overflow bits are clear (retried away)
         else:
-            stats = neighbors._stats
-        out_nl = NeighborList(nfn, None, stats, ref.clone(), neighbors.cell_list_capacity, neighbors.max_occupancy,
-                              neighbors._scratch, neighbors._grid)
-        return preds, out_nl
+            stats = nbrs._stats
+        out_nl = NeighborList(eng.h["neighbor_fn"], None, stats, ref.clone(), nbrs.cell_list_capacity,
+                              nbrs.max_occupancy, nbrs._scratch, nbrs._grid)
+        return self.preds, out_nl
+
+
+def run_batched(engines, jobs):
+    """The reference ``vmap``s a batch of trajectories (``rollout.py:221-228``); here every trajectory of
+    the batch gets its own engine and stream, and the chunks of all of them are in flight together --
+    small clouds are launch / latency bound, so their step graphs overlap on the device.
+    ``jobs``: one ``(window, particle_type, targets, n_steps, neighbors)`` per engine.
+    Returns ``[(predictions, neighbors), ...]``."""
+    live = [eng.start(*args) for eng, args in zip(engines, jobs)]
+    while any(not j.finished for j in live):
+        todo = [j for j in live if not j.finished]
+        for j in todo:
+            j.enqueue()
+        for j in todo:
+            j.collect()
+    return [j.result() for j in live]
 
 
 # ----------------------------------------------------------------------------- reference loop
@@ -222,8 +269,8 @@ def _forward_eval(params, state, sample, current_positions, target_positions, mo
 
 def _eval_batched_rollout(model_apply, case, params, state, traj_batch_i, neighbors, metrics_computer,
                           n_rollout_steps, t_window, n_extrap_steps=0, engine=None):
-    """``rollout.py:78-178``.  The reference ``vmap``s over the batch; here trajectories of
-    a batch are rolled out one after the other.  Returns
+    """``rollout.py:78-178``.  The reference ``vmap``s over the batch; here the trajectories of a batch
+    run concurrently, one engine and stream each (``run_batched``).  Returns
     ``(predictions (B, T, N, d), [metrics per trajectory], neighbors)``."""
     _cabi.require_cuda()
     h = case._lb200
@@ -235,17 +282,29 @@ def _eval_batched_rollout(model_apply, case, params, state, traj_batch_i, neighb
     traj_len = n_rollout_steps + n_extrap_steps
     dev = torch.device("cuda")
     predictions, metrics = [], []
+    currents, ptypes, targets_b, gts = [], [], [], []
     for b in range(bsz):
         pos_b = pos_input_batch[b].to(dev, h["dtype"])
-        ptype = particle_type_batch[b].to(dev, torch.int32)
-        current = pos_b[:, :t_window].contiguous()
+        ptypes.append(particle_type_batch[b].to(dev, torch.int32))
+        currents.append(pos_b[:, :t_window].contiguous())
         targets = pos_b[:, t_window:t_window + traj_len].permute(1, 0, 2).contiguous()  # (T, N, d)
         if targets.shape[0] < traj_len:  # extrapolation: JAX clamps the step index (rollout.py:158)
             pad = targets[-1:].expand(traj_len - targets.shape[0], -1, -1)
             targets = torch.cat([targets, pad], dim=0).contiguous()
-        if engine is not None:
-            preds, neighbors = engine.run(current, ptype, targets, traj_len, neighbors)
-        else:
+        targets_b.append(targets)
+        gts.append(pos_b[:, t_window:t_window + n_rollout_steps].permute(1, 0, 2))
+    if engine is not None:
+        # the batch axis of the reference's vmap: one engine (stream, scratch, step graph) per trajectory
+        while len(engine._siblings) < bsz - 1:
+            engine._siblings.append(RolloutEngine(engine.case, engine.model, engine._params, engine.steps_per_sync))
+        engines = [engine] + engine._siblings[:bsz - 1]
+        results = run_batched(engines, [(currents[b], ptypes[b], targets_b[b], traj_len, neighbors if b == 0 else None)
+                                        for b in range(bsz)])
+        predictions = [r[0] for r in results]
+        neighbors = results[0][1]
+    else:
+        for b in range(bsz):
+            current, ptype, targets = currents[b], ptypes[b], targets_b[b]
             preds = torch.empty((traj_len, n_nodes, dim), dtype=h["dtype"], device=dev)
             st, step = state, 0
             while step < traj_len:
@@ -257,12 +316,9 @@ def _eval_batched_rollout(model_apply, case, params, state, traj_batch_i, neighb
                                             case.integrate)
                 preds[step] = current[:, -1]
                 step += 1
-        predictions.append(preds)
-        if metrics_computer is not None:
-            gt = pos_b[:, t_window:t_window + n_rollout_steps].permute(1, 0, 2)
-            metrics.append(metrics_computer(preds[:n_rollout_steps], gt))
-        else:
-            metrics.append({})
+            predictions.append(preds)
+    for b in range(bsz):
+        metrics.append(metrics_computer(predictions[b][:n_rollout_steps], gts[b]) if metrics_computer is not None else {})
     return torch.stack(predictions), metrics, neighbors
 
 

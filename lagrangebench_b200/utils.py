@@ -97,10 +97,39 @@ def save_pytree(ckp_dir, pytree_obj, name):
         pickle.dump(_tree_map(lambda t: 0, pytree_obj), f)
 
 
+class _TreeUnpickler(pickle.Unpickler):
+    """``*_tree.pkl`` holds only the STRUCTURE of the pytree.  Checkpoints written with older haiku
+    versions pickle it as ``haiku._src.data_structures.FlatMapping`` (a Mapping); without haiku installed
+    that class -- and any other mapping class of a missing module -- is read as a plain dict."""
+
+    class _Mapping(dict):
+        def __setstate__(self, state):  # FlatMapping pickles {"_structure"/"_leaves"} or its dict
+            if isinstance(state, dict):
+                inner = state.get("_mapping", state.get("mapping", state))
+                self.update(inner if isinstance(inner, dict) else state)
+
+        def __reduce_ex__(self, protocol):
+            return (dict, (dict(self),))
+
+    def find_class(self, module, name):
+        try:
+            return super().find_class(module, name)
+        except (ImportError, AttributeError):
+            return _TreeUnpickler._Mapping
+
+
+def _plain(tree):
+    if isinstance(tree, dict):
+        return {k: _plain(v) for k, v in tree.items()}
+    if isinstance(tree, (tuple, list)):
+        return type(tree)(_plain(v) for v in tree)
+    return tree
+
+
 def load_pytree(model_dir, name):
     """``utils.py:99-109``."""
     with open(os.path.join(model_dir, f"{name}_tree.pkl"), "rb") as f:
-        tree_struct = pickle.load(f)
+        tree_struct = _plain(_TreeUnpickler(f).load())
     n_leaves = len(tree_leaves_sorted(tree_struct))
     with open(os.path.join(model_dir, f"{name}_array.npy"), "rb") as f:
         flat = [np.load(f) for _ in range(n_leaves)]

@@ -49,3 +49,10 @@ def test_three_ranks_sharing_one_gpu_with_reselection_and_migration():
                          "--mp", "3"))
     sel = int(out.split("selections=")[1].split()[0])
     assert sel >= 2, out
+
+
+def test_walled_box_with_kinematic_particles_shards():
+    """LDC-shaped cloud (no periodic axis, solid walls and a moving lid whose positions come from the
+    trajectory): open slabs at both ends, ``bound`` features, targets follow their owner."""
+    out = _run(_torchrun(2, 29580, "--case", "ldc3d", "--steps", "3", "--same-gpu", "--mp", "3"))
+    assert "world=2" in out

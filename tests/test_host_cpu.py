@@ -294,3 +294,52 @@ def test_fp16_range_bounds_of_the_weights():
     with pytest.warns(UserWarning, match="fp16 split"):
         cfg = models.gns_cfg(pk, 100, 1000, 15, 15)
     assert cfg.edge_impl == models.EDGE_IMPL["simt"]
+
+
+def test_load_haiku_reads_a_checkpoint_written_the_reference_way(tmp_path):
+    """``utils.py:50-58`` of the reference, restated here as an independent writer: the leaves of
+    ``jax.tree_leaves(params)`` (nested dict, keys sorted at every level) ``np.save``d back to back into
+    ``params_array.npy``, the structure with every leaf replaced by 0 pickled into ``params_tree.pkl`` --
+    here as a Mapping class of a module that does not exist at load time (haiku's FlatMapping)."""
+    import json
+    import pickle
+    import sys
+    import types
+
+    params = ogns.init_params(12, 3, 2, num_mp_steps=2, seed=9)
+
+    def leaves(tree):  # jax.tree_util order for dicts: sorted keys, depth first
+        if isinstance(tree, dict):
+            return [x for k in sorted(tree) for x in leaves(tree[k])]
+        return [tree]
+
+    ckp = tmp_path / "best"
+    ckp.mkdir()
+    with open(ckp / "params_array.npy", "wb") as f:
+        for x in leaves(params):
+            np.save(f, x, allow_pickle=False)
+    mod = types.ModuleType("haiku_like_structures")
+
+    class FlatMapping(dict):
+        pass
+
+    FlatMapping.__module__, FlatMapping.__qualname__ = "haiku_like_structures", "FlatMapping"
+    mod.FlatMapping = FlatMapping
+    sys.modules["haiku_like_structures"] = mod
+    try:
+        struct = FlatMapping({k: FlatMapping({kk: 0 for kk in v}) for k, v in params.items()})
+        with open(ckp / "params_tree.pkl", "wb") as f:
+            pickle.dump(struct, f)
+        with open(ckp / "state_tree.pkl", "wb") as f:
+            pickle.dump({}, f)
+        open(ckp / "state_array.npy", "wb").close()
+    finally:
+        del sys.modules["haiku_like_structures"]  # the loader must cope without the class
+    (ckp / "metadata_ckp.json").write_text(json.dumps({"step": 1234, "loss": 0.5}))
+    got, state, opt, step = utils.load_haiku(str(ckp))
+    assert step == 1234 and state == {} and opt is None
+    assert sorted(got) == sorted(params) and type(got) is dict
+    for k in params:
+        for kk in params[k]:
+            assert np.array_equal(got[k][kk], params[k][kk]), (k, kk)
+    assert utils.get_num_params(got) == ogns.num_params(params)

@@ -172,6 +172,11 @@ def test_infer_and_eval_rollout_api(tmp_path):
     assert payload["predicted_rollout"].shape == (11, 3200, 2)
     assert payload["ground_truth_rollout"].shape == (11, 3200, 2)
     assert np.array_equal(payload["predicted_rollout"][:6], payload["ground_truth_rollout"][:6])
+    # the trajectories of a batch run on concurrent engines (the reference's vmap axis): same numbers as one by one
+    one_by_one = infer(model, case, ds, params=params, state=state, cfg_eval_infer={"batch_size": 1, "metrics": ["mse"],
+                       "out_type": "none", "n_trajs": -1}, n_rollout_steps=5, seed=0)
+    for k in metrics:
+        assert torch.equal(torch.as_tensor(metrics[k]["mse"]).cpu(), torch.as_tensor(one_by_one[k]["mse"]).cpu())
 
 
 def test_infer_from_an_hdf5_dataset_with_saved_checkpoint(tmp_path):

@@ -46,15 +46,17 @@ def main():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     npd = np.float64 if args.dtype == "float64" else np.float32
     tdt = torch.float64 if args.dtype == "float64" else torch.float32
-    c = synthetic.make_case(args.case, 6, 0, 0, npd)
+    c = synthetic.make_case(args.case, 6, args.steps, 0, npd)  # future frames: where kinematic particles are put
     if args.spread > 0:  # a coherent drift along every axis plus the case's jitter
         dx = c["metadata"]["dx"]
         drift = args.spread * dx * np.arange(6, dtype=npd)[None, :, None]
-        c["positions"] = np.mod(c["positions"][:, :6] + drift, c["box"].astype(npd)).astype(npd)
+        c["positions"] = np.mod(c["positions"][:, :6] + drift, c["box"].astype(npd)).astype(npd)  # drops the future frames
         c["metadata"]["vel_mean"] = [args.spread * dx] * c["metadata"]["dim"]
     d = c["metadata"]["dim"]
     n = c["positions"].shape[0]
-    params = lbmodels.init_params(5 * d + d, d, 128, args.mp, 16, seed=0)
+    node_in = 5 * d + (2 * d if not any(c["metadata"]["periodic_boundary_conditions"]) else 0) + \
+        (d if c["force"] is not None else 0)
+    params = lbmodels.init_params(node_in, d, 128, args.mp, 16, seed=0)
     dr = DistributedRollout(c["box"], c["metadata"], params, args.mp, force=c["force"], dtype=tdt,
                             multiplier=c["multiplier"], halo_margin=args.margin, steps_per_sync=args.sync)
     dr.scatter(c["positions"], c["particle_type"])
@@ -73,7 +75,9 @@ def main():
         model = GNS(d, 128, 2, args.mp, 16)
         eng = RolloutEngine(case, model, params)
         window = torch.as_tensor(c["positions"][:, :6]).cuda().contiguous()
-        ref, _ = eng.run(window, c["particle_type"], None, args.steps)
+        fut = c["positions"][:, 6:6 + args.steps]
+        targets = torch.as_tensor(fut).permute(1, 0, 2).cuda().contiguous() if fut.shape[1] == args.steps else None
+        ref, _ = eng.run(window, c["particle_type"], targets, args.steps)
         diff = case.displacement(pos, ref[-1]).abs().max().item()
         dx = c["metadata"]["dx"]
         print(f"world={world} N={n} steps={args.steps} owned_total={int(owned)} edges_rank0={dr.edges_last} "
