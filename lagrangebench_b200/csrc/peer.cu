@@ -17,7 +17,11 @@ constexpr int kCtrlSigRight = 1;   // ... by the RIGHT neighbour
 constexpr int kCtrlEpoch = 2;      // rollout steps this rank has finished enqueuing-order-wise (local)
 constexpr int kCtrlSticky = 3;     // status bits raised on this rank or seen from any rank (local, sticky per call)
 constexpr int kCtrlGlobal = 4;     // OR over all ranks of this step's bits (the integrate kernel's skip flag)
-constexpr int kCtrlFlags = 16;     // [kCtrlFlags + r]: (epoch + 1) << 8 | bits, written by rank r
+// [kCtrlFlags + (epoch & 1) * LB200_MAX_RANKS + r]: (epoch + 1) << 8 | bits, written by rank r.  Two slots by step
+// parity: only NEIGHBOURS are fenced against each other by the exchanges, a rank two slabs away can already
+// publish step e + 1 while this rank has not read step e yet (it cannot reach step e + 2: that needs this
+// rank's word of step e + 1).
+constexpr int kCtrlFlags = 16;
 constexpr int64_t kCtrlBytes = 4096;
 constexpr long long kSpinTimeoutNs = 20ll * 1000 * 1000 * 1000;  // a dead peer must not hang the GPU
 
@@ -114,19 +118,20 @@ __global__ void shard_flag_bcast_kernel(uint32_t* ctrl, const int32_t* __restric
                                         CtrlAll ctrl_all) {
   const int r = threadIdx.x;
   const uint32_t bits = (ctrl[kCtrlSticky] | (uint32_t)nbr_stats[2] | (nbr_stats[3] ? LB200_ERR_NONFINITE : 0u)) & 0xffu;
-  const uint32_t word = ((ctrl[kCtrlEpoch] + 1u) << 8) | bits;
-  if (r < world) st_release_sys(ctrl_all.p[r] + kCtrlFlags + rank, word);
+  const uint32_t epoch = ctrl[kCtrlEpoch];
+  const uint32_t word = ((epoch + 1u) << 8) | bits;
+  if (r < world) st_release_sys(ctrl_all.p[r] + kCtrlFlags + (epoch & 1u) * LB200_MAX_RANKS + rank, word);
 }
 
 // OR of all ranks' bits of this step -> ctrl[kCtrlGlobal] (integrate's skip flag), sticky for the later steps
 __global__ void shard_flag_wait_kernel(uint32_t* ctrl, int world) {
   const int r = threadIdx.x;
-  const uint32_t tag = ctrl[kCtrlEpoch] + 1u;
+  const uint32_t epoch = ctrl[kCtrlEpoch], tag = epoch + 1u;
   uint32_t bits = 0;
   if (r < world) {
     const long long t0 = global_ns();
     for (;;) {
-      const uint32_t w = ld_acquire_sys(ctrl + kCtrlFlags + r);
+      const uint32_t w = ld_acquire_sys(ctrl + kCtrlFlags + (epoch & 1u) * LB200_MAX_RANKS + r);
       if ((w >> 8) == tag) {
         bits = w & 0xffu;
         break;

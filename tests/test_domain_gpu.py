@@ -56,3 +56,12 @@ def test_walled_box_with_kinematic_particles_shards():
     trajectory): open slabs at both ends, ``bound`` features, targets follow their owner."""
     out = _run(_torchrun(2, 29580, "--case", "ldc3d", "--steps", "3", "--same-gpu", "--mp", "3"))
     assert "world=2" in out
+
+
+def test_four_ranks_where_not_everybody_is_a_neighbour():
+    """From four slabs on, ranks two slabs apart are fenced against each other only through their common
+    neighbour and may be a step apart when the status words of a step are published (two slots by step
+    parity).  Drift makes every chunk stop early, so the no-op steps that follow a raised bit run too."""
+    out = _run(_torchrun(4, 29581, "--case", "rpf3d_8k", "--steps", "5", "--same-gpu", "--spread", "0.12",
+                         "--mp", "2"))
+    assert "world=4" in out and int(out.split("selections=")[1].split()[0]) >= 2
