@@ -70,6 +70,29 @@ int shard_call_init(const lb200_shard* sh, cudaStream_t s);
 void prof_begin(int cls, cudaStream_t s);
 void prof_end(int cls, cudaStream_t s);
 
+// ---- programmatic dependent launch: a kernel launched with the attribute may begin (its prologue: barrier
+// init, TMEM allocation, weights -> tensor memory) while the previous kernel of the stream drains; it calls
+// pdl_wait() before it touches anything that kernel produced.  Both instructions are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();  // LB200_PDL=0 switches the attribute off (A/B measurements)
+
+template <typename Arg>
+static inline cudaError_t launch_maybe_pdl(void (*kernel)(Arg), int grid, int block, size_t smem, cudaStream_t s,
+                                           const Arg& arg) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, arg);
+}
+
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -85,12 +85,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   const uint32_t bar_worker = 1 + wk;            // named barriers: the worker's 128 threads
   const uint32_t bar_ln = 1 + k2Workers + wk;
 
-  const int E = a.rowptr[a.n];
-  const int n_tiles = (E + k2Tile - 1) / k2Tile;
-  // this CTA's tiles: worker wk takes t_begin + wk + i * tile_stride
-  const int t_begin = (int)blockIdx.x * k2Workers;
-  if (t_begin >= n_tiles) return;
-
+  pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel's tail (it waits before reading)
   if (tid == 0) {
     for (int w = 0; w < 3 * k2Workers; ++w) mbar_init(sbase + k2OffBar + 8 * w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -112,11 +107,17 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above read constants only (weights); from here on the previous kernel's results are used
+  pdl_wait();
+  const int E = a.rowptr[a.n];
+  const int n_tiles = (E + k2Tile - 1) / k2Tile;
+  // this CTA's tiles: worker wk takes t_begin + wk + i * tile_stride
+  const int t_begin = (int)blockIdx.x * k2Workers;
 
   const uint32_t w1_hi = tmem + k2ColW1Hi, w1_lo = tmem + k2ColW1Lo, w2_hi = tmem + k2ColW2Hi, w2_lo = tmem + k2ColW2Lo;
   const int tile_stride = (int)gridDim.x * k2Workers;
 
-  {
+  if (t_begin < n_tiles) {
   const float b2c = vec[f], ln_scale = vec[128 + f], ln_offset = vec[256 + f];
   const uint32_t acc0 = tmem + k2ColAcc + wk * 64;                       // + buf * 32
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
@@ -511,7 +512,8 @@ static int launch_variant(const EdgeTcArgs& a, int grid, cudaStream_t s) {
     if (rc) return rc;
     ready[dev] = 1;
   }
-  edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref><<<grid, k2Threads, k2Smem, s>>>(a);
+  rc = (int)launch_maybe_pdl(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref>, grid, k2Threads, k2Smem, s, a);
+  if (rc) return rc;
   LB_LAUNCHED(1);
   return 0;
 }

@@ -56,7 +56,11 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
 
   const int n_tiles = (a.n + k2Tile - 1) / k2Tile;
   const int grid = (int)gridDim.x;
-  if ((int)blockIdx.x >= n_tiles) return;
+  pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel's tail (it waits before reading)
+  if ((int)blockIdx.x >= n_tiles) {
+    pdl_wait();  // a CTA never exits before the previous kernel is complete: the chain of waits stays transitive
+    return;
+  }
 
   if (tid == 0) {
     for (int w = 0; w < 2 * kN2Workers; ++w) mbar_init(sbase + kN2OffBar + 8 * w, 1);
@@ -85,6 +89,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // constants only so far (weights); h, the aggregates and the CSR are the previous kernels' results
 
   const float b1 = vec[f], b2c = vec[128 + f], ln_scale = vec[256 + f], ln_offset = vec[384 + f], b_next = vec[512 + f];
   const uint32_t w1h_hi = tmem, w1h_lo = tmem + 64, w1a_hi = tmem + 128, w1a_lo = tmem + 192, w2_hi = tmem + 256,
@@ -411,11 +416,9 @@ int launch_node_mp_tc2(const NodeTcArgs& a, cudaStream_t s) {
   // tile t belongs to CTA t % grid, worker (t / grid) % 4: a small cloud spreads over as many SMs as it has tiles
   const int n_tiles = cdiv(a.n, k2Tile);
   const int grid = n_tiles < sms ? n_tiles : sms;
-  if (a.enc) {
-    node_mp_tc2_kernel<true><<<grid, kN2Threads, kN2Smem, s>>>(a);
-  } else {
-    node_mp_tc2_kernel<false><<<grid, kN2Threads, kN2Smem, s>>>(a);
-  }
+  rc = (int)(a.enc ? launch_maybe_pdl(node_mp_tc2_kernel<true>, grid, kN2Threads, kN2Smem, s, a)
+                   : launch_maybe_pdl(node_mp_tc2_kernel<false>, grid, kN2Threads, kN2Smem, s, a));
+  if (rc) return rc;
   LB_LAUNCHED(1);
   return 0;
 }

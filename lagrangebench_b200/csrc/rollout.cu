@@ -17,6 +17,15 @@ namespace lb {
 
 std::atomic<int64_t> g_launches{0};
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LB200_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 int device_sm_count(int* rc) {
   static int sms[kMaxDevices];
   const int dev = device_slot(rc);

@@ -20,12 +20,12 @@ except Exception as exc:
     print(sys.argv[1], "FAILED", exc)
 PY
 }
-run base LB200_NODE_TC=2 --
-run node_v1 LB200_NODE_TC=1 --
-run tc2_arrive LB200_TC2_VARIANT=31 --
-run tc2_bucket LB200_TC2_VARIANT=47 --
-run tc2_both LB200_TC2_VARIANT=63 --
+run pdl_on LB200_PDL=1 --
+run pdl_off LB200_PDL=0 --
+run pdl_on2 LB200_PDL=1 --
+run pdl_off2 LB200_PDL=0 --
 run tgv2d X=1 -- --workload tgv2d
+run tgv2d_nopdl LB200_PDL=0 -- --workload tgv2d
 run rpf2d X=1 -- --workload rpf2d
 run dam2d X=1 -- --workload dam2d
 run ldc3d_8k X=1 -- --workload ldc3d
