@@ -491,6 +491,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "edge_mp_tc2_kernel (tcgen05, weights in TMEM: fused gather + edge MLP + "
                          "LayerNorm + residual + segmented sum)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(args.workload),
+                         "traffic_source": "profiles/ncu_traffic.json (dram bytes per launch of the committed ncu --set full "
+                                           "capture of this kernel and workload; not measured in this run)",
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_kind,
                          "avg_launch_ms": edge_ms_avg, "launches": int(kl[0]),
                          "share_of_step": kms[0] / ms_prof, "node_kernel_share_of_step": kms[1] / ms_prof,
