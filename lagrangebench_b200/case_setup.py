@@ -62,10 +62,12 @@ class NeighborList:
     hands back a list object that builds the jax-md ordered ``(2, E_cap)`` array from
     ``reference_position`` the first time it is read."""
 
-    def __init__(self, fn, idx, stats, reference_position, cell_list_capacity, max_occupancy, scratch, grid=None):
+    def __init__(self, fn, idx, stats, reference_position, cell_list_capacity, max_occupancy, scratch, grid=None,
+                 n_edges=None):
         self._fn = fn
         self._idx = idx  # (2, E_cap) int32: row 0 receivers, row 1 senders; pad = N
-        self._stats = stats  # device int32[4]: E, max cell occupancy, overflow bits, -
+        self._stats_dev = stats  # device int32[4]: E, max cell occupancy, overflow bits, -
+        self._n_edges = n_edges  # known on the host (engine results): the device words are made when somebody asks
         self.reference_position = reference_position
         self.cell_list_capacity = cell_list_capacity
         self.max_occupancy = max_occupancy
@@ -85,12 +87,21 @@ class NeighborList:
         self._idx = value
 
     @property
+    def _stats(self):
+        if self._stats_dev is None:  # an engine result: no overflow (the loop retried it away), E from its status
+            dev = self.reference_position.device
+            self._stats_dev = torch.tensor([int(self._n_edges or 0), 0, 0, 0], dtype=torch.int32).to(dev)
+        return self._stats_dev
+
+    @property
     def did_buffer_overflow(self):
         """0-dim bool device tensor; reading it on the host synchronises (as in the reference)."""
         return self._stats[2] != 0
 
     @property
     def n_edges(self):
+        if self._n_edges is not None and self._stats_dev is None:
+            return int(self._n_edges)
         return int(self._stats[0].item())
 
     def update(self, position, num_particles=None, **kwargs):

@@ -228,13 +228,12 @@ class _RolloutJob:
         # the list a per-step caller would hold now: built (lazily) on the positions the last step started from
         eng, window, nbrs = self.engine, self.window, self.neighbors
         ref = window[:, -2] if (self.n_steps > 0 and window.shape[1] > 1) else window[:, -1]
-        if self.n_steps > 0:
-            stats = torch.zeros(4, dtype=torch.int32, device=self.dev)
-            stats[0] = eng._status[2]  # edges of the last step; the overflow bits are clear (retried away)
+        if self.n_steps > 0:  # edges of the last step are known on the host; the overflow bits are clear (retried away)
+            out_nl = NeighborList(eng.h["neighbor_fn"], None, None, ref.clone(), nbrs.cell_list_capacity,
+                                  nbrs.max_occupancy, nbrs._scratch, nbrs._grid, n_edges=self.n_edges)
         else:
-            stats = nbrs._stats
-        out_nl = NeighborList(eng.h["neighbor_fn"], None, stats, ref.clone(), nbrs.cell_list_capacity,
-                              nbrs.max_occupancy, nbrs._scratch, nbrs._grid)
+            out_nl = NeighborList(eng.h["neighbor_fn"], None, nbrs._stats, ref.clone(), nbrs.cell_list_capacity,
+                                  nbrs.max_occupancy, nbrs._scratch, nbrs._grid)
         return self.preds, out_nl
 
 

@@ -252,3 +252,41 @@ def test_padding_particles_stay_out_of_the_search(name, dtype):
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
     assert b[0][n_real] == b[0][-1]
+
+
+def test_matscipy_padded_h5dataset_sample(tmp_path):
+    """``H5Dataset(..., nl_backend="matscipy")`` pads every sample to ``num_particles_max`` with particles of
+    type -1 at the origin (``data.py:183-197,222-223``); ``preprocess`` passes ``num_particles`` on
+    (``case.py:182-190``).  The padded sample's edge list is the oracle's, and a rollout through ``infer``
+    leaves the padding rows where the trajectory has them."""
+    import json
+
+    from h5write import write_h5
+    from lagrangebench_b200 import GNS, infer, synthetic
+    from lagrangebench_b200.data import H5Dataset
+
+    c = synthetic.make_case("tgv2d", 6, 3, seed=3, dtype=np.float32)
+    n = c["positions"].shape[0]
+    root = tmp_path / "2D_TGV_2500_10kevery100"
+    root.mkdir()
+    write_h5(str(root / "test.h5"), {"00000": {"position": np.ascontiguousarray(c["positions"].transpose(1, 0, 2)),
+                                               "particle_type": c["particle_type"].astype(np.int32)}}, chunk_rows=4)
+    meta = dict(c["metadata"], num_particles_max=n + 137)
+    (root / "metadata.json").write_text(json.dumps(meta))
+    ds = H5Dataset("test", str(root), input_seq_length=6, extra_seq_length=3, nl_backend="matscipy")
+    pos, ptype = ds[0]
+    assert pos.shape[0] == n + 137 and (ptype[n:] == -1).all() and (pos[n:] == 0).all()
+    kw = dict(cfg_neighbors={"multiplier": 1.25, "backend": "matscipy"}, noise_std=0.0)
+    ours = case_builder(c["box"], meta, 6, dtype="float32", **kw)
+    orac = ocase.case_builder(c["box"], meta, 6, dtype=np.float32, **kw)
+    _, n_gpu = ours.allocate_eval((pos[:, :6], ptype))
+    _, n_cpu = orac.allocate_eval((pos[:, :6], ptype))
+    idx = n_gpu.idx.cpu().numpy()
+    assert np.array_equal(idx, n_cpu.idx)
+    assert idx[idx < n + 137].max() < n  # no padding row is a sender or a receiver
+    model = GNS(2, 128, 2, 2, 16)
+    feats, _ = ours.allocate_eval((pos[:, :6], ptype))
+    params, state = model.init(0, (feats, ptype))
+    out = infer(model, ours, ds, params=params, state=state, cfg_eval_infer={"batch_size": 1, "metrics": ["mse"],
+                "out_type": "none", "n_trajs": 1}, n_rollout_steps=3)
+    assert np.isfinite(np.asarray(torch.as_tensor(out["rollout_0"]["mse"]).cpu())).all()

@@ -13,3 +13,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-strong-scaling > gpurun_out/${tag}_launches.log 2>&1
 python profiles/summarize_launches.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_launches.summary.txt 2>&1
 head -30 gpurun_out/${tag}_launches.summary.txt
+timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; tail -2 gpurun_out/${tag}_smoke.log
