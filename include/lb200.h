@@ -243,6 +243,10 @@ typedef struct {
   const struct lb200_shard_s* shard;
   /* dev int32* or NULL: OR-ed with 1 when an output acceleration is NaN / Inf (see LB200_ERR_NONFINITE) */
   int32_t* nonfinite_flag;
+  /* the model's latent width (gns.py:37 latent_size), 0 = 128.  Narrower models (the published GNS-5-64) run on the
+   * 128-wide kernels: every latent dimension of the weights is zero-padded to 128 when they are packed, and
+   * LayerNorm divides by this width (the padding columns are exactly zero throughout). */
+  int32_t latent;
 } lb200_gns_cfg;
 
 /* device scratch the forward needs, in bytes (node latents, projections, edge latents ...) */

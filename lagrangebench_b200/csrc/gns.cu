@@ -118,22 +118,25 @@ __device__ __forceinline__ float half_warp_sum(float v) {
 }
 
 // hk.LayerNorm(axis=-1): (scale * rsqrt(var + 1e-5)) * (x - mean) + offset, biased variance
+// `latent` <= 128 is the model's true width: columns beyond it are zero padding (zero weights, scale, offset),
+// which adds nothing to the sum and (128 - latent) * mean^2 to the sum of squared deviations.
 __device__ __forceinline__ void layer_norm_rows(float (&y)[4][8], const float* __restrict__ scale,
-                                                const float* __restrict__ offset) {
+                                                const float* __restrict__ offset, int latent) {
   const int tx = threadIdx.x & 15;
+  const float inv_n = 1.0f / (float)latent, n_pad = (float)(kLatent - latent);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) s += y[i][j];
-    const float mean = half_warp_sum(s) * (1.0f / kLatent);
+    const float mean = half_warp_sum(s) * inv_n;
     float v = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float d = y[i][j] - mean;
       v = fmaf(d, d, v);
     }
-    const float var = half_warp_sum(v) * (1.0f / kLatent);
+    const float var = fmaxf(half_warp_sum(v) - n_pad * mean * mean, 0.f) * inv_n;
     const float inv = 1.0f / sqrtf(var + 1e-5f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -201,7 +204,7 @@ __device__ __forceinline__ void project_next(const float* hs, int lda, const Mlp
 
 // ------------------------------------------------------------------ node encoder
 struct NodeEncArgs {
-  int n, node_in, node_stride, embed, n_types;
+  int n, node_in, node_stride, embed, n_types, latent;
   const float* node_feat;
   const int32_t* ptype;
   const float* embedding;
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_encoder_kernel(NodeEncArgs a
   zero_acc(acc);
   gemm_tile<kLatent>(acc, Hs, kLdA, a.enc.w1, ws);
   add_bias(acc, a.enc.b1, false);
-  layer_norm_rows(acc, a.enc.lns, a.enc.lno);
+  layer_norm_rows(acc, a.enc.lns, a.enc.lno, a.latent);
   store_tile_global(acc, a.h, row0, rows, kLatent, 0);
   store_tile_smem(acc, Hs, kLdA);  // gemm_tile ended with a barrier: Hs is free
   __syncthreads();
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_encoder_kernel(NodeEncArgs a
 
 // ------------------------------------------------------------------ edge encoder
 struct EdgeEncArgs {
-  int n;
+  int n, latent;
   const int32_t* rowptr;  // rowptr[n] = number of real edges
   const int32_t* perm;
   const float4* edge_feat;  // LIST order
@@ -295,13 +298,13 @@ __global__ void __launch_bounds__(kThreads, 2) edge_encoder_kernel(EdgeEncArgs a
   zero_acc(acc);
   gemm_tile<kLatent>(acc, Hs, kLdA, a.enc.w1, ws);
   add_bias(acc, a.enc.b1, false);
-  layer_norm_rows(acc, a.enc.lns, a.enc.lno);
+  layer_norm_rows(acc, a.enc.lns, a.enc.lno, a.latent);
   store_tile_global(acc, a.e, slot0, rows, kLatent, 0);
 }
 
 // ------------------------------------------------------------------ message passing: edges
 struct EdgeMpArgs {
-  int n;
+  int n, latent;
   const int32_t *rowptr, *snd, *rcv;
   const float* P;  // [n][256]
   MlpW mlp;        // w0 = (384,128): rows 256..383 act on the edge latent; b0 is folded into P
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 2) edge_mp_kernel(EdgeMpArgs a) {
   zero_acc(acc);
   gemm_tile<kLatent>(acc, A2, kLdA, a.mlp.w1, ws);
   add_bias(acc, a.mlp.b1, false);
-  layer_norm_rows(acc, a.mlp.lns, a.mlp.lno);
+  layer_norm_rows(acc, a.mlp.lns, a.mlp.lno, a.latent);
   store_tile_smem(acc, A2, kLdA);  // e' (the message), for the column-wise segmented sum
   // residual: e <- e' + e (gns.py:120-122)
 #pragma unroll
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, 2) edge_mp_kernel(EdgeMpArgs a) {
 
 // ------------------------------------------------------------------ message passing: nodes
 struct NodeMpArgs {
-  int n, dim, last;
+  int n, dim, last, latent;
   const int32_t* rowptr;
   const float *agg, *carry_first, *carry_last;
   MlpW mlp;  // w0 = (256,128): rows 0..127 act on h, 128..255 on the aggregate
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_mp_kernel(NodeMpArgs a) {
   zero_acc(acc);
   gemm_tile<kLatent>(acc, As + kLatent, lda, a.mlp.w1, ws);
   add_bias(acc, a.mlp.b1, false);
-  layer_norm_rows(acc, a.mlp.lns, a.mlp.lno);
+  layer_norm_rows(acc, a.mlp.lns, a.mlp.lno, a.latent);
   // residual: h <- n' + h (gns.py:120-122); each thread owns its (row, col) elements of As
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -592,7 +595,8 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   if (!c || !weights_dev || !node_feat_dev || !edge_feat_dev || !ptype_dev || !rowptr_dev ||
       !snd_dev || !rcv_dev || !out_dev || !scratch_dev)
     return LB200_EINVAL;
-  if (c->num_mp_steps < 1 || c->node_in + c->embed_size > kEncK || (c->dim != 2 && c->dim != 3) || c->e_cap < 1)
+  if (c->num_mp_steps < 1 || c->node_in + c->embed_size > kEncK || (c->dim != 2 && c->dim != 3) || c->e_cap < 1 ||
+      c->latent < 0 || c->latent > kLatent)
     return LB200_EUNSUPPORTED;
   int rc = set_smem_once();
   if (rc) return rc;
@@ -610,6 +614,8 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   float* cl = ar.take<float>((int64_t)(n_sub + 1) * kLatent);
   if (!ar.ok()) return LB200_EINVAL;
   const float* w = weights_dev;
+  const int latent = c->latent > 0 ? c->latent : kLatent;  // the model's true width; beyond it: zero padding
+  const float inv_latent = 1.0f / (float)latent;
   // Decomposed cloud: the projections live in the peer heap, two arrays alternating by message-passing
   // step (a neighbour's store for step m + 1 can then never race this rank's message kernel of step m);
   // exchange 0 of a step is the ghost positions (rollout.cu), exchanges 1 .. num_mp_steps the projections.
@@ -625,6 +631,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     na.push_left = na.push_right = nullptr;
     na.dst_left = na.dst_right = 0;
     na.flag = c->nonfinite_flag;
+    na.inv_latent = inv_latent;
     if (sh == nullptr) return;
     if (sh->has_left && sh->n_send_left > 0) {
       na.P_left = shard_p_left(sh, m_out);
@@ -640,6 +647,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
 
   NodeEncArgs ne;
   ne.n = n_own;
+  ne.latent = latent;
   ne.node_in = c->node_in;
   ne.node_stride = c->node_stride;
   ne.embed = c->embed_size;
@@ -683,6 +691,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       c->enc_edge.b0 == c->enc_edge.w0 + 4 * kLatent) {
     EdgeTcArgs et;
     et.n = n_own;
+    et.inv_latent = inv_latent;
     et.rowptr = rowptr_dev;
     et.snd = snd_dev;
     et.rcv = rcv_dev;
@@ -702,6 +711,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   } else {
     EdgeEncArgs ee;
     ee.n = n_own;
+    ee.latent = latent;
     ee.rowptr = rowptr_dev;
     ee.perm = perm_dev;
     ee.edge_feat = reinterpret_cast<const float4*>(edge_feat_dev);
@@ -716,6 +726,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     if (c->edge_impl != 1 && eo.tc_w >= 0 && eo.tc_vec >= 0) {
       EdgeTcArgs et;
       et.n = n_own;
+      et.inv_latent = inv_latent;
       et.rowptr = rowptr_dev;
       et.snd = snd_dev;
       et.rcv = rcv_dev;
@@ -735,6 +746,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     } else {
       EdgeMpArgs em;
       em.n = n_own;
+      em.latent = latent;
       em.rowptr = rowptr_dev;
       em.snd = snd_dev;
       em.rcv = rcv_dev;
@@ -773,6 +785,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     } else {
       NodeMpArgs nm;
       nm.n = n_own;
+      nm.latent = latent;
       nm.dim = c->dim;
       nm.last = last;
       nm.rowptr = rowptr_dev;

@@ -7,6 +7,7 @@ namespace lb {
 
 struct EdgeTcArgs {
   int n;
+  float inv_latent;  // 1 / (the model's true latent width <= 128): LayerNorm's divisor (columns beyond it are zero padding)
   const int32_t *rowptr, *snd, *rcv;
   const float* P;       // [n][256] per-node projections (sender half | receiver half + b1)
   const void* w_tc;     // W1e^T hi, lo, W2c^T hi, lo: four 128x128 fp16 operands in UMMA K-major layout
@@ -42,6 +43,7 @@ struct NodeTcArgs {
   const int32_t *push_left, *push_right;
   int dst_left, dst_right;
   int32_t* flag;  // OR-ed with 1 when a decoded output is NaN / Inf (or NULL)
+  float inv_latent;  // as EdgeTcArgs
 };
 
 int launch_node_mp_tc(const NodeTcArgs& a, cudaStream_t s);

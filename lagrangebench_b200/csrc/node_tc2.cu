@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
       red[q * 32 + lane] = part;
       asm volatile("bar.sync %0, %1;" ::"r"(bar_ln), "n"(kN2WThreads) : "memory");
       {
-        const float var = (red[lane] + red[32 + lane] + red[64 + lane] + red[96 + lane]) * (1.0f / kLatent);
+        const float var = (red[lane] + red[32 + lane] + red[64 + lane] + red[96 + lane]) * a.inv_latent;
         invs[lane] = 1.0f / sqrtf(var + 1e-5f);
       }
       __syncwarp();

@@ -72,7 +72,7 @@ def fp16_range_bounds(params, num_mp_steps, latent=128):
 class PackedParams:
     """One contiguous float32 device blob + the offset table ``lb200_gns_cfg`` expects."""
 
-    fp16_safe, fp16_report = True, ""
+    fp16_safe, fp16_report, latent = True, "", _cabi.LATENT
 
     def __init__(self, blob, embedding, enc_node, enc_edge, dec, proc_edge, proc_node, node_in_total, embed_size,
                  num_types, dim, num_mp_steps):
@@ -84,13 +84,71 @@ class PackedParams:
         self.embed_size, self.num_types, self.dim, self.num_mp_steps = embed_size, num_types, dim, num_mp_steps
 
 
-def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
+def _pad_latent(params, num_mp_steps, width, latent):
+    """A GNS of latent width ``width`` < 128 as the same function on 128-wide arrays: every latent dimension
+    of every matrix / vector is zero-padded (block by block where a matrix acts on a concatenation,
+    ``gns.py:97-100,109-111``).  The padding columns stay exactly zero through ReLU, LayerNorm (scale and
+    offset padded with zeros; the kernels divide by the true width) and the residuals."""
+    pad = latent - width
+
+    def cols(a):
+        a = np.asarray(a, dtype=np.float32)
+        return np.concatenate([a, np.zeros(a.shape[:-1] + (pad,), np.float32)], axis=-1)
+
+    def row_blocks(w, n_blocks):
+        w = np.asarray(w, dtype=np.float32)
+        parts = np.split(w, n_blocks, axis=0)
+        return np.concatenate([np.concatenate([b, np.zeros((pad, w.shape[1]), np.float32)], axis=0) for b in parts])
+
+    out = {k: dict(v) for k, v in params.items()}
+
+    def fix(scope, idx, in_blocks, latent_out=True, ln=True):
+        sfx = "" if idx == 0 else f"_{idx}"
+        k0 = [k for k in out if k.endswith(f"{scope}/MLP{sfx}/~/linear_0")][0]
+        k1 = [k for k in out if k.endswith(f"{scope}/MLP{sfx}/~/linear_1")][0]
+        w0 = out[k0]["w"] if in_blocks == 0 else row_blocks(out[k0]["w"], in_blocks)
+        out[k0] = {"w": cols(w0), "b": cols(out[k0]["b"])}
+        w1 = row_blocks(out[k1]["w"], 1)
+        out[k1] = {"w": cols(w1), "b": cols(out[k1]["b"])} if latent_out else {"w": w1, "b": np.asarray(out[k1]["b"], np.float32)}
+        if ln:
+            kl = [k for k in out if k.endswith(f"{scope}/layer_norm{sfx}")][0]
+            out[kl] = {"scale": cols(out[kl]["scale"]), "offset": cols(out[kl]["offset"])}
+
+    fix("_encoder", 0, 0)
+    fix("_encoder", 1, 0)
+    for m in range(num_mp_steps):
+        fix("_processor", 2 * m, 3)
+        fix("_processor", 2 * m + 1, 2)
+    fix("_decoder", 0, 1, latent_out=False, ln=False)
+    return out
+
+
+def pack_params(params, num_mp_steps, dim, latent=None, device="cuda"):
     """haiku params -> :class:`PackedParams`.  Matrices stay row-major ``(in, out)`` as
     ``hk.Linear`` stores them; the node-encoder input matrix is zero-padded to
-    ``LB200_MAX_NODE_IN`` rows and the edge-encoder one to 4 rows."""
-    if latent != _cabi.LATENT:
-        raise NotImplementedError(f"kernels are specialised for latent_dim={_cabi.LATENT}")
+    ``LB200_MAX_NODE_IN`` rows and the edge-encoder one to 4 rows.  ``latent`` < 128 (the published
+    GNS-5-64): the model is zero-padded to the kernels' width (``_pad_latent``)."""
+    if latent is None:  # the width the parameters themselves have
+        latent = np.asarray(_mlp_modules(params, "_encoder", 0)[1]["w"]).shape[1]
+    width = int(latent)
+    if not 0 < width <= _cabi.LATENT:
+        raise NotImplementedError(f"kernels cover latent sizes up to {_cabi.LATENT}")
+    latent = _cabi.LATENT
+    bounds_params = params
+    if width < latent:
+        params = _pad_latent(params, num_mp_steps, width, latent)
     chunks, cursor = [], [0]
+
+    def row_mean(w):
+        """Mean of a second-layer matrix over its REAL output columns (LayerNorm's mean, folded into the weights)."""
+        return w[:, :width].sum(axis=1, keepdims=True) / width
+
+    def centered(w, b):
+        wc = w - row_mean(w)
+        bc = b - b[:width].sum() / width
+        wc[:, width:] = 0.0
+        bc[width:] = 0.0
+        return wc, bc
 
     def put(arr, rows_pad=None):
         a = np.asarray(arr, dtype=np.float32)
@@ -120,10 +178,8 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
         """Tensor-core operands of a processor edge MLP (include/lb200.h, lb200_mlp_off.tc_*)."""
         l0, l1, ln = mods
         w1e_t = np.asarray(l0["w"], dtype=np.float32)[2 * latent:3 * latent].T  # (f, k)
-        w2 = np.asarray(l1["w"], dtype=np.float64)
-        b2 = np.asarray(l1["b"], dtype=np.float64)
-        w2c_t = (w2 - w2.mean(axis=1, keepdims=True)).astype(np.float32).T  # LayerNorm mean folded in
-        b2c = (b2 - b2.mean()).astype(np.float32)
+        w2c, b2c = centered(np.array(l1["w"], dtype=np.float64), np.array(l1["b"], dtype=np.float64))
+        w2c_t, b2c = w2c.astype(np.float32).T, b2c.astype(np.float32)  # LayerNorm mean folded in
         h1, l1_ = umma_operand(w1e_t)
         h2, l2_ = umma_operand(w2c_t)
         halves = np.concatenate([h1, l1_, h2, l2_])
@@ -133,11 +189,10 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
     def put_tc_encoder(mods, o):
         """Tensor-core operands of the edge encoder's second layer: W1c^T hi|lo, b1c|scale|offset."""
         _, l1, ln = mods
-        w = np.asarray(l1["w"], dtype=np.float64)
-        b = np.asarray(l1["b"], dtype=np.float64)
-        hi, lo = umma_operand((w - w.mean(axis=1, keepdims=True)).astype(np.float32).T)
+        wc, bc = centered(np.array(l1["w"], dtype=np.float64), np.array(l1["b"], dtype=np.float64))
+        hi, lo = umma_operand(wc.astype(np.float32).T)
         o.tc_w = put(np.concatenate([hi, lo]).view(np.float32))
-        o.tc_vec = put(np.concatenate([(b - b.mean()).astype(np.float32), np.asarray(ln["scale"], np.float32),
+        o.tc_vec = put(np.concatenate([bc.astype(np.float32), np.asarray(ln["scale"], np.float32),
                                        np.asarray(ln["offset"], np.float32)]))
 
     def put_tc_node(mods, nxt_l0, o, last):
@@ -147,10 +202,8 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
         b1 | b2c | ln_scale | ln_offset | b_next | wd1[128][3] | bd1[4] (csrc/gns_tc.cu)."""
         l0, l1, ln = mods
         w1 = np.asarray(l0["w"], dtype=np.float32)
-        w2 = np.asarray(l1["w"], dtype=np.float64)
-        b2 = np.asarray(l1["b"], dtype=np.float64)
-        w2c_t = (w2 - w2.mean(axis=1, keepdims=True)).astype(np.float32).T
-        b2c = (b2 - b2.mean()).astype(np.float32)
+        w2c, b2c = centered(np.array(l1["w"], dtype=np.float64), np.array(l1["b"], dtype=np.float64))
+        w2c_t, b2c = w2c.astype(np.float32).T, b2c.astype(np.float32)
         wn = np.asarray(nxt_l0["w"], dtype=np.float32)
         mats = [w1[:latent].T, w1[latent:2 * latent].T, w2c_t, wn[:latent].T]
         if not last:
@@ -179,10 +232,8 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
         w0 = np.asarray(l0["w"], dtype=np.float32)
         w0pad = np.zeros((latent, latent), np.float32)
         w0pad[:w0.shape[0]] = w0
-        w1 = np.asarray(l1["w"], dtype=np.float64)
-        b1 = np.asarray(l1["b"], dtype=np.float64)
-        w1c_t = (w1 - w1.mean(axis=1, keepdims=True)).astype(np.float32).T
-        b1c = (b1 - b1.mean()).astype(np.float32)
+        w1c, b1c = centered(np.array(l1["w"], dtype=np.float64), np.array(l1["b"], dtype=np.float64))
+        w1c_t, b1c = w1c.astype(np.float32).T, b1c.astype(np.float32)
         wn = np.asarray(nxt_l0["w"], dtype=np.float32)
         halves = []
         for m in (w0pad.T, w1c_t, wn[:latent].T, wn[latent:2 * latent].T):
@@ -247,7 +298,8 @@ def pack_params(params, num_mp_steps, dim, latent=_cabi.LATENT, device="cuda"):
     blob = torch.from_numpy(np.concatenate(chunks)).to(device)
     pk = PackedParams(blob, embedding, enc_node, enc_edge, dec, proc_edge, proc_node, node_in_total, embed_size,
                       num_types, dim, num_mp_steps)
-    over = {k: v for k, v in fp16_range_bounds(params, num_mp_steps, latent).items() if not v <= FP16_MAX}
+    pk.latent = width
+    over = {k: v for k, v in fp16_range_bounds(bounds_params, num_mp_steps, width).items() if not v <= FP16_MAX}
     if over:
         pk.fp16_safe = False
         pk.fp16_report = ", ".join(f"{k} <= {v:.3g}" for k, v in over.items())
@@ -274,6 +326,7 @@ def gns_cfg(packed, n, e_cap, node_in, node_stride, edge_impl="tc"):
         edge_impl = "simt"
     c.edge_impl = EDGE_IMPL[edge_impl]
     c.n, c.dim, c.num_mp_steps = n, packed.dim, packed.num_mp_steps
+    c.latent = packed.latent
     c.node_in, c.node_stride = node_in, node_stride
     c.embed_size, c.num_particle_types = packed.embed_size, packed.num_types
     c.e_cap = e_cap
@@ -330,8 +383,8 @@ class GNS:
 
     def __init__(self, particle_dimension, latent_size, blocks_per_step, num_mp_steps,
                  particle_type_embedding_size, num_particle_types=int(NodeType.SIZE)):
-        if latent_size != _cabi.LATENT:
-            raise NotImplementedError(f"kernels are specialised for latent_size={_cabi.LATENT}")
+        if not 0 < latent_size <= _cabi.LATENT:
+            raise NotImplementedError(f"kernels cover latent_size up to {_cabi.LATENT} (narrower models are zero-padded)")
         if blocks_per_step != 2:
             raise NotImplementedError("kernels are specialised for 2-layer MLPs (num_mlp_layers=2)")
         self._output_size = int(particle_dimension)

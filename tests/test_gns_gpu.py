@@ -113,6 +113,28 @@ def test_fp16_split_range_is_guarded():
     assert rel_err(out_s["acc"].cpu().numpy(), ref_s) <= TOL
 
 
+@pytest.mark.parametrize("latent,mp", [(64, 5), (96, 2)])
+def test_narrower_latent_sizes_run_zero_padded(latent, mp):
+    """``GNS(latent_size=64, num_mp_steps=5)`` is the reference's published GNS-5-64 (``baselines.rst:55``): it runs
+    on the 128-wide kernels, every latent dimension zero-padded and LayerNorm dividing by the true width, on the
+    tensor-core path and on the float32 CUDA-core path."""
+    c, ours, orac = build_pair("rpf2d", "float32")
+    sample = (c["positions"], c["particle_type"])
+    f_gpu, _ = ours.allocate_eval(sample)
+    f_cpu, _ = orac.allocate_eval(sample)
+    params = ogns.init_params(12, 3, 2, latent=latent, num_mp_steps=mp, seed=4, perturb=True)
+    ref = ogns.forward(params, f_cpu, c["particle_type"], mp, np.float64)["acc"]
+    for impl in ("tc", "simt"):
+        model = GNS(2, latent, 2, mp, 16)
+        model.edge_impl = impl
+        out, _ = model.apply(params, {}, (f_gpu, c["particle_type"]))
+        err = rel_err(out["acc"].cpu().numpy(), ref)
+        print(f"latent {latent}, {mp} MP steps, {impl}: rel err {err:.2e}")
+        assert err <= TOL
+    with pytest.raises(NotImplementedError):
+        GNS(2, 256, 2, mp, 16)
+
+
 def test_forward_single_mp_step_and_type_embedding():
     """One message-passing step; particle types other than FLUID exercise the embedding."""
     got, ref64, _, _ = _forward_both("ldc3d", "float32", num_mp_steps=1)

