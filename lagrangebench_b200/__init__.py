@@ -13,6 +13,7 @@ from .data import H5Dataset  # noqa: F401
 from .defaults import defaults  # noqa: F401
 from .evaluate import MetricsComputer, RolloutEngine, averaged_metrics, eval_rollout, infer  # noqa: F401
 from .models import GNS  # noqa: F401
+from .strats import push_forward_build  # noqa: F401
 from .utils import NodeType, get_kinematic_mask  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -214,3 +214,28 @@ def test_infer_from_an_hdf5_dataset_with_saved_checkpoint(tmp_path):
     for k in ("rollout_0", "rollout_1"):
         a, b = torch.as_tensor(from_files[k]["mse"]).cpu(), torch.as_tensor(from_memory[k]["mse"]).cpu()
         assert a.shape == (n_steps,) and torch.equal(a, b)
+
+
+def test_push_forward_unroll_reuses_the_rollout_path():
+    """``train/strats.py:137-159``: the forward-only unroll of the pushforward trick is one rollout step --
+    model forward, integrate, window shift, neighbor / feature update -- checked against the oracle's."""
+    from lagrangebench_b200 import push_forward_build
+    from oracle import gns as ogns
+
+    c, ours, orac, params, model, _ = _setup("rpf2d", "float64", 0)
+    ptype = c["particle_type"]
+    cur_g = torch.as_tensor(c["positions"][:, :6]).cuda()
+    cur_c = c["positions"][:, :6].copy()
+    f_g, n_g = ours.allocate_eval((cur_g, ptype))
+    f_c, n_c = orac.allocate_eval((cur_c, ptype))
+    pf = push_forward_build(model.apply, ours)
+    for _ in range(2):
+        cur_g, n_g, f_g = pf(f_g, cur_g, ptype, n_g, params, {})
+        f32 = {k: (np.asarray(v).astype(np.float32) if np.asarray(v).dtype.kind == "f" else v) for k, v in f_c.items()}
+        pred = ogns.forward(params, f32, ptype, model._mp_steps, np.float32)
+        nxt = orac.integrate(pred, cur_c)
+        cur_c = np.concatenate([cur_c[:, 1:], nxt[:, None]], axis=1)
+        f_c, n_c = orac.preprocess_eval((cur_c, ptype), n_c)
+    assert cur_g.shape == cur_c.shape and np.abs(cur_g.cpu().numpy() - cur_c).max() <= 1e-9
+    assert np.array_equal(n_g.idx.cpu().numpy(), n_c.idx)
+    assert np.allclose(f_g["vel_hist"].cpu().numpy(), f_c["vel_hist"], atol=1e-4)
