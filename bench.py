@@ -433,31 +433,29 @@ def run_ours(args):
     _cabi.check(lib.lb200_profile_read(kms, kl))
     lib.lb200_profile(0)
 
-    # end-to-end leg: the same steps through the public per-step API with HOST buffers --
-    # every step uploads that step's kinematic-target frame from pinned memory and reads the
-    # predicted positions back (one host synchronisation per step, as the reference loop has)
+    # end-to-end leg: the same steps through the public per-step API with HOST buffers -- every step is one
+    # RolloutEngine.run(...) call that uploads that step's kinematic-target frame from pinned memory, advances
+    # one step and reads the predicted positions back into pinned memory: one host synchronisation per step
+    # (as the reference loop has), which covers upload, step, read-back and status
     esz = 8 if args.dtype == "float64" else 4
     h_targets = torch.as_tensor(spec["positions"][:, 6:6 + K + W]).permute(1, 0, 2).to(tdt).contiguous().pin_memory()
-    h_out = torch.empty((n, d), dtype=tdt).pin_memory()
-    d_tgt = torch.empty((1, n, d), dtype=tdt, device=dev)
+    h_out = torch.empty((1, n, d), dtype=tdt).pin_memory()
+    d_out = torch.empty((1, n, d), dtype=tdt, device=dev)
     window_e = torch.as_tensor(spec["positions"][:, :6]).to(dev, tdt).contiguous()
     engine_e = RolloutEngine(case, model, params, steps_per_sync=1)
     nb_e = None
-    for t in range(min(W, 3) + 4):  # untimed: also lets the per-step graphs (two alternating output buffers) be captured
-        d_tgt[0].copy_(h_targets[t], non_blocking=True)
-        p, nb_e = engine_e.run(window_e, ptype, d_tgt, 1, nb_e)
-        h_out.copy_(p[0], non_blocking=True)
+    for t in range(min(W, 3) + 4):  # untimed: also lets the per-step graph be captured
+        _, nb_e = engine_e.run(window_e, ptype, h_targets[t:t + 1], 1, nb_e, out=d_out, host_out=h_out)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for t in range(K):
-        d_tgt[0].copy_(h_targets[W + t], non_blocking=True)
-        p, nb_e = engine_e.run(window_e, ptype, d_tgt, 1, nb_e)
-        h_out.copy_(p[0], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        _, nb_e = engine_e.run(window_e, ptype, h_targets[W + t:W + t + 1], 1, nb_e, out=d_out, host_out=h_out)
+    torch.cuda.current_stream().synchronize()
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    assert torch.isfinite(h_out).all()
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)

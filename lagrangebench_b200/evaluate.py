@@ -108,6 +108,8 @@ class RolloutEngine:
         self._stream = None  # non-default stream: lets lb200_rollout_steps replay steps from a CUDA graph
         # persistent small buffers: stable device pointers let the library reuse its captured graph
         self._status = None
+        self._status_host = None
+        self._target_buf = None
         self._ptype = (None, None, 0)  # (source, int32 device copy, number of real particles)
         self.n_reallocations = 0
         self.n_launch_calls = 0
@@ -133,30 +135,33 @@ class RolloutEngine:
             self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=neighbors.reference_position.device)
         self._cfg, self._cfg_key, self._grid_ref = cfg, key, neighbors._grid
 
-    def run(self, window, particle_type, targets, n_steps, neighbors=None, out=None):
+    def run(self, window, particle_type, targets, n_steps, neighbors=None, out=None, host_out=None):
         """Advance ``window`` (N, isl, d) in place by ``n_steps``.
 
-        ``targets`` (n_steps, N, d) or None supplies the positions of kinematic particles.
+        ``targets`` (n_steps, N, d) or None supplies the positions of kinematic particles; a HOST tensor
+        (pinned for an asynchronous copy) is uploaded on the engine's stream in front of the steps.
         ``out``: optional preallocated ``(n_steps, N, d)`` tensor for the predictions (a caller that
         repeats a call with the very same buffers lets the library replay its captured step graph
-        from the first step on).  Returns ``(predictions (n_steps, N, d), neighbors)``; the returned
+        from the first step on).  ``host_out``: optional pinned host tensor of that shape; every chunk's
+        predictions are copied into it behind the steps, so that the chunk's one synchronisation covers
+        upload, steps, read-back and status.  Returns ``(predictions (n_steps, N, d), neighbors)``; the returned
         list carries the capacities and builds its ``idx`` array on first access (the step loop
         itself works on the receiver-major view of the graph)."""
-        job = self.start(window, particle_type, targets, n_steps, neighbors, out)
+        job = self.start(window, particle_type, targets, n_steps, neighbors, out, host_out)
         while not job.finished:
             job.enqueue()
             job.collect()
         return job.result()
 
-    def start(self, window, particle_type, targets, n_steps, neighbors=None, out=None):
+    def start(self, window, particle_type, targets, n_steps, neighbors=None, out=None, host_out=None):
         """A rollout as a job: ``enqueue()`` puts the next chunk of steps on this engine's stream without
         waiting, ``collect()`` reads the chunk's status (the host synchronisation).  Several engines can
         have their chunks in flight at once (``run_batched``)."""
-        return _RolloutJob(self, window, particle_type, targets, n_steps, neighbors, out)
+        return _RolloutJob(self, window, particle_type, targets, n_steps, neighbors, out, host_out)
 
 
 class _RolloutJob:
-    def __init__(self, engine, window, particle_type, targets, n_steps, neighbors, out):
+    def __init__(self, engine, window, particle_type, targets, n_steps, neighbors, out, host_out=None):
         self.engine = eng = engine
         h = eng.h
         assert window.is_cuda and window.is_contiguous() and window.dtype == h["dtype"]
@@ -181,13 +186,26 @@ class _RolloutJob:
             preds = out
         else:
             preds = torch.empty((n_steps, n, dim), dtype=window.dtype, device=dev)
-        if targets is not None:
-            targets = targets.to(dev, window.dtype).contiguous()
-            assert targets.shape == (n_steps, n, dim)
         if eng._status is None or eng._status.device != dev:
             eng._status = torch.zeros(4, dtype=torch.int32, device=dev)
+            eng._status_host = torch.zeros(4, dtype=torch.int32).pin_memory()
         if eng._stream is None:
             eng._stream = torch.cuda.Stream(device=dev)
+        self.upload = None
+        if targets is not None:
+            targets = torch.as_tensor(targets)
+            assert tuple(targets.shape) == (n_steps, n, dim)
+            if not targets.is_cuda:  # host frames: uploaded on the engine's stream, into a buffer the step graph keeps seeing
+                buf = eng._target_buf
+                if buf is None or buf.shape != targets.shape or buf.dtype != window.dtype or buf.device != dev:
+                    buf = eng._target_buf = torch.empty(targets.shape, dtype=window.dtype, device=dev)
+                self.upload = targets if targets.dtype == window.dtype else targets.to(window.dtype)
+                targets = buf
+            else:
+                targets = targets.to(dev, window.dtype).contiguous()
+        if host_out is not None:
+            assert not host_out.is_cuda and tuple(host_out.shape) == (n_steps, n, dim) and host_out.dtype == window.dtype
+        self.host_out = host_out
         self.window, self.ptype, self.n_valid, self.targets, self.preds = window, ptype, n_valid, targets, preds
         self.neighbors, self.n_steps, self.done, self.n_edges = neighbors, n_steps, 0, 0
         self.dev = dev
@@ -201,18 +219,26 @@ class _RolloutJob:
         chunk = min(eng.steps_per_sync, self.n_steps - self.done)
         eng._stream.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(eng._stream):
+            if self.upload is not None:
+                self.targets.copy_(self.upload, non_blocking=True)
+                self.upload = None
             # base pointers + first frame: every chunk of a long rollout replays the same cached step graph;
             # status is reset on the device at the start of every lb200_rollout_steps call
             _cabi.check(lib.lb200_rollout_steps(
                 C.byref(eng._cfg), chunk, _cabi.ptr(eng.packed.blob), _cabi.ptr(self.window), _cabi.ptr(self.ptype), None,
                 _cabi.ptr(self.targets), _cabi.ptr(self.preds), self.done, None, _cabi.ptr(eng._status),
                 _cabi.ptr(eng._scratch), eng._scratch.numel(), _cabi.stream()))
+            if self.host_out is not None:  # read-back behind the steps (rows of a step that did not complete are rewritten)
+                sl = slice(self.done, self.done + chunk)
+                self.host_out[sl].copy_(self.preds[sl], non_blocking=True)
+            eng._status_host.copy_(eng._status, non_blocking=True)
         eng.n_launch_calls += 1
 
     def collect(self):
         eng = self.engine
+        eng._stream.synchronize()  # the one host sync per chunk: upload, steps, read-back, status
         torch.cuda.current_stream(self.dev).wait_stream(eng._stream)
-        completed, overflow, n_edges, _ = eng._status.tolist()  # the one host sync per chunk
+        completed, overflow, n_edges, _ = eng._status_host.tolist()
         self.done += completed
         self.n_edges = n_edges
         if overflow & _cabi.ERR_NONFINITE:

@@ -239,3 +239,25 @@ def test_push_forward_unroll_reuses_the_rollout_path():
     assert cur_g.shape == cur_c.shape and np.abs(cur_g.cpu().numpy() - cur_c).max() <= 1e-9
     assert np.array_equal(n_g.idx.cpu().numpy(), n_c.idx)
     assert np.allclose(f_g["vel_hist"].cpu().numpy(), f_c["vel_hist"], atol=1e-4)
+
+
+def test_host_buffer_mode_equals_device_buffers():
+    """``run(..., targets=<pinned host tensor>, host_out=<pinned host tensor>)``: upload, steps and read-back ride
+    on the engine's stream behind one synchronisation per chunk; same numbers as with device tensors."""
+    n_steps = 5
+    c, ours, _, params, model, _ = _setup("ldc3d", "float64", n_steps)
+    targets = torch.as_tensor(c["positions"][:, 6:6 + n_steps]).permute(1, 0, 2).contiguous()
+    w_dev = torch.as_tensor(c["positions"][:, :6]).cuda().contiguous()
+    ref, _ = RolloutEngine(ours, model, params).run(w_dev, c["particle_type"], targets.cuda(), n_steps)
+    h_targets, h_out = targets.pin_memory(), torch.empty_like(targets).pin_memory()
+    w_host = torch.as_tensor(c["positions"][:, :6]).cuda().contiguous()
+    eng = RolloutEngine(ours, model, params, steps_per_sync=2)
+    got, _ = eng.run(w_host, c["particle_type"], h_targets, n_steps, host_out=h_out)
+    assert torch.equal(got, ref) and torch.equal(h_out.cuda(), ref) and torch.equal(w_host, w_dev)
+    # per-step calls with one-frame host buffers (bench.py's e2e leg)
+    w_step = torch.as_tensor(c["positions"][:, :6]).cuda().contiguous()
+    eng1 = RolloutEngine(ours, model, params, steps_per_sync=1)
+    d_out, h1, nb = torch.empty_like(ref[:1]), torch.empty_like(targets[:1]).pin_memory(), None
+    for t in range(n_steps):
+        _, nb = eng1.run(w_step, c["particle_type"], h_targets[t:t + 1], 1, nb, out=d_out, host_out=h1)
+        assert torch.equal(h1.cuda(), ref[t:t + 1])
