@@ -153,6 +153,11 @@ typedef struct {
   double force_threshold;    /* pos[axis] > threshold ? force_hi : force_lo */
   double force_lo[3], force_hi[3];
   int32_t node_stride;       /* floats per node_feat row (>= number of feature columns) */
+  /* optional: append the particle-type embedding (gns.py:61-63,141-145) behind the feature columns, i.e. write
+   * the node encoder's whole input row [features | Embed(ptype) | 0 ...] (embed_size = 0: features only) */
+  int32_t embed_size, num_particle_types;
+  const float* embedding_dev;  /* dev float[num_particle_types][embed_size] */
+  const int32_t* ptype_dev;    /* dev int32[n] */
 } lb200_feature_cfg;
 
 int32_t lb200_node_feature_width(const lb200_feature_cfg* c);
@@ -243,6 +248,10 @@ typedef struct {
   const struct lb200_shard_s* shard;
   /* dev int32* or NULL: OR-ed with 1 when an output acceleration is NaN / Inf (see LB200_ERR_NONFINITE) */
   int32_t* nonfinite_flag;
+  /* 1: rows [0, n_owned) of h (lb200_gns_scratch_layout) already hold the encoder's input rows
+   * [features | Embed(ptype) | 0 ...] (lb200_features with embed_size > 0 and node_stride = 128); node_feat_dev is
+   * not read.  Tensor-core path only. */
+  int32_t node_inputs_in_h;
   /* the model's latent width (gns.py:37 latent_size), 0 = 128.  Narrower models (the published GNS-5-64) run on the
    * 128-wide kernels: every latent dimension of the weights is zero-padded to 128 when they are packed, and
    * LayerNorm divides by this width (the padding columns are exactly zero throughout). */

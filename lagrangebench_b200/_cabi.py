@@ -33,7 +33,9 @@ class FeatureCfg(C.Structure):
                 ("magnitude_features", C.c_int32), ("bound_features", C.c_int32),
                 ("bounds_lo", C.c_double * 3), ("bounds_hi", C.c_double * 3),
                 ("force_mode", C.c_int32), ("force_axis", C.c_int32), ("force_threshold", C.c_double),
-                ("force_lo", C.c_double * 3), ("force_hi", C.c_double * 3), ("node_stride", C.c_int32)]
+                ("force_lo", C.c_double * 3), ("force_hi", C.c_double * 3), ("node_stride", C.c_int32),
+                ("embed_size", C.c_int32), ("num_particle_types", C.c_int32), ("embedding_dev", C.c_void_p),
+                ("ptype_dev", C.c_void_p)]
 
 
 class MlpOff(C.Structure):
@@ -47,7 +49,7 @@ class GnsCfg(C.Structure):
                 ("e_cap", C.c_int32), ("embedding", C.c_int64), ("enc_node", MlpOff), ("enc_edge", MlpOff),
                 ("dec", MlpOff), ("proc_edge", C.POINTER(MlpOff)), ("proc_node", C.POINTER(MlpOff)),
                 ("edge_impl", C.c_int32), ("n_owned", C.c_int32), ("shard", C.c_void_p),
-                ("nonfinite_flag", C.c_void_p), ("latent", C.c_int32)]
+                ("nonfinite_flag", C.c_void_p), ("node_inputs_in_h", C.c_int32), ("latent", C.c_int32)]
 
 
 MAX_RANKS = 16

@@ -10,7 +10,9 @@
 namespace lb {
 
 struct FeatDev {
-  int n, dim, tw, periodic, mag, bound, force_mode, force_axis, stride;
+  int n, dim, tw, periodic, mag, bound, force_mode, force_axis, stride, embed, n_types;
+  const float* embedding;
+  const int32_t* ptype;
   double box[3], r, vmean[3], vstd[3], lo[3], hi[3], fthr, flo[3], fhi[3];
 };
 
@@ -71,6 +73,13 @@ __global__ void node_feature_kernel(FeatDev c, const T* __restrict__ window, con
 #pragma unroll
     for (int k = 0; k < DIM; ++k) o[col + k] = force_in[(int64_t)i * DIM + k];
     col += DIM;
+  }
+  if (c.embed > 0) {  // hk.Embed (gns.py:61-63): row lookup, NumPy indexing (-1 = last row)
+    int t = c.ptype[i];
+    if (t < 0) t += c.n_types;
+    t = min(max(t, 0), c.n_types - 1);
+    for (int k = 0; k < c.embed; ++k) o[col + k] = c.embedding[t * c.embed + k];
+    col += c.embed;
   }
   for (; col < c.stride; ++col) o[col] = 0.f;
 }
@@ -178,7 +187,9 @@ extern "C" int lb200_features(const lb200_feature_cfg* c, const void* window_dev
                               const int32_t* idx_dev, int32_t e_cap, float* node_feat_dev, float* edge_feat_dev,
                               void* stream) {
   if (!c || !window_dev || (c->dim != 2 && c->dim != 3) || c->t_window < 1) return LB200_EINVAL;
-  if (node_feat_dev && (c->t_window < 2 || c->node_stride < lb200_node_feature_width(c))) return LB200_EINVAL;
+  if (node_feat_dev && (c->t_window < 2 || c->node_stride < lb200_node_feature_width(c) + (c->embed_size > 0 ? c->embed_size : 0)))
+    return LB200_EINVAL;
+  if (c->embed_size > 0 && (!c->embedding_dev || !c->ptype_dev || c->num_particle_types < 1)) return LB200_EINVAL;
   if (c->force_mode == 2 && !force_dev) return LB200_EINVAL;
   FeatDev d;
   d.n = c->n;
@@ -190,6 +201,10 @@ extern "C" int lb200_features(const lb200_feature_cfg* c, const void* window_dev
   d.force_mode = c->force_mode;
   d.force_axis = c->force_axis;
   d.stride = c->node_stride;
+  d.embed = c->embed_size > 0 ? c->embed_size : 0;
+  d.n_types = c->num_particle_types;
+  d.embedding = c->embedding_dev;
+  d.ptype = c->ptype_dev;
   d.r = c->r_cutoff;
   d.fthr = c->force_threshold;
   for (int k = 0; k < 3; ++k) {

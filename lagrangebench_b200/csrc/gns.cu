@@ -592,7 +592,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
                                  const float* edge_feat_dev, const int32_t* ptype_dev, const int32_t* rowptr_dev,
                                  const int32_t* perm_dev, const int32_t* snd_dev, const int32_t* rcv_dev,
                                  float* out_dev, void* scratch_dev, int64_t scratch_bytes, void* stream) {
-  if (!c || !weights_dev || !node_feat_dev || !edge_feat_dev || !ptype_dev || !rowptr_dev ||
+  if (!c || !weights_dev || (!node_feat_dev && !c->node_inputs_in_h) || !edge_feat_dev || !ptype_dev || !rowptr_dev ||
       !snd_dev || !rcv_dev || !out_dev || !scratch_dev)
     return LB200_EINVAL;
   if (c->num_mp_steps < 1 || c->node_in + c->embed_size > kEncK || (c->dim != 2 && c->dim != 3) || c->e_cap < 1 ||
@@ -661,9 +661,11 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   ne.P = p_of(0);
   if (c->edge_impl != 1 && c->enc_node.tc_w >= 0 && c->enc_node.tc_vec >= 0) {
     // tensor-core encoder: the node-update kernel in encoder mode over the zero-padded input features
-    rc = launch_node_embed(node_feat_dev, c->node_in, c->node_stride, ptype_dev, w + c->embedding, c->embed_size,
-                           c->num_particle_types, n_own, h, s);
-    if (rc) return rc;
+    if (!c->node_inputs_in_h) {
+      rc = launch_node_embed(node_feat_dev, c->node_in, c->node_stride, ptype_dev, w + c->embedding, c->embed_size,
+                             c->num_particle_types, n_own, h, s);
+      if (rc) return rc;
+    }
     NodeTcArgs na;
     na.n = n_own;
     na.last = 0;
@@ -683,6 +685,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     if (rc) return rc;
     if (sh != nullptr) shard_exchange(sh, 1, per_step, s);
   } else {
+    if (c->node_inputs_in_h) return LB200_EUNSUPPORTED;
     node_encoder_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeEnc, s>>>(ne);
     LB_LAUNCHED(1);
   }

@@ -303,6 +303,22 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
   const lb200_shard* sh = c->shard;
   lb200_gns_cfg gns = c->gns;
   gns.nonfinite_flag = b.stats + 3;  // NaN / Inf accelerations (fp16 split out of range) -> status bit
+  // tensor-core node encoder: the feature kernel writes its whole input row [features | Embed(ptype) | 0] straight
+  // into the latent array (one kernel and one round trip through node_feat less)
+  lb200_feature_cfg feat = c->feat;
+  float* node_rows = b.node_feat;
+  if (direct && gns.edge_impl != 1 && gns.enc_node.tc_w >= 0 && gns.enc_node.tc_vec >= 0 && feat.force_mode != 2 &&
+      lb200_node_feature_width(&feat) + gns.embed_size <= kLatent) {
+    int64_t off_h = 0;
+    lb200_gns_scratch_layout(gns.n, gns.e_cap, &off_h, nullptr, nullptr, nullptr);
+    node_rows = reinterpret_cast<float*>((char*)b.gns_scratch + off_h);
+    feat.node_stride = kLatent;
+    feat.embed_size = gns.embed_size;
+    feat.num_particle_types = gns.num_particle_types;
+    feat.embedding_dev = weights_dev + gns.embedding;
+    feat.ptype_dev = ptype_dev;
+    gns.node_inputs_in_h = 1;
+  }
   if (sh != nullptr) {
     if (!direct || c->gns.shard != sh || c->gns.n_owned != sh->n_owned || c->integ.n != sh->n_owned ||
         c->feat.n != sh->n_owned || n != sh->n_owned + sh->n_ghost_left + sh->n_ghost_right || n > sh->n_cap ||
@@ -326,7 +342,7 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
       if (rc) return rc;
       rc = shard_flag_bcast(sh, b.stats, s);
       if (rc) return rc;
-      rc = lb200_features(&c->feat, window_dev, force_dev, nullptr, 0, b.node_feat, nullptr, stream);
+      rc = lb200_features(&feat, window_dev, force_dev, nullptr, 0, node_rows, nullptr, stream);
       if (rc) return rc;
       rc = lb200_gns_forward(&gns, weights_dev, b.node_feat, b.edge_feat, ptype_dev, b.rowptr, nullptr, b.snd,
                              b.rcv, b.out, b.gns_scratch, b.gns_bytes, stream);
@@ -352,7 +368,7 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
       rc = lb200_nbr_csr_build(&c->grid, last, (int64_t)tw * dim, c->cell_capacity, 0, b.rowptr, b.snd, b.rcv,
                                b.edge_feat, b.perm, c->e_cap, b.stats, b.nbr_scratch, b.nbr_bytes, stream);
       if (rc) return rc;
-      rc = lb200_features(&c->feat, window_dev, force_dev, nullptr, 0, b.node_feat, nullptr, stream);
+      rc = lb200_features(&feat, window_dev, force_dev, nullptr, 0, node_rows, nullptr, stream);
       if (rc) return rc;
     } else {
       rc = lb200_csr_build(list, n, c->e_cap, b.rowptr, b.perm, b.snd, b.rcv, b.csr_scratch, b.csr_bytes, stream);

@@ -236,7 +236,7 @@ def test_push_forward_unroll_reuses_the_rollout_path():
         nxt = orac.integrate(pred, cur_c)
         cur_c = np.concatenate([cur_c[:, 1:], nxt[:, None]], axis=1)
         f_c, n_c = orac.preprocess_eval((cur_c, ptype), n_c)
-    assert cur_g.shape == cur_c.shape and np.abs(cur_g.cpu().numpy() - cur_c).max() <= 1e-9
+    assert cur_g.shape == cur_c.shape and np.abs(cur_g.cpu().numpy() - cur_c).max() <= 1e-8  # 1e-5 of an acceleration
     assert np.array_equal(n_g.idx.cpu().numpy(), n_c.idx)
     assert np.allclose(f_g["vel_hist"].cpu().numpy(), f_c["vel_hist"], atol=1e-4)
 
