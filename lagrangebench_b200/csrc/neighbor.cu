@@ -202,26 +202,22 @@ __global__ void cell_scatter_kernel(const int32_t* __restrict__ hash, int n, con
   sid[cell_start[h] + atomicSub(&cell_count[h], 1) - 1] = i;
 }
 
-// stable argsort by hash == ascending particle id within each cell; then the cell-ordered positions
+// stable argsort by hash == ascending particle id within each cell, and the cell-ordered positions: every
+// particle finds its rank among the (few) ids scattered into its cell and writes itself there
 template <typename T, int DIM>
-__global__ void cell_sort_gather_kernel(const int32_t* __restrict__ cell_start, int n_cells, int32_t* __restrict__ sid,
-                                        const T* __restrict__ pos, int64_t stride, T* __restrict__ spos) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_cells) return;
-  int a = cell_start[c], b = cell_start[c + 1];
-  for (int i = a + 1; i < b; ++i) {
-    int v = sid[i], j = i - 1;
-    while (j >= a && sid[j] > v) {
-      sid[j + 1] = sid[j];
-      --j;
-    }
-    sid[j + 1] = v;
-  }
-  for (int i = a; i < b; ++i) {
-    const int64_t p = (int64_t)sid[i] * stride;
+__global__ void cell_rank_gather_kernel(const int32_t* __restrict__ hash, const int32_t* __restrict__ cell_start,
+                                        const int32_t* __restrict__ sid_unsorted, int n, const T* __restrict__ pos,
+                                        int64_t stride, int32_t* __restrict__ sid, T* __restrict__ spos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int h = hash[i];
+  const int a = cell_start[h], b = cell_start[h + 1];
+  int rank = 0;
+  for (int j = a; j < b; ++j) rank += sid_unsorted[j] < i ? 1 : 0;
+  const int q = a + rank;
+  sid[q] = i;
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) spos[(int64_t)i * DIM + k] = pos[p + k];
-  }
+  for (int k = 0; k < DIM; ++k) spos[(int64_t)q * DIM + k] = pos[(int64_t)i * stride + k];
 }
 
 template <typename T, int DIM>
@@ -467,7 +463,7 @@ static GridDev grid_dev(const lb200_grid* gr, int cap) {
   return g;
 }
 
-// hash -> cell scan (+ max occupancy into stats[1]) -> scatter -> per-cell sort + cell-ordered positions
+// hash -> cell scan (+ max occupancy into stats[1]) -> scatter -> rank inside the cell + cell-ordered positions
 template <typename T, int DIM>
 static int build_cells(const GridDev& g, const T* pos, int64_t stride, const NbrBufs<T>& b, int32_t* stats,
                        cudaStream_t s) {
@@ -477,8 +473,9 @@ static int build_cells(const GridDev& g, const T* pos, int64_t stride, const Nbr
   { hash_kernel<T, DIM><<<cdiv(nv, tb), tb, 0, s>>>(pos, stride, g, b.hash, b.cell_count); LB_LAUNCHED(1); }
   int rc = scan_lookback(b.cell_count, b.cell_start, nc, b.st_cells, 0x7fffffff, nullptr, stats + 1, s);
   if (rc) return rc;
-  { cell_scatter_kernel<<<cdiv(nv, tb), tb, 0, s>>>(b.hash, nv, b.cell_start, b.cell_count, b.sid); LB_LAUNCHED(1); }
-  { cell_sort_gather_kernel<T, DIM><<<cdiv(nc, tb), tb, 0, s>>>(b.cell_start, nc, b.sid, pos, stride, b.spos); LB_LAUNCHED(1); }
+  // b.cnt is free until the count sweep: it holds the unsorted cell contents
+  { cell_scatter_kernel<<<cdiv(nv, tb), tb, 0, s>>>(b.hash, nv, b.cell_start, b.cell_count, b.cnt); LB_LAUNCHED(1); }
+  { cell_rank_gather_kernel<T, DIM><<<cdiv(nv, tb), tb, 0, s>>>(b.hash, b.cell_start, b.cnt, nv, pos, stride, b.sid, b.spos); LB_LAUNCHED(1); }
   return 0;
 }
 
