@@ -412,10 +412,12 @@ __global__ void nbr_pad_kernel(int32_t* __restrict__ idx, int e_cap, int n, cons
   }
 }
 
+constexpr int kPark = 48;  // accepted candidates the count pass parks per receiver (in-degrees beyond it: the fill pass sweeps again)
+
 // ------------------------------------------------------------------ scratch layout of one build
 template <typename T>
 struct NbrBufs {
-  int32_t *cnt, *off, *tot, *hash, *sid, *cell_start;
+  int32_t *cnt, *off, *tot, *hash, *sid, *cell_start, *park;
   T* spos;
   // zeroed by ONE memset per build: cell_count | scan state (cells) | scan state (particles)
   char* zero;
@@ -435,6 +437,7 @@ static bool nbr_carve(const lb200_grid* gr, void* scratch, int64_t bytes, NbrBuf
   b->sid = ar.take<int32_t>(n);
   b->cell_start = ar.take<int32_t>(nc + 1);
   b->spos = ar.take<T>(n * 3);
+  b->park = ar.take<int32_t>(nc > 0 ? n * kPark : 0);
   const int64_t w_cells = scan_state_words(nc), w_part = scan_state_words(n);
   b->zero = ar.take<char>((nc + 1) * 4 + 256 + (w_cells + w_part) * 8 + 256);
   b->cell_count = reinterpret_cast<int32_t*>(b->zero);
@@ -577,7 +580,7 @@ template <typename T, int DIM>
 __global__ void __launch_bounds__(kSweepThreads) count_in_kernel(GridDev g, int n_recv, const T* __restrict__ spos,
                                                                  const int32_t* __restrict__ sid,
                                                                  const int32_t* __restrict__ cell_start,
-                                                                 int32_t* __restrict__ cnt) {
+                                                                 int32_t* __restrict__ cnt, int32_t* __restrict__ park) {
   const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (q >= g.n_valid) return;
   const int v = sid[q];
@@ -587,8 +590,15 @@ __global__ void __launch_bounds__(kSweepThreads) count_in_kernel(GridDev g, int 
     T pv[DIM];
 #pragma unroll
     for (int k = 0; k < DIM; ++k) pv[k] = spos[(int64_t)q * DIM + k];
-    sweep_rows<T, DIM>(lane, pv, g, geo, spos, cell_start,
-                       [&](bool ok, int) { c += __popc(__ballot_sync(0xffffffffu, ok)); });
+    int32_t* mine = park + (int64_t)q * kPark;  // the accepted candidates (cell-ordered ranks), for the fill pass
+    sweep_rows<T, DIM>(lane, pv, g, geo, spos, cell_start, [&](bool ok, int t) {
+      const uint32_t m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int k = c + __popc(m & ((1u << lane) - 1u));
+        if (k < kPark) mine[k] = t;
+      }
+      c += __popc(m);
+    });
   }
   if (lane == 0) cnt[v] = c;
 }
@@ -619,7 +629,8 @@ template <typename T, int DIM>
 __global__ void __launch_bounds__(kSweepThreads) fill_csr_kernel(
     GridDev g, int n_recv, const T* __restrict__ spos, const int32_t* __restrict__ sid,
     const int32_t* __restrict__ cell_start, const int32_t* __restrict__ rowptr, int32_t* __restrict__ snd,
-    int32_t* __restrict__ rcv, float4* __restrict__ edge_feat, int32_t* __restrict__ tmp, int e_cap) {
+    int32_t* __restrict__ rcv, float4* __restrict__ edge_feat, int32_t* __restrict__ tmp, int e_cap,
+    const int32_t* __restrict__ cnt, const int32_t* __restrict__ park) {
   __shared__ int s_id[kSweepThreads / 32][kFastDeg];
   __shared__ int s_t[kSweepThreads / 32][kFastDeg];
   const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
@@ -635,20 +646,31 @@ __global__ void __launch_bounds__(kSweepThreads) fill_csr_kernel(
   T pv[DIM];
 #pragma unroll
   for (int k = 0; k < DIM; ++k) pv[k] = spos[(int64_t)q * DIM + k];
-  int deg = 0;
-  sweep_rows<T, DIM>(lane, pv, g, geo, spos, cell_start, [&](bool ok, int t) {
-    const uint32_t m = __ballot_sync(0xffffffffu, ok);
-    if (ok) {
-      const int k = deg + __popc(m & ((1u << lane) - 1u));
-      if (k < kFastDeg) {
-        ids[k] = sid[t];
-        ts[k] = t;
-      } else if (base + k < e_cap) {
-        tmp[base + k] = t;
-      }
+  int deg = cnt[v];
+  static_assert(kPark <= kFastDeg, "parked candidates are ranked in shared memory");
+  if (deg <= kPark) {  // the count pass left the accepted candidates behind: no second sweep
+    const int32_t* mine = park + (int64_t)q * kPark;
+    for (int k = lane; k < deg; k += 32) {
+      const int t = mine[k];
+      ids[k] = sid[t];
+      ts[k] = t;
     }
-    deg += __popc(m);
-  });
+  } else {
+    deg = 0;
+    sweep_rows<T, DIM>(lane, pv, g, geo, spos, cell_start, [&](bool ok, int t) {
+      const uint32_t m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int k = deg + __popc(m & ((1u << lane) - 1u));
+        if (k < kFastDeg) {
+          ids[k] = sid[t];
+          ts[k] = t;
+        } else if (base + k < e_cap) {
+          tmp[base + k] = t;
+        }
+      }
+      deg += __popc(m);
+    });
+  }
   __syncwarp();
   const int n_fast = min(deg, kFastDeg);
   const int n_all = min(deg, e_cap - base);  // entries that were recorded (fast ones always are)
@@ -683,12 +705,12 @@ static int nbr_csr_build_t(const lb200_grid* gr, const T* pos, int64_t stride, i
   int rc = build_cells<T, DIM>(g, pos, stride, b, stats, s);
   if (rc) return rc;
   const int grid = cdiv((int64_t)g.n_valid * 32, kSweepThreads);
-  { count_in_kernel<T, DIM><<<grid, kSweepThreads, 0, s>>>(g, n_recv, b.spos, b.sid, b.cell_start, b.cnt); LB_LAUNCHED(1); }
+  { count_in_kernel<T, DIM><<<grid, kSweepThreads, 0, s>>>(g, n_recv, b.spos, b.sid, b.cell_start, b.cnt, b.park); LB_LAUNCHED(1); }
   if (g.n_valid < n) { zero_tail_kernel<<<cdiv(n - g.n_valid, 256), 256, 0, s>>>(b.cnt, g.n_valid, n); LB_LAUNCHED(1); }
   rc = scan_lookback(b.cnt, rowptr, n, b.st_part, e_cap, b.tot, nullptr, s);
   if (rc) return rc;
   { fill_csr_kernel<T, DIM><<<grid, kSweepThreads, 0, s>>>(g, n_recv, b.spos, b.sid, b.cell_start, rowptr, snd, rcv,
-                                                           reinterpret_cast<float4*>(edge_feat), tmp, e_cap); LB_LAUNCHED(1); }
+                                                           reinterpret_cast<float4*>(edge_feat), tmp, e_cap, b.cnt, b.park); LB_LAUNCHED(1); }
   { nbr_finalize_kernel<<<1, 1, 0, s>>>(b.tot, cap, e_cap, 1, stats); LB_LAUNCHED(1); }
   LB_LAUNCH_CHECK();
   return 0;
