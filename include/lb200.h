@@ -248,10 +248,10 @@ typedef struct {
   const struct lb200_shard_s* shard;
   /* dev int32* or NULL: OR-ed with 1 when an output acceleration is NaN / Inf (see LB200_ERR_NONFINITE) */
   int32_t* nonfinite_flag;
-  /* 1: rows [0, n_owned) of h (lb200_gns_scratch_layout) already hold the encoder's input rows
-   * [features | Embed(ptype) | 0 ...] (lb200_features with embed_size > 0 and node_stride = 128); node_feat_dev is
-   * not read.  Tensor-core path only. */
-  int32_t node_inputs_in_h;
+  /* 1: the rows of node_feat already end with the particle-type embedding -- [features | Embed(ptype) | 0 ...],
+   * lb200_features with embed_size > 0, node_stride a multiple of 4 -- and the node encoder reads them as they
+   * are (no separate embedding pass).  Tensor-core path only. */
+  int32_t node_feat_embedded;
   /* the model's latent width (gns.py:37 latent_size), 0 = 128.  Narrower models (the published GNS-5-64) run on the
    * 128-wide kernels: every latent dimension of the weights is zero-padded to 128 when they are packed, and
    * LayerNorm divides by this width (the padding columns are exactly zero throughout). */

@@ -49,7 +49,7 @@ class GnsCfg(C.Structure):
                 ("e_cap", C.c_int32), ("embedding", C.c_int64), ("enc_node", MlpOff), ("enc_edge", MlpOff),
                 ("dec", MlpOff), ("proc_edge", C.POINTER(MlpOff)), ("proc_node", C.POINTER(MlpOff)),
                 ("edge_impl", C.c_int32), ("n_owned", C.c_int32), ("shard", C.c_void_p),
-                ("nonfinite_flag", C.c_void_p), ("node_inputs_in_h", C.c_int32), ("latent", C.c_int32)]
+                ("nonfinite_flag", C.c_void_p), ("node_feat_embedded", C.c_int32), ("latent", C.c_int32)]
 
 
 MAX_RANKS = 16

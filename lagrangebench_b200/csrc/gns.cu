@@ -516,13 +516,17 @@ static int edge_tc_version(int edge_impl) {
 }
 
 // Which tensor-core node kernel runs: v2 (node_tc2.cu) unless LB200_NODE_TC=1 asks for v1 (A/B measurements).
-static int launch_node(const NodeTcArgs& a, cudaStream_t s) {
+static int node_tc_version() {
   static int env = -1;
   if (env < 0) {
     const char* e = getenv("LB200_NODE_TC");
     env = (e && e[0] == '1') ? 1 : 2;
   }
-  return env == 1 ? launch_node_mp_tc(a, s) : launch_node_mp_tc2(a, s);
+  return env;
+}
+static bool launch_node_is_v2() { return node_tc_version() == 2; }
+static int launch_node(const NodeTcArgs& a, cudaStream_t s) {
+  return node_tc_version() == 1 ? launch_node_mp_tc(a, s) : launch_node_mp_tc2(a, s);
 }
 
 static MlpW mlp_ptrs(const float* w, const lb200_mlp_off& o) {
@@ -592,7 +596,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
                                  const float* edge_feat_dev, const int32_t* ptype_dev, const int32_t* rowptr_dev,
                                  const int32_t* perm_dev, const int32_t* snd_dev, const int32_t* rcv_dev,
                                  float* out_dev, void* scratch_dev, int64_t scratch_bytes, void* stream) {
-  if (!c || !weights_dev || (!node_feat_dev && !c->node_inputs_in_h) || !edge_feat_dev || !ptype_dev || !rowptr_dev ||
+  if (!c || !weights_dev || !node_feat_dev || !edge_feat_dev || !ptype_dev || !rowptr_dev ||
       !snd_dev || !rcv_dev || !out_dev || !scratch_dev)
     return LB200_EINVAL;
   if (c->num_mp_steps < 1 || c->node_in + c->embed_size > kEncK || (c->dim != 2 && c->dim != 3) || c->e_cap < 1 ||
@@ -661,7 +665,9 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
   ne.P = p_of(0);
   if (c->edge_impl != 1 && c->enc_node.tc_w >= 0 && c->enc_node.tc_vec >= 0) {
     // tensor-core encoder: the node-update kernel in encoder mode over the zero-padded input features
-    if (!c->node_inputs_in_h) {
+    const bool embedded = c->node_feat_embedded != 0 && launch_node_is_v2();
+    if (c->node_feat_embedded && (!embedded || c->node_stride % 4 != 0 || c->node_stride > kLatent)) return LB200_EINVAL;
+    if (!embedded) {
       rc = launch_node_embed(node_feat_dev, c->node_in, c->node_stride, ptype_dev, w + c->embedding, c->embed_size,
                              c->num_particle_types, n_own, h, s);
       if (rc) return rc;
@@ -681,11 +687,13 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     na.P = p_of(0);
     na.out = out_dev;
     set_push(na, 0);
+    na.enc_in = embedded ? node_feat_dev : h;
+    na.enc_stride = embedded ? c->node_stride : kLatent;
     rc = launch_node(na, s);
     if (rc) return rc;
     if (sh != nullptr) shard_exchange(sh, 1, per_step, s);
   } else {
-    if (c->node_inputs_in_h) return LB200_EUNSUPPORTED;
+    if (c->node_feat_embedded) return LB200_EUNSUPPORTED;
     node_encoder_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeEnc, s>>>(ne);
     LB_LAUNCHED(1);
   }
@@ -781,6 +789,8 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       nt_args.h = h;
       nt_args.P = p_of(m + 1);
       nt_args.out = out_dev;
+      nt_args.enc_in = nullptr;
+      nt_args.enc_stride = 0;
       set_push(nt_args, m + 1);
       rc = launch_node(nt_args, s);
       if (rc) return rc;

@@ -44,6 +44,9 @@ struct NodeTcArgs {
   int dst_left, dst_right;
   int32_t* flag;  // OR-ed with 1 when a decoded output is NaN / Inf (or NULL)
   float inv_latent;  // as EdgeTcArgs
+  // encoder mode: input rows [n][enc_stride] (enc_stride <= 128, a multiple of 4; columns beyond it are zero)
+  const float* enc_in;
+  int enc_stride;
 };
 
 int launch_node_mp_tc(const NodeTcArgs& a, cudaStream_t s);

@@ -144,7 +144,11 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
         e0[i] = e1[i] = 0;
         if (r < rows) {
           const int64_t v = row0 + r;
-          hv[i] = reinterpret_cast<const float4*>(a.h + v * kLatent)[lane];
+          if (kEnc) {
+            if (lane * 4 < a.enc_stride) hv[i] = reinterpret_cast<const float4*>(a.enc_in + v * a.enc_stride)[lane];
+          } else {
+            hv[i] = reinterpret_cast<const float4*>(a.h + v * kLatent)[lane];
+          }
           if (!kEnc) {
             e0[i] = __ldg(a.rowptr + v);
             e1[i] = __ldg(a.rowptr + v + 1);

@@ -199,6 +199,8 @@ static GraphEntry* graph_capture(const std::string& key, cudaStream_t s, Step& o
   return &g_graphs.back();
 }
 
+constexpr int kNodeFeatStride = LB200_MAX_NODE_IN;  // room for [features | embedding] rows (the encoder's input width limit)
+
 struct RolloutBufs {
   void* pos;
   int32_t *stats, *rowptr, *perm, *snd, *rcv, *idx;
@@ -217,7 +219,7 @@ static bool carve(const lb200_rollout_cfg* c, void* scratch, int64_t bytes, Roll
   b->snd = ar.take<int32_t>(e_cap);
   b->rcv = ar.take<int32_t>(e_cap);
   b->idx = c->grid.use_cells ? nullptr : ar.take<int32_t>(2 * e_cap);  // all-pairs grids go through the list
-  b->node_feat = ar.take<float>(n * c->feat.node_stride);
+  b->node_feat = ar.take<float>(n * (c->feat.node_stride > kNodeFeatStride ? c->feat.node_stride : kNodeFeatStride));
   b->edge_feat = ar.take<float>(e_cap * 4);
   b->out = ar.take<float>(n * 3);
   b->nbr_bytes = lb200_nbr_scratch_bytes(&c->grid);
@@ -303,21 +305,21 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
   const lb200_shard* sh = c->shard;
   lb200_gns_cfg gns = c->gns;
   gns.nonfinite_flag = b.stats + 3;  // NaN / Inf accelerations (fp16 split out of range) -> status bit
-  // tensor-core node encoder: the feature kernel writes its whole input row [features | Embed(ptype) | 0] straight
-  // into the latent array (one kernel and one round trip through node_feat less)
+  // tensor-core node encoder: the feature kernel appends the particle-type embedding to its rows and the encoder
+  // reads them as they are (one kernel and one round trip through the latent array less)
   lb200_feature_cfg feat = c->feat;
-  float* node_rows = b.node_feat;
-  if (direct && gns.edge_impl != 1 && gns.enc_node.tc_w >= 0 && gns.enc_node.tc_vec >= 0 && feat.force_mode != 2 &&
-      lb200_node_feature_width(&feat) + gns.embed_size <= kLatent) {
-    int64_t off_h = 0;
-    lb200_gns_scratch_layout(gns.n, gns.e_cap, &off_h, nullptr, nullptr, nullptr);
-    node_rows = reinterpret_cast<float*>((char*)b.gns_scratch + off_h);
-    feat.node_stride = kLatent;
-    feat.embed_size = gns.embed_size;
-    feat.num_particle_types = gns.num_particle_types;
-    feat.embedding_dev = weights_dev + gns.embedding;
-    feat.ptype_dev = ptype_dev;
-    gns.node_inputs_in_h = 1;
+  {
+    const int wide = (lb200_node_feature_width(&feat) + gns.embed_size + 3) / 4 * 4;
+    if (direct && gns.edge_impl != 1 && gns.enc_node.tc_w >= 0 && gns.enc_node.tc_vec >= 0 && feat.force_mode != 2 &&
+        getenv("LB200_NODE_TC") == nullptr && wide <= kNodeFeatStride) {
+      feat.node_stride = wide;
+      feat.embed_size = gns.embed_size;
+      feat.num_particle_types = gns.num_particle_types;
+      feat.embedding_dev = weights_dev + gns.embedding;
+      feat.ptype_dev = ptype_dev;
+      gns.node_stride = wide;
+      gns.node_feat_embedded = 1;
+    }
   }
   if (sh != nullptr) {
     if (!direct || c->gns.shard != sh || c->gns.n_owned != sh->n_owned || c->integ.n != sh->n_owned ||
@@ -342,7 +344,7 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
       if (rc) return rc;
       rc = shard_flag_bcast(sh, b.stats, s);
       if (rc) return rc;
-      rc = lb200_features(&feat, window_dev, force_dev, nullptr, 0, node_rows, nullptr, stream);
+      rc = lb200_features(&feat, window_dev, force_dev, nullptr, 0, b.node_feat, nullptr, stream);
       if (rc) return rc;
       rc = lb200_gns_forward(&gns, weights_dev, b.node_feat, b.edge_feat, ptype_dev, b.rowptr, nullptr, b.snd,
                              b.rcv, b.out, b.gns_scratch, b.gns_bytes, stream);
@@ -368,7 +370,7 @@ extern "C" int lb200_rollout_steps(const lb200_rollout_cfg* c, int32_t n_steps, 
       rc = lb200_nbr_csr_build(&c->grid, last, (int64_t)tw * dim, c->cell_capacity, 0, b.rowptr, b.snd, b.rcv,
                                b.edge_feat, b.perm, c->e_cap, b.stats, b.nbr_scratch, b.nbr_bytes, stream);
       if (rc) return rc;
-      rc = lb200_features(&feat, window_dev, force_dev, nullptr, 0, node_rows, nullptr, stream);
+      rc = lb200_features(&feat, window_dev, force_dev, nullptr, 0, b.node_feat, nullptr, stream);
       if (rc) return rc;
     } else {
       rc = lb200_csr_build(list, n, c->e_cap, b.rowptr, b.perm, b.snd, b.rcv, b.csr_scratch, b.csr_bytes, stream);
