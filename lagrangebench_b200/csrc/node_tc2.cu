@@ -38,6 +38,22 @@ constexpr uint32_t kN2OffInv = kN2OffRed + kN2Workers * 3 * 128 * 4;            
 constexpr uint32_t kN2OffBar = kN2OffInv + 16 * 32 * 4;                          // mbarriers g1[4], g2[4]; tmem slot
 constexpr uint32_t kN2Smem = kN2OffBar + 8 * 8 + 16;
 
+#ifdef LB200_CROSSCHECK
+// phase timeline of CTA 0 (cross-check builds only): [worker][event] = (id, SM clock); lb200_debug_node_trace reads it
+__device__ long long g_node_trace[kN2Workers][64][2];
+__device__ int g_node_trace_n[kN2Workers];
+#define LB_TRACE(id)                                                                          \
+  do {                                                                                        \
+    if (!kEnc && !a.last && blockIdx.x == 0 && q == 0 && lane == 0 && g_node_trace_n[wk] < 64) { \
+      const int _i = g_node_trace_n[wk]++;                                                    \
+      g_node_trace[wk][_i][0] = (id);                                                         \
+      g_node_trace[wk][_i][1] = clock64();                                                    \
+    }                                                                                         \
+  } while (0)
+#else
+#define LB_TRACE(id) do { } while (0)
+#endif
+
 template <bool kEnc>
 __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -57,6 +73,10 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
   const int n_tiles = (a.n + k2Tile - 1) / k2Tile;
   const int grid = (int)gridDim.x;
   pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel's tail (it waits before reading)
+#ifdef LB200_CROSSCHECK
+  if (!kEnc && !a.last && blockIdx.x == 0 && q == 0 && lane == 0) g_node_trace_n[wk] = 0;
+#endif
+  LB_TRACE(0);
   if ((int)blockIdx.x >= n_tiles) {
     pdl_wait();  // a CTA never exits before the previous kernel is complete: the chain of waits stays transitive
     return;
@@ -75,6 +95,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  LB_TRACE(1);
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
   const uint4* wsrc = reinterpret_cast<const uint4*>(a.w_tc);  // operand halves (hi, lo, hi, lo ...) of 2048 uint4
   // ---- pass A weights -> tensor memory: columns [0,128) W1h (encoder: W0 padded), [128,256) W1a, [256,384) W2c
@@ -89,7 +110,9 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  LB_TRACE(2);
   pdl_wait();  // constants only so far (weights); h, the aggregates and the CSR are the previous kernels' results
+  LB_TRACE(3);
 
   const float b1 = vec[f], b2c = vec[128 + f], ln_scale = vec[256 + f], ln_offset = vec[384 + f], b_next = vec[512 + f];
   const uint32_t w1h_hi = tmem, w1h_lo = tmem + 64, w1a_hi = tmem + 128, w1a_lo = tmem + 192, w2_hi = tmem + 256,
@@ -199,6 +222,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
         if (!kEnc) put_row4(y_hi_p, y_lo_p, r0 + i, av[i]);
       }
     }
+    LB_TRACE(10);
     if (operand_ready()) {
       tc_fence_after();
       // acc = (W1h_lo' X_hi + W1a_lo' Y_hi) 2^-11 + W1h_hi X_lo + W1a_hi Y_lo + W1h_hi X_hi + W1a_hi Y_hi
@@ -223,10 +247,12 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
       }
       umma_commit(bar_g1);
     }
+    LB_TRACE(11);
     // ---- E1: hidden = relu(acc + b1) -> Y, node-contiguous (MN-major core matrices, 16-byte stores); GEMM 2
     mbar_wait(bar_g1, ph1);
     ph1 ^= 1;
     tc_fence_after();
+    LB_TRACE(12);
     {
       unsigned char* hi_p = y_hi_p + (uint32_t)(f >> 3) * kLboB + (uint32_t)(f & 7) * 16;
       unsigned char* lo_p = hi_p + kBBytes;
@@ -256,6 +282,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
       }
       if (hid_bad && a.flag != nullptr) atomicOr(a.flag, 1);
     }
+    LB_TRACE(13);
     if (operand_ready()) {
       tc_fence_after();
       issue_gemm_ts<false>(w2_hi, w2_lo, y_hi, y_lo, acc, k2IdescBMn);
@@ -266,9 +293,11 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
     float hold[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) hold[j] = (!kEnc && j < rows) ? hrow[(int64_t)j * kLatent] : 0.f;  // no residual in the encoder
+    LB_TRACE(14);
     mbar_wait(bar_g2, ph2);
     ph2 ^= 1;
     tc_fence_after();
+    LB_TRACE(15);
     {
       float yc[32];
       float part;
@@ -301,12 +330,15 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
       }
     }
     tc_fence_before();  // the accumulator reads of this tile are ordered before the next GEMM 1 (worker barrier)
+    LB_TRACE(16);
   }
 
   // ================================================================ switch the resident weights
+  LB_TRACE(20);
   tc_fence_before();
   __syncthreads();  // every worker has waited for its last GEMM and written its rows of h
   tc_fence_after();
+  LB_TRACE(21);
   {
     const int first = kEnc ? 4 : 6;             // operand halves of pass B in the blob
     const int halves = a.last ? 2 : 4;          // decoder: one operand
@@ -316,6 +348,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  LB_TRACE(22);
   const uint32_t ws_hi = tmem, ws_lo = tmem + 64, wr_hi = tmem + 128, wr_lo = tmem + 192;
   const bool push = a.P_left != nullptr || a.P_right != nullptr;
 
@@ -332,15 +365,18 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
       if (r < rows) hv = reinterpret_cast<const float4*>(a.h + (row0 + r) * kLatent)[lane];
       put_row4(x_hi_p, x_lo_p, r, hv);
     }
+    LB_TRACE(30);
     if (operand_ready()) {
       tc_fence_after();
       issue_gemm_ts<false>(ws_hi, ws_lo, x_hi, x_lo, acc_s, k2Idesc);
       if (!a.last) issue_gemm_ts<false>(wr_hi, wr_lo, x_hi, x_lo, acc_r, k2Idesc);
       umma_commit(bar_g1);
     }
+    LB_TRACE(31);
     mbar_wait(bar_g1, ph1);
     ph1 ^= 1;
     tc_fence_after();
+    LB_TRACE(32);
     if (!a.last) {
       // ---- next step's sender projection P[:, 0:128] (+ the neighbours' ghost rows), receiver projection P[:, 128:256]
       float* const prow = a.P + row0 * (2 * kLatent) + f;
@@ -394,7 +430,9 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
       }
     }
     tc_fence_before();
+    LB_TRACE(33);
   }
+  LB_TRACE(40);
   if (push) __threadfence_system();  // peer stores are performed before the kernel completes (exchange kernel follows)
   tc_fence_before();
   __syncthreads();
@@ -428,3 +466,13 @@ int launch_node_mp_tc2(const NodeTcArgs& a, cudaStream_t s) {
 }
 
 }  // namespace lb
+
+#ifdef LB200_CROSSCHECK
+// debug (cross-check builds): copy the phase timeline of the last node-kernel launch's CTA 0 to the host
+extern "C" int lb200_debug_node_trace(long long* out_4x64x2, int* n_out4) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out_4x64x2, lb::g_node_trace, sizeof(long long) * 4 * 64 * 2);
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(n_out4, lb::g_node_trace_n, sizeof(int) * 4);
+  return (int)e;
+}
+#endif
