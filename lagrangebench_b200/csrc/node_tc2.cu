@@ -179,6 +179,14 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
         }
       }
       if (!kEnc) {
+        // the worker's NEXT tile: its h and aggregate rows -> L1 while this tile computes (lane = row / 128-byte line)
+        const int64_t nrow = (int64_t)(tile + kN2Workers * grid) * k2Tile + r0 + (lane >> 2);
+        if (nrow < a.n) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(a.h + nrow * kLatent + (lane & 3) * 32));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(a.agg + nrow * kLatent + (lane & 3) * 32));
+        }
+      }
+      if (!kEnc) {
         // a bucket inside one carry sub-tile: its aggregate; a bucket that straddles sub-tiles (about every second
         // one at 14 in-edges per node): carry_last of its first sub-tile + carry_first of the following ones,
         // in slot order.  The first two terms of all 8 rows are requested together.
@@ -339,6 +347,10 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
   __syncthreads();  // every worker has waited for its last GEMM and written its rows of h
   tc_fence_after();
   LB_TRACE(21);
+  {  // this worker's first pass-B tile: its h rows -> L1 under the weight reload
+    const int64_t nrow = (int64_t)((int)blockIdx.x + wk * grid) * k2Tile + r0 + (lane >> 2);
+    if (nrow < a.n) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.h + nrow * kLatent + (lane & 3) * 32));
+  }
   {
     const int first = kEnc ? 4 : 6;             // operand halves of pass B in the blob
     const int halves = a.last ? 2 : 4;          // decoder: one operand
@@ -366,6 +378,10 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
       put_row4(x_hi_p, x_lo_p, r, hv);
     }
     LB_TRACE(30);
+    {  // the worker's next pass-B tile: its (just written) h rows -> L1
+      const int64_t nrow = (int64_t)(tile + kN2Workers * grid) * k2Tile + r0 + (lane >> 2);
+      if (nrow < a.n) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.h + nrow * kLatent + (lane & 3) * 32));
+    }
     if (operand_ready()) {
       tc_fence_after();
       issue_gemm_ts<false>(ws_hi, ws_lo, x_hi, x_lo, acc_s, k2Idesc);
