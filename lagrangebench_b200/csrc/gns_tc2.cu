@@ -66,6 +66,23 @@ constexpr uint32_t k2Smem = k2OffStage + k2Workers * k2StageBytes;
 // Round 2, measured and dropped as well (LDC-3D 28k, 132.1 us base): bar.arrive for the three non-issuing warps
 // at "operand complete" with two alternating barrier ids (133.1 us); loading P_r[rcv] only at bucket starts
 // through predicated loads (143.5 us: the select chain costs more issue slots than the L1 wavefronts it saves).
+#ifdef LB200_CROSSCHECK
+// phase timeline of CTA 0, worker 0, warps 0 (issues the GEMMs) and 1 (cross-check builds): (id, SM clock) pairs of
+// the pipeline iterations 8..11; lb200_debug_edge_trace reads it
+__device__ long long g_edge_trace[2][96][2];
+__device__ int g_edge_trace_n[2];
+#define ET(id)                                                                                          \
+  do {                                                                                                  \
+    if (!kEnc && trace_it && lane == 0 && g_edge_trace_n[q] < 96) {                                     \
+      const int _i = g_edge_trace_n[q]++;                                                               \
+      g_edge_trace[q][_i][0] = (id);                                                                    \
+      g_edge_trace[q][_i][1] = clock64();                                                               \
+    }                                                                                                   \
+  } while (0)
+#else
+#define ET(id) do { } while (0)
+#endif
+
 template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref>
 __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -86,6 +103,10 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   const uint32_t bar_ln = 1 + k2Workers + wk;
 
   pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel's tail (it waits before reading)
+#ifdef LB200_CROSSCHECK
+  bool trace_it = false;
+  if (!kEnc && blockIdx.x == 0 && wk == 0 && q < 2 && lane == 0) g_edge_trace_n[q] = 0;
+#endif
   if (tid == 0) {
     for (int w = 0; w < 3 * k2Workers; ++w) mbar_init(sbase + k2OffBar + 8 * w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -170,7 +191,9 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     int* ridx = rclamp + 32;  // ridx[0] = receiver before the tile, ridx[1 + i] = edge i, ridx[1 + rows] = after
     float4 v[8];
     if (kStage) {
+      ET(0);
       mbar_wait(bar_st, ph_st);  // the tile's rows were bulk-copied a pipeline round ago
+      ET(1);
       ph_st ^= 1;
       const float4* srow = reinterpret_cast<const float4*>(smem + k2OffStage + wk * k2StageBytes) + r0 * 32 + lane;
 #pragma unroll
@@ -225,6 +248,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     }
     fence_async_smem();
     tc_fence_before();
+    ET(2);
     if (operand_ready()) {  // this warp issues (one elected lane per instruction)
       tc_fence_after();
       const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
@@ -232,6 +256,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       umma_commit(bar_g1);
       if (kStage) stage_rows(tile + tile_stride);  // every warp is done reading the staged tile
     }
+    ET(3);
   };
 
   // ---- E1(tile in buffers b / ib): hidden = relu(acc + P_s[snd] + P_r[rcv]) -> operand, GEMM 2
@@ -252,9 +277,11 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       pr[j0 + 2] = __ldg(a.P + (int64_t)r4.z * (2 * kLatent) + kLatent + f);
       pr[j0 + 3] = __ldg(a.P + (int64_t)r4.w * (2 * kLatent) + kLatent + f);
     }
+    ET(10);
     mbar_wait(bar_g1, ph1);
     ph1 ^= 1;
     tc_fence_after();
+    ET(11);
     constexpr float kS = kNoScale ? 1.0f : kLoScale;
     if (kMn) {
       // edge-contiguous operand: 8 edges of feature k = f are one 16-byte chunk at
@@ -304,12 +331,14 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     }
     fence_async_smem();
     tc_fence_before();
+    ET(12);
     if (operand_ready()) {
       tc_fence_after();
       const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
       issue_gemm_ts<!kNoScale>(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, kMn ? k2IdescBMn : k2Idesc);
       umma_commit(bar_g2);
     }
+    ET(13);
   };
 
   float eold[32];  // residual rows of the tile E2 finishes
@@ -343,10 +372,12 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       mbar_wait(bar_g1, ph1);
       ph1 ^= 1;
     } else {
+      ET(20);
       mbar_wait(bar_g2, ph2);
       ph2 ^= 1;
     }
     tc_fence_after();
+    ET(21);
     float yc[32];
     float part;
     {
@@ -360,7 +391,9 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       part = warp_transpose_reduce(sq);  // lane l: this warp's 32 features, edge l
     }
     red[q * 32 + lane] = part;
+    ET(22);
     asm volatile("bar.sync %0, %1;" ::"r"(bar_ln), "n"(k2WThreads) : "memory");
+    ET(23);
     {
       const float var = (red[lane] + red[32 + lane] + red[64 + lane] + red[96 + lane]) * a.inv_latent;
       invs[lane] = 1.0f / sqrtf(var + 1e-5f);  // once per edge per warp (same value in the 4 warps)
@@ -485,9 +518,16 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   int buf = 0, ib = 0;
   for (int tile = k0; tile < n_tiles; tile += tile_stride) {
     const int ib_next = ib == 2 ? 0 : ib + 1;
+#ifdef LB200_CROSSCHECK
+    {
+      const int it = (tile - k0) / tile_stride;
+      trace_it = blockIdx.x == 0 && wk == 0 && q < 2 && it >= 8 && it < 12;
+    }
+#endif
     phase_e1(buf, ib);
     if (tile + tile_stride < n_tiles) phase_a(tile + tile_stride, buf ^ 1, ib_next);
     phase_e2(tile, buf, ib);
+    ET(30);
     buf ^= 1;
     ib = ib_next;
   }
@@ -651,6 +691,15 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(float* out) {
 }
 
 }  // namespace lb
+
+#ifdef LB200_CROSSCHECK
+extern "C" int lb200_debug_edge_trace(long long* out_2x96x2, int* n_out2) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out_2x96x2, lb::g_edge_trace, sizeof(long long) * 2 * 96 * 2);
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(n_out2, lb::g_edge_trace_n, sizeof(int) * 2);
+  return (int)e;
+}
+#endif
 
 extern "C" int lb200_tc_selftest(float* out5_dev, void* stream) {
   if (!out5_dev) return LB200_EINVAL;
