@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
 }
 
 template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref>
-static int launch_variant(const EdgeTcArgs& a, int grid, cudaStream_t s) {
+static int launch_variant(const EdgeTcArgs& a, int grid, int e_cap, cudaStream_t s) {
   static int ready[kMaxDevices];
   int rc = 0;
   const int dev = device_slot(&rc);
@@ -552,7 +552,7 @@ static int launch_variant(const EdgeTcArgs& a, int grid, cudaStream_t s) {
     if (rc) return rc;
     ready[dev] = 1;
   }
-  rc = (int)launch_maybe_pdl(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref>, grid, k2Threads, k2Smem, s, a);
+  rc = (int)launch_maybe_pdl(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref>, grid, k2Threads, k2Smem, s, a, e_cap);
   if (rc) return rc;
   LB_LAUNCHED(1);
   return 0;
@@ -569,17 +569,17 @@ int launch_edge_mp_tc2(const EdgeTcArgs& a, int e_cap, cudaStream_t s) {
   if (rc) return rc;
   const int n_groups = cdiv(cdiv(e_cap, k2Tile), k2Workers);
   const int grid = n_groups < sms ? n_groups : sms;
-  if (a.encoder) return launch_variant<true, true, true, false, false>(a, grid, s);
+  if (a.encoder) return launch_variant<true, true, true, false, false>(a, grid, e_cap, s);
 #ifdef LB200_CROSSCHECK
   switch (variant) {  // the measured ladder, cross-check builds only
-    case 0: return launch_variant<false, false, false, false, false>(a, grid, s);
-    case 1: return launch_variant<false, true, false, false, false>(a, grid, s);
-    case 3: return launch_variant<false, true, true, false, false>(a, grid, s);
-    case 7: return launch_variant<false, true, true, true, false>(a, grid, s);
+    case 0: return launch_variant<false, false, false, false, false>(a, grid, e_cap, s);
+    case 1: return launch_variant<false, true, false, false, false>(a, grid, e_cap, s);
+    case 3: return launch_variant<false, true, true, false, false>(a, grid, e_cap, s);
+    case 7: return launch_variant<false, true, true, true, false>(a, grid, e_cap, s);
     default: break;
   }
 #endif
-  return launch_variant<false, true, true, true, true>(a, grid, s);
+  return launch_variant<false, true, true, true, true>(a, grid, e_cap, s);
 }
 
 // =====================================================================================

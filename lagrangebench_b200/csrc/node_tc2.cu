@@ -474,8 +474,9 @@ int launch_node_mp_tc2(const NodeTcArgs& a, cudaStream_t s) {
   // tile t belongs to CTA t % grid, worker (t / grid) % 4: a small cloud spreads over as many SMs as it has tiles
   const int n_tiles = cdiv(a.n, k2Tile);
   const int grid = n_tiles < sms ? n_tiles : sms;
-  rc = (int)(a.enc ? launch_maybe_pdl(node_mp_tc2_kernel<true>, grid, kN2Threads, kN2Smem, s, a)
-                   : launch_maybe_pdl(node_mp_tc2_kernel<false>, grid, kN2Threads, kN2Smem, s, a));
+  const int64_t work = (int64_t)a.n * 14;  // ~ edges of a 3-D cloud: the same size switch as the message kernel
+  rc = (int)(a.enc ? launch_maybe_pdl(node_mp_tc2_kernel<true>, grid, kN2Threads, kN2Smem, s, a, work)
+                   : launch_maybe_pdl(node_mp_tc2_kernel<false>, grid, kN2Threads, kN2Smem, s, a, work));
   if (rc) return rc;
   LB_LAUNCHED(1);
   return 0;

@@ -17,13 +17,13 @@ namespace lb {
 
 std::atomic<int64_t> g_launches{0};
 
-bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
+bool pdl_enabled(int64_t work_items) {
+  static int mode = -1;  // 0 off, 1 on, 2 by size
+  if (mode < 0) {
     const char* e = getenv("LB200_PDL");
-    on = (e && e[0] == '0') ? 0 : 1;
+    mode = e ? (e[0] == '0' ? 0 : 1) : 2;
   }
-  return on == 1;
+  return mode == 1 || (mode == 2 && work_items <= kPdlMaxEdges);
 }
 
 int device_sm_count(int* rc) {
