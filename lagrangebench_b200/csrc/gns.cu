@@ -714,6 +714,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
     et.carry_first = nullptr;
     et.carry_last = nullptr;
     et.encoder = 1;
+    et.reverse = 0;
     et.edge_feat = reinterpret_cast<const float4*>(edge_feat_dev);
     et.perm = perm_dev;
     et.enc_vec = w + c->enc_edge.w0;
@@ -749,6 +750,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       et.carry_first = cf;
       et.carry_last = cl;
       et.encoder = 0;
+      et.reverse = (m & 1) == 0;  // the encoder went forwards: each launch starts where the previous one ended (L2)
       et.edge_feat = nullptr;
       et.perm = nullptr;
       et.enc_vec = nullptr;

@@ -20,6 +20,7 @@ struct EdgeTcArgs {
   const float4* edge_feat;
   const int32_t* perm;
   const float* enc_vec;
+  int reverse;  // 1: tiles are visited from the end of the edge array (consecutive launches alternate, gns_tc2.cu)
   int l2_mode;  // 1: the residual read and the store of e carry an L2 evict-first hint (gns_tc2.cu)
 };
 

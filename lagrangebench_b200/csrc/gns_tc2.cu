@@ -138,6 +138,11 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
 
   const uint32_t w1_hi = tmem + k2ColW1Hi, w1_lo = tmem + k2ColW1Lo, w2_hi = tmem + k2ColW2Hi, w2_lo = tmem + k2ColW2Lo;
   const int tile_stride = (int)gridDim.x * k2Workers;
+  // Consecutive launches walk the edge array in opposite directions: a launch starts with the tiles the previous
+  // one wrote last, which are still in L2 (the array itself is larger than L2).  Everything below counts LOGICAL
+  // tiles 0 .. n_tiles-1; phys() is the tile's place in the arrays.
+  const int rev_base = a.reverse ? n_tiles - 1 : 0, rev_sign = a.reverse ? -1 : 1;
+  auto phys = [&](int t) { return rev_base + rev_sign * t; };
 
   if (t_begin < n_tiles) {
   const float b2c = vec[f], ln_scale = vec[128 + f], ln_offset = vec[256 + f];
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   auto stage_rows = [&](int tile) {
     if (tile >= n_tiles) return;
     if (elect_one()) {
-      const int64_t s0 = (int64_t)tile * k2Tile;
+      const int64_t s0 = (int64_t)phys(tile) * k2Tile;
       const uint32_t bytes = (uint32_t)min(k2Tile, E - (int)s0) * (kLatent * 4);
       mbar_expect_tx(bar_st, bytes);
       bulk_g2s(sbase + k2OffStage + wk * k2StageBytes, a.e + s0 * kLatent, bytes, bar_st);
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
 
   auto prefetch_idx = [&](int tile) {
     if (tile >= n_tiles) return;
-    const int64_t s = (int64_t)tile * k2Tile + lane;
+    const int64_t s = (int64_t)phys(tile) * k2Tile + lane;
     if (kPref || q == 0) pre_r = s < E ? __ldg(a.rcv + s) : -1;
     if (kPref || q == 1) pre_s = s < E ? __ldg(a.snd + s) : 0;
     if (q == 0) {
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   // ---- phase A(tile -> operand buffer b, index buffer ib): indices -> smem, edge latents -> fp16
   //      hi/lo operand, GEMM 1
   auto phase_a = [&](int tile, int b, int ib) {
-    const int64_t slot0 = (int64_t)tile * k2Tile;
+    const int64_t slot0 = (int64_t)phys(tile) * k2Tile;
     const int rows = min(k2Tile, E - (int)slot0);
     int* sidx = idx_base + ib * k2IdxInts;
     int* rclamp = sidx + 32;
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       // pull the rows of the tile after this one into L2
       const int nt = tile + tile_stride;
       if (nt < n_tiles) {
-        const float* nrow = a.e + ((int64_t)nt * k2Tile + r0) * kLatent + lane * 4;
+        const float* nrow = a.e + ((int64_t)phys(nt) * k2Tile + r0) * kLatent + lane * 4;
 #pragma unroll
         for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + (int64_t)i * kLatent));
       }
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
 
   float eold[32];  // residual rows of the tile E2 finishes
   auto load_eold = [&](int tile) {
-    const int64_t slot0 = (int64_t)tile * k2Tile;
+    const int64_t slot0 = (int64_t)phys(tile) * k2Tile;
     const int valid = min(k2Tile, E - (int)slot0);
     const float* erow = a.e + slot0 * kLatent + f;
     if (valid == 32) {
@@ -364,7 +369,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
 
   // ---- E2(tile in buffers b / ib): LayerNorm (mean folded into the weights), residual, store, segmented sum
   auto phase_e2 = [&](int tile, int b, int ib) {
-    const int64_t slot0 = (int64_t)tile * k2Tile;
+    const int64_t slot0 = (int64_t)phys(tile) * k2Tile;
     const int valid = min(k2Tile, E - (int)slot0);  // edges of this tile that exist (>= 1)
     const int* ridx = idx_base + ib * k2IdxInts + 64;
     float* const erow = a.e + slot0 * kLatent + f;
@@ -409,8 +414,8 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     const uint32_t emask = kEnc ? 0u : endm[ib];
     const bool first_cont = !kEnc && ridx[0] == ridx[1];
     const bool last_cont = !kEnc && ridx[1 + valid] == ridx[valid];
-    float* const cfirst = a.carry_first + (int64_t)tile * kLatent + f;
-    float* const clast = a.carry_last + (int64_t)tile * kLatent + f;
+    float* const cfirst = a.carry_first + (int64_t)phys(tile) * kLatent + f;
+    float* const clast = a.carry_last + (int64_t)phys(tile) * kLatent + f;
     float seg_sum = 0.f;
     bool seg_first = true;  // still inside the first bucket of the sub-tile
     auto finish = [&](auto full_tag) {
@@ -454,7 +459,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     float4* feat_w = reinterpret_cast<float4*>(smem + k2OffStage) + warp * 32;  // this warp's copy of the tile's features
     // edge features live in LIST order and are addressed through perm; the next tile's are fetched a phase ahead
     auto feat_of = [&](int tile) -> float4 {
-      const int64_t s = (int64_t)tile * k2Tile + lane;
+      const int64_t s = (int64_t)phys(tile) * k2Tile + lane;
       return (tile < n_tiles && s < E) ? a.edge_feat[a.perm ? a.perm[s] : s] : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     float4 pre_f = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -566,15 +571,18 @@ static int launch_variant(const EdgeTcArgs& a, int grid, int e_cap, cudaStream_t
 }
 
 int launch_edge_mp_tc2(const EdgeTcArgs& a_in, int e_cap, cudaStream_t s) {
-  static int variant = -1, l2_mode = -1;
+  static int variant = -1, l2_mode = -1, no_reverse = 0;
   if (variant < 0) {
     const char* e = getenv("LB200_TC2_VARIANT");  // bit 0: kMn, bit 1: kNoScale, bit 2: kStage, bit 3: kPref
     variant = e ? (atoi(e) & 15) : k2DefaultVariant;
     const char* h = getenv("LB200_L2HINT");  // A/B of the eviction hints (EdgeTcArgs::l2_mode)
     l2_mode = h ? (atoi(h) & 1) : k2DefaultL2Mode;
+    const char* r = getenv("LB200_REVERSE");  // 0: every launch walks forwards (A/B)
+    no_reverse = r && r[0] == '0';
   }
   EdgeTcArgs a = a_in;
   a.l2_mode = l2_mode;
+  if (no_reverse) a.reverse = 0;
   int rc = 0;
   const int sms = device_sm_count(&rc);
   if (rc) return rc;
