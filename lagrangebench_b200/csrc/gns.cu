@@ -796,6 +796,7 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       set_push(nt_args, m + 1);
       rc = launch_node(nt_args, s);
       if (rc) return rc;
+      prof_end(1, s);  // the node kernel alone: the wait for the neighbours' stores is not its time
       if (sh != nullptr && !last) shard_exchange(sh, m + 2, per_step, s);
     } else {
       NodeMpArgs nm;
@@ -814,8 +815,8 @@ extern "C" int lb200_gns_forward(const lb200_gns_cfg* c, const float* weights_de
       nm.flag = c->nonfinite_flag;
       nm.out = out_dev;
       { node_mp_kernel<<<cdiv(n_own, kTM), kThreads, kSmemNodeMp, s>>>(nm); LB_LAUNCHED(1); }
+      prof_end(1, s);
     }
-    prof_end(1, s);
   }
   LB_LAUNCH_CHECK();
   return 0;

@@ -528,51 +528,65 @@ __device__ __forceinline__ void sweep_rows(int lane, const T* pv, const GridDev&
   int cc[3] = {0, 0, 0};
   cell_hash<T, DIM>(pv, geo, g, cc);
   constexpr int NROWS = DIM == 2 ? 3 : 9;
-  int a0 = 0, b0 = 0, a1 = 0, b1 = 0;
-  if (lane < NROWS) {
+  // lane p < 2 NROWS owns piece p of the candidate ranges: row p / 2 (x-contiguous cells), piece 0 = the cells that
+  // are contiguous in memory, piece 1 = the cell wrapped around the x boundary (empty for an interior cell)
+  int a = 0, len = 0;
+  if (lane < 2 * NROWS) {
+    const int r = lane >> 1, piece = lane & 1;
     int rowbase = 0;
     {
-      int cy = cc[1] - (lane % 3 - 1);
+      int cy = cc[1] - (r % 3 - 1);
       cy = cy < 0 ? cy + g.nc[1] : (cy >= g.nc[1] ? cy - g.nc[1] : cy);
       rowbase = cy * g.nc[0];
       if (DIM == 3) {
-        int cz = cc[2] - (lane / 3 - 1);
+        int cz = cc[2] - (r / 3 - 1);
         cz = cz < 0 ? cz + g.nc[2] : (cz >= g.nc[2] ? cz - g.nc[2] : cz);
         rowbase += cz * g.nc[0] * g.nc[1];
       }
     }
     const int nx = g.nc[0], cx = cc[0];
+    int lo = 0, hi = 0;  // cells [lo, hi) of the row
     if (cx > 0 && cx < nx - 1) {
-      a0 = cell_start[rowbase + cx - 1];
-      b0 = cell_start[rowbase + cx + 2];
+      if (piece == 0) { lo = cx - 1; hi = cx + 2; }
     } else if (cx == 0) {  // cells 0, 1 and the wrapped nx - 1 (nx >= 3)
-      a0 = cell_start[rowbase];
-      b0 = cell_start[rowbase + 2];
-      a1 = cell_start[rowbase + nx - 1];
-      b1 = cell_start[rowbase + nx];
+      if (piece == 0) { lo = 0; hi = 2; } else { lo = nx - 1; hi = nx; }
     } else {               // cells nx - 2, nx - 1 and the wrapped 0
-      a0 = cell_start[rowbase + nx - 2];
-      b0 = cell_start[rowbase + nx];
-      a1 = cell_start[rowbase];
-      b1 = cell_start[rowbase + 1];
+      if (piece == 0) { lo = nx - 2; hi = nx; } else { lo = 0; hi = 1; }
+    }
+    if (hi > lo) {
+      a = cell_start[rowbase + lo];
+      len = cell_start[rowbase + hi] - a;
     }
   }
-  for (int r = 0; r < NROWS; ++r) {
+  // The pieces are concatenated (same order as a row-by-row walk) and swept 32 candidates at a time: two or three
+  // dependent position loads per particle instead of one per row.
+  int incl = len;
 #pragma unroll
-    for (int piece = 0; piece < 2; ++piece) {
-      const int a = __shfl_sync(0xffffffffu, piece ? a1 : a0, r), b = __shfl_sync(0xffffffffu, piece ? b1 : b0, r);
-      for (int t0 = a; t0 < b; t0 += 32) {
-        const int t = t0 + lane;
-        bool ok = false;
-        if (t < b) {
-          T pj[DIM];
+  for (int off = 1; off < 32; off <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += up;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  for (int k0 = 0; k0 < total; k0 += 32) {
+    const int k = k0 + lane;
+    int p = 0;  // first piece whose inclusive end exceeds k
 #pragma unroll
-          for (int k = 0; k < DIM; ++k) pj[k] = spos[(int64_t)t * DIM + k];
-          ok = within<T, DIM>(pj, pv, geo);
-        }
-        f(ok, t);
-      }
+    for (int step = 16; step; step >>= 1) {
+      const int v = __shfl_sync(0xffffffffu, incl, (p + step - 1) & 31);
+      if (v <= k) p += step;
     }
+    p &= 31;
+    const int a_p = __shfl_sync(0xffffffffu, a, p), end_p = __shfl_sync(0xffffffffu, incl, p),
+              len_p = __shfl_sync(0xffffffffu, len, p);
+    const int t = a_p + (k - (end_p - len_p));
+    bool ok = false;
+    if (k < total) {
+      T pj[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) pj[d] = spos[(int64_t)t * DIM + d];
+      ok = within<T, DIM>(pj, pv, geo);
+    }
+    f(ok, t);
   }
 }
 
