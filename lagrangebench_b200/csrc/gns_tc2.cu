@@ -60,7 +60,8 @@ constexpr uint32_t k2Smem = k2OffStage + k2Workers * k2StageBytes;
 //           one phase before E1 gathers them.  Pays only together with kStage: the edge tiles then no
 //           longer pass through L1 and the prefetched lines survive until they are used.
 // Measured on LDC-3D 28k (us per launch): v1 176 -> TMEM weights + pipeline 149 -> kMn + kNoScale 141
-// -> kStage 138 -> kPref 131 (52 % of the measured HBM roofline).  Tried and dropped (no gain):
+// -> kStage 138 -> kPref 131 -> L2 evict-first hints on the streamed latents + alternating direction 128.6
+// (53 % of the measured HBM roofline).  Tried and dropped (no gain):
 // contiguous tile ranges per CTA; "last arriving warp issues the GEMM" instead of bar.sync (a dedicated
 // 17th MMA warp is worse still: 5 warps on one SM sub-partition cap every thread at 96 registers);
 // requesting the residual rows before phase A; ld.global.L1::no_allocate for the residual rows (slower).
