@@ -178,8 +178,11 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
           }
         }
       }
+      LB_TRACE(5);
       if (!kEnc) {
-        // the worker's NEXT tile: its h and aggregate rows -> L1 while this tile computes (lane = row / 128-byte line)
+        // the worker's NEXT tile: its h and aggregate rows -> L1 while this tile computes (lane = row / 128-byte line).
+        // (Also prefetching the tile's bucket bounds and the carry rows of its straddling buckets, or prefetching
+        // into L2 instead of L1, changed nothing: 117-123 us per launch at 125 k nodes in every variant.)
         const int64_t nrow = (int64_t)(tile + kN2Workers * grid) * k2Tile + r0 + (lane >> 2);
         if (nrow < a.n) {
           asm volatile("prefetch.global.L1 [%0];" ::"l"(a.h + nrow * kLatent + (lane & 3) * 32));
@@ -202,6 +205,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
             if (tb > ta) cv[i] = reinterpret_cast<const float4*>(a.carry_first + (int64_t)(ta + 1) * kLatent)[lane];
           }
         }
+        LB_TRACE(6);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           av[i].x += cv[i].x; av[i].y += cv[i].y; av[i].z += cv[i].z; av[i].w += cv[i].w;
@@ -224,6 +228,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
               !(fabsf(g.w) <= 65504.f);
       }
       if (bad && a.flag != nullptr) atomicOr(a.flag, 1);
+      LB_TRACE(7);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         put_row4(x_hi_p, x_lo_p, r0 + i, hv[i]);

@@ -13,7 +13,7 @@ try:
     d = json.load(open(sys.argv[2]))
     r = d["roofline"]
     print(f"{sys.argv[1]:36s} {d['ms_per_step']*1e3:8.1f} us/step  edge {r['avg_launch_ms']*1e3:7.1f} us ({r['frac']:.3f})  "
-          f"node share {r['node_kernel_share_of_step']:.3f}  clocks {d['clocks']['sm_mhz']} {d['clocks']['reasons']}")
+          f"node {r['node_kernel_share_of_step'] * d['config']['ms_per_step_kernel_leg_eager_with_events'] * 1e3 / d['config']['mp_steps']:6.1f} us  clocks {d['clocks']['sm_mhz']} {d['clocks']['reasons']}")
 except Exception as exc:
     print(sys.argv[1], "FAILED", exc)
 PY

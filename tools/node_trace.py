@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lagrangebench_b200 import GNS, _cabi, case_builder, synthetic  # noqa: E402
 from lagrangebench_b200 import models as lbmodels  # noqa: E402
 
-NAMES = {0: "entry", 1: "alloc+vec", 2: "weightsA", 3: "pdl wait", 10: "A0 built", 11: "G1 issued", 12: "G1 done",
+NAMES = {0: "entry", 1: "alloc+vec", 2: "weightsA", 3: "pdl wait", 5: "A0 req1", 6: "A0 req2", 7: "A0 data", 10: "A0 built", 11: "G1 issued", 12: "G1 done",
          13: "E1 hidden", 14: "resid req", 15: "G2 done", 16: "tile A end", 20: "switch>", 21: "switch<", 22: "weightsB",
          30: "B0 built", 31: "GB issued", 32: "GB done", 33: "tile B end", 40: "end"}
 
