@@ -79,11 +79,12 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // a kernel runs for tens of microseconds (the early prologue's weight traffic competes with the running kernel's
 // tail), so it is applied to small problems only.  LB200_PDL=1 / 0 forces it on / off (A/B measurements).
 bool pdl_enabled(int64_t work_items);
+int early_issue_mask();  // LB200_EARLY: bit 0 message kernel, bit 1 node kernel issue their first loads before the weights (A/B)
 constexpr int64_t kPdlMaxEdges = 100000;
 
 template <typename Arg>
 static inline cudaError_t launch_maybe_pdl(void (*kernel)(Arg), int grid, int block, size_t smem, cudaStream_t s,
-                                           const Arg& arg, int64_t work_items) {
+                                           const Arg& arg, bool pdl) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)block);
@@ -93,7 +94,7 @@ static inline cudaError_t launch_maybe_pdl(void (*kernel)(Arg), int grid, int bl
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled(work_items) ? 1 : 0;
+  cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, arg);
 }
 

@@ -20,6 +20,8 @@ struct EdgeTcArgs {
   const float4* edge_feat;
   const int32_t* perm;
   const float* enc_vec;
+  int pdl;      // launched with programmatic stream serialization: constants first, then griddepcontrol.wait;
+                // otherwise the first tile's loads are issued before the weights are loaded
   int reverse;  // 1: tiles are visited from the end of the edge array (consecutive launches alternate, gns_tc2.cu)
   int l2_mode;  // 1: the residual read and the store of e carry an L2 evict-first hint (gns_tc2.cu)
 };
@@ -46,6 +48,7 @@ struct NodeTcArgs {
   int dst_left, dst_right;
   int32_t* flag;  // OR-ed with 1 when a decoded output is NaN / Inf (or NULL)
   float inv_latent;  // as EdgeTcArgs
+  int pdl;           // as EdgeTcArgs
   // encoder mode: input rows [n][enc_stride] (enc_stride <= 128, a multiple of 4; columns beyond it are zero)
   const float* enc_in;
   int enc_stride;

@@ -122,16 +122,22 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // resident weights -> TMEM: warp group g (4 warps, one per lane quarter) loads operand g
-  if (!kEnc || wk >= 2)  // encoder: w_tc holds only the second-layer pair, which goes to the W2 slots
-    weight_to_tmem(reinterpret_cast<const uint4*>(a.w_tc) + (kEnc ? wk - 2 : wk) * 2048, f,
-                   tmem + ((uint32_t)(q * 32) << 16) + wk * 64);
-  tmem_st_wait();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  // everything above read constants only (weights); from here on the previous kernel's results are used
-  pdl_wait();
+  // resident weights -> TMEM: warp group g (4 warps, one per lane quarter) loads operand g.  CTA-wide (barrier).
+  auto load_weights = [&]() {
+    if (!kEnc || wk >= 2)  // encoder: w_tc holds only the second-layer pair, which goes to the W2 slots
+      weight_to_tmem(reinterpret_cast<const uint4*>(a.w_tc) + (kEnc ? wk - 2 : wk) * 2048, f,
+                     tmem + ((uint32_t)(q * 32) << 16) + wk * 64);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  };
+  // Programmatic dependent launch (small clouds): constants (the weights) first, then wait for the previous kernel.
+  // Otherwise the first tile's rows and indices are requested first and travel while the weights are loaded.
+  if (a.pdl) {
+    load_weights();
+    pdl_wait();
+  }
   const int E = a.rowptr[a.n];
   const int n_tiles = (E + k2Tile - 1) / k2Tile;
   // this CTA's tiles: worker wk takes t_begin + wk + i * tile_stride
@@ -508,10 +514,9 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       }
     };
     const int k0 = t_begin + wk;
-    if (k0 < n_tiles) {
-      pre_f = feat_of(k0);
-      phase_a_enc(k0, 0);
-    }
+    if (k0 < n_tiles) pre_f = feat_of(k0);
+    if (!a.pdl) load_weights();
+    if (k0 < n_tiles) phase_a_enc(k0, 0);
     int buf = 0;
     for (int tile = k0; tile < n_tiles; tile += tile_stride) {
       if (tile + tile_stride < n_tiles) phase_a_enc(tile + tile_stride, buf ^ 1);
@@ -526,8 +531,9 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   if (k0 < n_tiles) {
     if (kStage && q == 0) stage_rows(k0);
     prefetch_idx(k0);
-    phase_a(k0, 0, 0);
   }
+  if (!a.pdl) load_weights();
+  if (k0 < n_tiles) phase_a(k0, 0, 0);
   int buf = 0, ib = 0;
   for (int tile = k0; tile < n_tiles; tile += tile_stride) {
     const int ib_next = ib == 2 ? 0 : ib + 1;
@@ -554,7 +560,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
 }
 
 template <bool kEnc, bool kMn, bool kNoScale, bool kStage, bool kPref>
-static int launch_variant(const EdgeTcArgs& a, int grid, int e_cap, cudaStream_t s) {
+static int launch_variant(const EdgeTcArgs& a_in, int grid, int e_cap, cudaStream_t s) {
   static int ready[kMaxDevices];
   int rc = 0;
   const int dev = device_slot(&rc);
@@ -565,7 +571,10 @@ static int launch_variant(const EdgeTcArgs& a, int grid, int e_cap, cudaStream_t
     if (rc) return rc;
     ready[dev] = 1;
   }
-  rc = (int)launch_maybe_pdl(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref>, grid, k2Threads, k2Smem, s, a, e_cap);
+  EdgeTcArgs a = a_in;
+  const bool pdl = pdl_enabled(e_cap);
+  a.pdl = (pdl || !(early_issue_mask() & 1)) ? 1 : 0;
+  rc = (int)launch_maybe_pdl(edge_mp_tc2_kernel<kEnc, kMn, kNoScale, kStage, kPref>, grid, k2Threads, k2Smem, s, a, pdl);
   if (rc) return rc;
   LB_LAUNCHED(1);
   return 0;

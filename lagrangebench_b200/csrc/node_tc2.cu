@@ -82,6 +82,17 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
     return;
   }
 
+  if (!a.pdl && !kEnc) {
+    // not a programmatic dependent launch: the previous kernel is complete, so this worker's first tile (h and
+    // aggregate rows, bucket bounds) can travel towards L1 / L2 while the weights are loaded
+    const int tile0 = (int)blockIdx.x + wk * grid;
+    const int64_t row = (int64_t)tile0 * k2Tile + q * 8 + (lane >> 2);
+    if (row < a.n) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a.h + row * kLatent + (lane & 3) * 32));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a.agg + row * kLatent + (lane & 3) * 32));
+      if ((lane & 3) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.rowptr + row));
+    }
+  }
   if (tid == 0) {
     for (int w = 0; w < 2 * kN2Workers; ++w) mbar_init(sbase + kN2OffBar + 8 * w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -462,8 +473,9 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
   }
 }
 
-int launch_node_mp_tc2(const NodeTcArgs& a, cudaStream_t s) {
+int launch_node_mp_tc2(const NodeTcArgs& a_in, cudaStream_t s) {
   static int ready[kMaxDevices];
+  NodeTcArgs a = a_in;
   int rc = 0;
   const int dev = device_slot(&rc);
   if (dev < 0) return rc;
@@ -479,9 +491,10 @@ int launch_node_mp_tc2(const NodeTcArgs& a, cudaStream_t s) {
   // tile t belongs to CTA t % grid, worker (t / grid) % 4: a small cloud spreads over as many SMs as it has tiles
   const int n_tiles = cdiv(a.n, k2Tile);
   const int grid = n_tiles < sms ? n_tiles : sms;
-  const int64_t work = (int64_t)a.n * 14;  // ~ edges of a 3-D cloud: the same size switch as the message kernel
-  rc = (int)(a.enc ? launch_maybe_pdl(node_mp_tc2_kernel<true>, grid, kN2Threads, kN2Smem, s, a, work)
-                   : launch_maybe_pdl(node_mp_tc2_kernel<false>, grid, kN2Threads, kN2Smem, s, a, work));
+  const bool pdl = pdl_enabled((int64_t)a.n * 14);  // ~ edges of a 3-D cloud: the same size switch as the message kernel
+  a.pdl = (pdl || !(early_issue_mask() & 2)) ? 1 : 0;
+  rc = (int)(a.enc ? launch_maybe_pdl(node_mp_tc2_kernel<true>, grid, kN2Threads, kN2Smem, s, a, pdl)
+                   : launch_maybe_pdl(node_mp_tc2_kernel<false>, grid, kN2Threads, kN2Smem, s, a, pdl));
   if (rc) return rc;
   LB_LAUNCHED(1);
   return 0;

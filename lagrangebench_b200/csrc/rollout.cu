@@ -17,6 +17,15 @@ namespace lb {
 
 std::atomic<int64_t> g_launches{0};
 
+int early_issue_mask() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LB200_EARLY");
+    on = e ? (atoi(e) & 3) : 3;
+  }
+  return on;
+}
+
 bool pdl_enabled(int64_t work_items) {
   static int mode = -1;  // 0 off, 1 on, 2 by size
   if (mode < 0) {
