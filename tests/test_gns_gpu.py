@@ -178,6 +178,34 @@ def test_high_degree_receiver_straddles_many_tiles():
     assert rel_err(out["acc"].cpu().numpy(), ref) <= TOL
 
 
+@pytest.mark.parametrize("n,e_real,n_pad", [(1, 1, 0), (2, 3, 5), (31, 31, 1), (33, 64, 0), (40, 65, 7), (200, 0, 4),
+                                           (593, 2368, 0), (600, 18945, 3)])
+def test_tiny_and_ragged_graphs(n, e_real, n_pad):
+    """Edge cases of the tiling: one particle, edge counts at and around the 32-edge tile, fewer tiles than workers,
+    one tile more than a whole round of the 148 x 4 workers, nodes without in-edges, an EMPTY edge list
+    (jraph's segment_sum of nothing = 0), padding edges -- both kernel paths against the oracle."""
+    rng = np.random.default_rng(n * 7 + e_real)
+    d = 3
+    snd = rng.integers(0, n, e_real).astype(np.int32)
+    rcv = rng.integers(0, max(1, n - n // 4), e_real).astype(np.int32)  # the last quarter of the nodes receives nothing
+    pad = np.full(n_pad, n, np.int32)
+    snd, rcv = np.concatenate([snd, pad]), np.concatenate([rcv, pad])
+    e = snd.shape[0]
+    feats = {"vel_hist": rng.standard_normal((n, 15)).astype(np.float32),
+             "rel_disp": rng.standard_normal((e, d)).astype(np.float32),
+             "rel_dist": rng.random((e, 1)).astype(np.float32), "senders": snd, "receivers": rcv}
+    ptype = rng.integers(0, 3, n).astype(np.int32)
+    params = ogns.init_params(15, d + 1, d, num_mp_steps=3, seed=2, perturb=True)
+    ref = ogns.forward(params, feats, ptype, 3, np.float64)["acc"]
+    for impl in ("tc", "simt"):
+        model = GNS(d, 128, 2, 3, 16)
+        model.edge_impl = impl
+        out, _ = model.apply(params, {}, (feats, ptype))
+        got = out["acc"].cpu().numpy()
+        assert got.shape == (n, d) and np.isfinite(got).all()
+        assert rel_err(got, ref) <= TOL, (impl, rel_err(got, ref))
+
+
 def test_forward_is_deterministic():
     got1, _, _, (c, ours, f_gpu, params, model) = _forward_both("rpf2d", "float32")
     out2, _ = model.apply(params, {}, (f_gpu, c["particle_type"]))
