@@ -200,6 +200,37 @@ def test_direct_csr_is_the_list_path_bit_for_bit(name, dtype):
         assert np.array_equal(x[:e], y)
 
 
+@pytest.mark.parametrize("name,dims,dtype", [("tgv2d", (5, 5), "float32"), ("tgv2d", (7, 5), "float64"),
+                                             ("rpf3d_8k", (5, 5, 5), "float64"), ("ldc3d", (6, 5, 7), "float32"),
+                                             ("tgv2d", (4, 4), "float64")])
+def test_small_random_clouds_with_coincident_and_border_particles(name, dims, dtype):
+    """Smallest cell grids (3 cells per side; (4, 4) falls back to all pairs), uniformly random positions instead
+    of a lattice, particles ON the lower box border, in the last ulp below the upper one, and coincident pairs
+    (distance 0): the list equals the oracle's bit for bit and the direct view equals the list path."""
+    c, ours, orac = build_pair(name, dtype, dims=dims, multiplier=2.0)
+    rng = np.random.default_rng(sum(dims))
+    n, t, d = c["positions"].shape
+    box = c["box"].astype(c["positions"].dtype)
+    pos = (rng.random((n, d)) * c["box"]).astype(c["positions"].dtype)
+    pos[0] = 0
+    pos[1] = np.nextafter(box, np.zeros_like(box))
+    pos[2, 0] = 0
+    pos[3] = pos[4]                                  # coincident pair
+    pos[5] = pos[4] + np.asarray(1e-7, pos.dtype)    # and an almost coincident one
+    window = np.repeat(pos[:, None], 6, axis=1)
+    _, n_gpu = ours.allocate_eval((window, c["particle_type"]))
+    _, n_cpu = orac.allocate_eval((window, c["particle_type"]))
+    assert n_gpu.n_edges == n_cpu.n_edges and n_gpu.max_occupancy == n_cpu.max_occupancy
+    assert np.array_equal(n_gpu.idx.cpu().numpy(), n_cpu.idx)
+    assert not bool(n_gpu.did_buffer_overflow)
+    if n_gpu._grid.use_cells:
+        w = torch.as_tensor(window).cuda().contiguous()
+        a, b, stats = _csr_both_ways(ours, w, n_gpu)
+        assert stats[0] == n_cpu.n_edges and stats[2] == 0
+        for x, y, what in zip(a, b, ("rowptr", "snd", "rcv", "edge features")):
+            assert np.array_equal(x, y), what
+
+
 def test_direct_csr_dense_bucket_and_capacity_clamp():
     """In-degrees beyond the shared-memory fast path (a pile of particles), and a capacity smaller
     than the edge count: the view is the truncated bucket structure, the flag is raised."""
