@@ -250,23 +250,25 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
     if (operand_ready()) {
       tc_fence_after();
       // acc = (W1h_lo' X_hi + W1a_lo' Y_hi) 2^-11 + W1h_hi X_lo + W1a_hi Y_lo + W1h_hi X_hi + W1a_hi Y_hi
-#pragma unroll
+      // (rolled loops: the issuing warp runs this once per tile, straight-line code would only fill the
+      // instruction cache -- the kernel's `no_instruction` stalls were 12 % of its samples)
+#pragma unroll 1
       for (int j = 0; j < 8; ++j) umma_ts(acc, w1h_lo + j * 8, bdesc(x_hi, j), j > 0 ? 1u : 0u, k2Idesc);
       if (!kEnc) {
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < 8; ++j) umma_ts(acc, w1a_lo + j * 8, bdesc(y_hi, j), 1u, k2Idesc);
       }
       umma_ts_rescale11(acc, w1h_hi, bdesc(x_lo, 0), k2Idesc);
-#pragma unroll
+#pragma unroll 1
       for (int j = 1; j < 8; ++j) umma_ts(acc, w1h_hi + j * 8, bdesc(x_lo, j), 1u, k2Idesc);
       if (!kEnc) {
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < 8; ++j) umma_ts(acc, w1a_hi + j * 8, bdesc(y_lo, j), 1u, k2Idesc);
       }
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 8; ++j) umma_ts(acc, w1h_hi + j * 8, bdesc(x_hi, j), 1u, k2Idesc);
       if (!kEnc) {
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < 8; ++j) umma_ts(acc, w1a_hi + j * 8, bdesc(y_hi, j), 1u, k2Idesc);
       }
       umma_commit(bar_g1);
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
     LB_TRACE(13);
     if (operand_ready()) {
       tc_fence_after();
-      issue_gemm_ts<false>(w2_hi, w2_lo, y_hi, y_lo, acc, k2IdescBMn);
+      issue_gemm_ts_rolled(w2_hi, w2_lo, y_hi, y_lo, acc, k2IdescBMn);
       umma_commit(bar_g2);
     }
     // ---- E2: LayerNorm (mean folded into the weights) + residual -> h
@@ -400,8 +402,8 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
     }
     if (operand_ready()) {
       tc_fence_after();
-      issue_gemm_ts<false>(ws_hi, ws_lo, x_hi, x_lo, acc_s, k2Idesc);
-      if (!a.last) issue_gemm_ts<false>(wr_hi, wr_lo, x_hi, x_lo, acc_r, k2Idesc);
+      issue_gemm_ts_rolled(ws_hi, ws_lo, x_hi, x_lo, acc_s, k2Idesc);
+      if (!a.last) issue_gemm_ts_rolled(wr_hi, wr_lo, x_hi, x_lo, acc_r, k2Idesc);
       umma_commit(bar_g1);
     }
     LB_TRACE(31);
@@ -417,9 +419,11 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
         tmem_ld32(acc_s + lane_sel, ps);
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j < rows) {
-            prow[(int64_t)j * (2 * kLatent)] = ps[j];
-            if (push) {  // boundary rows: the same 128-byte segment goes into the neighbour's ghost row (NVLink store)
+          if (j < rows) prow[(int64_t)j * (2 * kLatent)] = ps[j];
+        if (push) {  // boundary rows: the same 128-byte segment goes into the neighbour's ghost row (NVLink store)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < rows) {
               const int64_t v = row0 + j;
               if (a.P_left != nullptr) {
                 const int k = __ldg(a.push_left + v);
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
                 if (k >= 0) a.P_right[(int64_t)(a.dst_right + k) * (2 * kLatent) + f] = ps[j];
               }
             }
-          }
+        }
       }
       {
         float pr[32];

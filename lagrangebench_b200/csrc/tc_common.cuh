@@ -285,6 +285,18 @@ __device__ __forceinline__ void issue_gemm_ts(uint32_t a_hi, uint32_t a_lo, uint
   }
 }
 
+// issue_gemm_ts<false> with rolled loops (a quarter of the code; for kernels that run it once or twice per CTA tile)
+__device__ __forceinline__ void issue_gemm_ts_rolled(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                     uint32_t acc, uint32_t idesc) {
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) umma_ts(acc, a_lo + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), j > 0 ? 1u : 0u, idesc);
+  umma_ts_rescale11(acc, a_hi, umma_desc(b_lo, kLboB), idesc);
+#pragma unroll 1
+  for (int j = 1; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_lo + j * 2 * kLboB, kLboB), 1u, idesc);
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
+}
+
 // 16 columns of this warp's 32 TMEM lanes -> registers (thread == lane)
 __device__ __forceinline__ void tmem_ld16(uint32_t ta, float (&a)[16]) {
   uint32_t x[16];
