@@ -26,6 +26,7 @@ namespace lb {
 
 constexpr int k2Threads = 512;
 constexpr int k2Workers = 4;
+constexpr int kIssuer2 = 3;           // warp (of a worker) that issues GEMM 2
 constexpr int k2DefaultL2Mode = 1;  // LB200_L2HINT=0 switches the eviction hints off (A/B)
 constexpr int k2DefaultVariant = 15;  // see launch_edge_mp_tc2
 constexpr int k2WThreads = k2Threads / k2Workers;
@@ -183,9 +184,9 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
 
   // Every thread has written its part of an operand (and fenced it for the async proxy): a worker-wide
   // bar.sync, after which the worker's first warp issues the GEMM.  Returns true in that warp.
-  auto operand_ready = [&]() -> bool {
+  auto operand_ready = [&](int issuer = 0) -> bool {
     asm volatile("bar.sync %0, %1;" ::"r"(bar_worker), "n"(k2WThreads) : "memory");
-    return q == 0;
+    return q == issuer;
   };
 
   auto prefetch_idx = [&](int tile) {
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     fence_async_smem();
     tc_fence_before();
     ET(12);
-    if (operand_ready()) {
+    if (operand_ready(kIssuer2)) {  // GEMM 2 is issued by another warp than GEMM 1: warp 0 already carries the index work
       tc_fence_after();
       const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
       issue_gemm_ts<!kNoScale>(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, kMn ? k2IdescBMn : k2Idesc);
