@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     if (operand_ready()) {  // this warp issues (one elected lane per instruction)
       tc_fence_after();
       const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
-      issue_gemm_ts<!kNoScale>(w1_hi, w1_lo, bh, bh + kBBytes, acc0 + b * 32, k2Idesc);
+      if (kNoScale) issue_gemm_ts_d(w1_hi, w1_lo, bh, bh + kBBytes, acc0 + b * 32, k2Idesc);
+      else issue_gemm_ts<true>(w1_hi, w1_lo, bh, bh + kBBytes, acc0 + b * 32, k2Idesc);
       umma_commit(bar_g1);
       if (kStage) stage_rows(tile + tile_stride);  // every warp is done reading the staged tile
     }
@@ -355,7 +356,8 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
     if (operand_ready(kIssuer2)) {  // GEMM 2 is issued by another warp than GEMM 1: warp 0 already carries the index work
       tc_fence_after();
       const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
-      issue_gemm_ts<!kNoScale>(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, kMn ? k2IdescBMn : k2Idesc);
+      if (kNoScale) issue_gemm_ts_d(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, kMn ? k2IdescBMn : k2Idesc);
+      else issue_gemm_ts<true>(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, kMn ? k2IdescBMn : k2Idesc);
       umma_commit(bar_g2);
     }
     ET(13);
@@ -508,7 +510,8 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
       if (operand_ready()) {
         tc_fence_after();
         const uint32_t bh = sbase + b_off + b * 2 * kBBytes;
-        issue_gemm_ts<!kNoScale>(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, k2IdescBMn);
+        if (kNoScale) issue_gemm_ts_d(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, k2IdescBMn);
+        else issue_gemm_ts<true>(w2_hi, w2_lo, bh, bh + kBBytes, acc0 + b * 32, k2IdescBMn);
         // A'(k+1) commits before E2(k) waits: each buffer has its own barrier, so that no barrier
         // ever runs two phases ahead of a waiter (a parity wait cannot tell phase n from n + 2)
         umma_commit(b ? bar_g1 : bar_g2);

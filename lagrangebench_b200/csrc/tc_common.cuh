@@ -297,6 +297,54 @@ __device__ __forceinline__ void issue_gemm_ts_rolled(uint32_t a_hi, uint32_t a_l
   for (int j = 0; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
 }
 
+// ---- the same GEMM with the B descriptor advanced by ONE 32-bit add per instruction: the descriptor of K slab j is
+// the descriptor of slab 0 plus j * (2 LBO >> 4) in its low word (start-address field; no carry: the field has 14 bits
+// and shared memory ends below 2^18).  Halves the uniform-datapath instructions the issuing warp spends per MMA.
+__device__ __forceinline__ void umma_ts_d(uint32_t tmem_d, uint32_t tmem_a, uint32_t desc_lo, uint32_t desc_hi,
+                                          uint32_t accumulate, uint32_t idesc) {
+  if (elect_one())
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 d;\n\t"
+        "mov.b64 d, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d, %4, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts_d_rescale11(uint32_t tmem_d, uint32_t tmem_a, uint32_t desc_lo, uint32_t desc_hi,
+                                                    uint32_t idesc) {
+  if (elect_one()) {
+    const uint32_t zero = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 d;\n\t"
+        "mov.b64 d, {%2, %3};\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d, %4, {%5, %5, %5, %5}, p, 11;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(zero)
+        : "memory");
+  }
+}
+// activation low halves unscaled (issue_gemm_ts<false>):  acc = (A_lo' B_hi) 2^-11 + A_hi B_lo + A_hi B_hi
+__device__ __forceinline__ void issue_gemm_ts_d(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t acc,
+                                                uint32_t idesc) {
+  const uint64_t dh = umma_desc(b_hi, kLboB), dl = umma_desc(b_lo, kLboB);
+  const uint32_t hi_word = (uint32_t)(dh >> 32), h0 = (uint32_t)dh, l0 = (uint32_t)dl;
+  constexpr uint32_t kStep = (2 * kLboB) >> 4;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) umma_ts_d(acc, a_lo + j * 8, h0 + j * kStep, hi_word, j > 0 ? 1u : 0u, idesc);
+  umma_ts_d_rescale11(acc, a_hi, l0, hi_word, idesc);
+#pragma unroll
+  for (int j = 1; j < 8; ++j) umma_ts_d(acc, a_hi + j * 8, l0 + j * kStep, hi_word, 1u, idesc);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) umma_ts_d(acc, a_hi + j * 8, h0 + j * kStep, hi_word, 1u, idesc);
+}
+
 // 16 columns of this warp's 32 TMEM lanes -> registers (thread == lane)
 __device__ __forceinline__ void tmem_ld16(uint32_t ta, float (&a)[16]) {
   uint32_t x[16];
