@@ -68,7 +68,9 @@ constexpr uint32_t k2Smem = k2OffStage + k2Workers * k2StageBytes;
 // requesting the residual rows before phase A; ld.global.L1::no_allocate for the residual rows (slower).
 // Round 2, measured and dropped as well (LDC-3D 28k, 132.1 us base): bar.arrive for the three non-issuing warps
 // at "operand complete" with two alternating barrier ids (133.1 us); loading P_r[rcv] only at bucket starts
-// through predicated loads (143.5 us: the select chain costs more issue slots than the L1 wavefronts it saves).
+// through predicated loads (143.5 us: the select chain costs more issue slots than the L1 wavefronts it saves);
+// deferring the issue of GEMM 1 into E2, behind the residual loads, where the issuing warp would otherwise wait for
+// GEMM 2 (same-box A/B: 128.9 vs 128.8 us).
 #ifdef LB200_CROSSCHECK
 // phase timeline of CTA 0, worker 0, warps 0 (issues the GEMMs) and 1 (cross-check builds): (id, SM clock) pairs of
 // the pipeline iterations 8..11; lb200_debug_edge_trace reads it

@@ -36,13 +36,13 @@ def main():
         model.apply(params, {}, (feats, c["particle_type"]))
     torch.cuda.synchronize()
     lib = C.CDLL(_cabi.library_path())
-    buf = (C.c_longlong * (2 * 96 * 2))()
-    cnt = (C.c_int * 2)()
+    buf = (C.c_longlong * (4 * 96 * 2))()
+    cnt = (C.c_int * 4)()
     assert lib.lb200_debug_edge_trace(buf, cnt) == 0
-    arr = np.array(buf[:]).reshape(2, 96, 2)
+    arr = np.array(buf[:]).reshape(4, 96, 2)
     ghz = 1.9
-    t0 = min(arr[w, 0, 1] for w in range(2) if cnt[w] > 0)
-    for w in range(2):
+    t0 = min(arr[w, 0, 1] for w in range(4) if cnt[w] > 0)
+    for w in range(4):
         print(f"warp {w}:")
         line = []
         for i in range(cnt[w]):
