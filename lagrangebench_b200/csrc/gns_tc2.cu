@@ -72,10 +72,10 @@ constexpr uint32_t k2Smem = k2OffStage + k2Workers * k2StageBytes;
 // deferring the issue of GEMM 1 into E2, behind the residual loads, where the issuing warp would otherwise wait for
 // GEMM 2 (same-box A/B: 128.9 vs 128.8 us).
 #ifdef LB200_CROSSCHECK
-// phase timeline of CTA 0, worker 0, warps 0 (issues the GEMMs) and 1 (cross-check builds): (id, SM clock) pairs of
+// phase timeline of CTA 0, worker 0, its four warps (cross-check builds): (id, SM clock) pairs of
 // the pipeline iterations 8..11; lb200_debug_edge_trace reads it
-__device__ long long g_edge_trace[2][96][2];
-__device__ int g_edge_trace_n[2];
+__device__ long long g_edge_trace[4][96][2];
+__device__ int g_edge_trace_n[4];
 #define ET(id)                                                                                          \
   do {                                                                                                  \
     if (!kEnc && trace_it && lane == 0 && g_edge_trace_n[q] < 96) {                                     \
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
   pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel's tail (it waits before reading)
 #ifdef LB200_CROSSCHECK
   bool trace_it = false;
-  if (!kEnc && blockIdx.x == 0 && wk == 0 && q < 2 && lane == 0) g_edge_trace_n[q] = 0;
+  if (!kEnc && blockIdx.x == 0 && wk == 0 && lane == 0) g_edge_trace_n[q] = 0;
 #endif
   if (tid == 0) {
     for (int w = 0; w < 3 * k2Workers; ++w) mbar_init(sbase + k2OffBar + 8 * w, 1);
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(k2Threads, 1) edge_mp_tc2_kernel(EdgeTcArgs a)
 #ifdef LB200_CROSSCHECK
     {
       const int it = (tile - k0) / tile_stride;
-      trace_it = blockIdx.x == 0 && wk == 0 && q < 2 && it >= 8 && it < 12;
+      trace_it = blockIdx.x == 0 && wk == 0 && it >= 8 && it < 12;
     }
 #endif
     phase_e1(buf, ib);
@@ -728,10 +728,10 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(float* out) {
 }  // namespace lb
 
 #ifdef LB200_CROSSCHECK
-extern "C" int lb200_debug_edge_trace(long long* out_2x96x2, int* n_out2) {
+extern "C" int lb200_debug_edge_trace(long long* out_4x96x2, int* n_out4) {
   cudaError_t e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out_2x96x2, lb::g_edge_trace, sizeof(long long) * 2 * 96 * 2);
-  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(n_out2, lb::g_edge_trace_n, sizeof(int) * 2);
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out_4x96x2, lb::g_edge_trace, sizeof(long long) * 4 * 96 * 2);
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(n_out4, lb::g_edge_trace_n, sizeof(int) * 4);
   return (int)e;
 }
 #endif
