@@ -250,26 +250,31 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
     if (operand_ready()) {
       tc_fence_after();
       // acc = (W1h_lo' X_hi + W1a_lo' Y_hi) 2^-11 + W1h_hi X_lo + W1a_hi Y_lo + W1h_hi X_hi + W1a_hi Y_hi
-      // (rolled loops: the issuing warp runs this once per tile, straight-line code would only fill the
-      // instruction cache -- the kernel's `no_instruction` stalls were 12 % of its samples)
-#pragma unroll 1
-      for (int j = 0; j < 8; ++j) umma_ts(acc, w1h_lo + j * 8, bdesc(x_hi, j), j > 0 ? 1u : 0u, k2Idesc);
+      // One dependent chain of 48 instructions: its latency is on the tile's critical path, so the issue is
+      // unrolled and every B descriptor is the slab-0 descriptor plus one 32-bit add (tc_common.cuh).
+      const uint64_t dxh = umma_desc(x_hi, kLboB), dxl = umma_desc(x_lo, kLboB), dyh = umma_desc(y_hi, kLboB),
+                     dyl = umma_desc(y_lo, kLboB);
+      const uint32_t dw = (uint32_t)(dxh >> 32), xh0 = (uint32_t)dxh, xl0 = (uint32_t)dxl, yh0 = (uint32_t)dyh,
+                     yl0 = (uint32_t)dyl;
+      constexpr uint32_t kStep = (2 * kLboB) >> 4;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) umma_ts_d(acc, w1h_lo + j * 8, xh0 + j * kStep, dw, j > 0 ? 1u : 0u, k2Idesc);
       if (!kEnc) {
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j) umma_ts(acc, w1a_lo + j * 8, bdesc(y_hi, j), 1u, k2Idesc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) umma_ts_d(acc, w1a_lo + j * 8, yh0 + j * kStep, dw, 1u, k2Idesc);
       }
-      umma_ts_rescale11(acc, w1h_hi, bdesc(x_lo, 0), k2Idesc);
-#pragma unroll 1
-      for (int j = 1; j < 8; ++j) umma_ts(acc, w1h_hi + j * 8, bdesc(x_lo, j), 1u, k2Idesc);
+      umma_ts_d_rescale11(acc, w1h_hi, xl0, dw, k2Idesc);
+#pragma unroll
+      for (int j = 1; j < 8; ++j) umma_ts_d(acc, w1h_hi + j * 8, xl0 + j * kStep, dw, 1u, k2Idesc);
       if (!kEnc) {
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j) umma_ts(acc, w1a_hi + j * 8, bdesc(y_lo, j), 1u, k2Idesc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) umma_ts_d(acc, w1a_hi + j * 8, yl0 + j * kStep, dw, 1u, k2Idesc);
       }
-#pragma unroll 1
-      for (int j = 0; j < 8; ++j) umma_ts(acc, w1h_hi + j * 8, bdesc(x_hi, j), 1u, k2Idesc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) umma_ts_d(acc, w1h_hi + j * 8, xh0 + j * kStep, dw, 1u, k2Idesc);
       if (!kEnc) {
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j) umma_ts(acc, w1a_hi + j * 8, bdesc(y_hi, j), 1u, k2Idesc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) umma_ts_d(acc, w1a_hi + j * 8, yh0 + j * kStep, dw, 1u, k2Idesc);
       }
       umma_commit(bar_g1);
     }
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
     LB_TRACE(13);
     if (operand_ready()) {
       tc_fence_after();
-      issue_gemm_ts_rolled(w2_hi, w2_lo, y_hi, y_lo, acc, k2IdescBMn);
+      issue_gemm_ts_d(w2_hi, w2_lo, y_hi, y_lo, acc, k2IdescBMn);
       umma_commit(bar_g2);
     }
     // ---- E2: LayerNorm (mean folded into the weights) + residual -> h
@@ -402,8 +407,32 @@ __global__ void __launch_bounds__(kN2Threads, 1) node_mp_tc2_kernel(NodeTcArgs a
     }
     if (operand_ready()) {
       tc_fence_after();
-      issue_gemm_ts_rolled(ws_hi, ws_lo, x_hi, x_lo, acc_s, k2Idesc);
-      if (!a.last) issue_gemm_ts_rolled(wr_hi, wr_lo, x_hi, x_lo, acc_r, k2Idesc);
+      if (a.last) {
+        issue_gemm_ts_d(ws_hi, ws_lo, x_hi, x_lo, acc_s, k2Idesc);
+      } else {
+        // two independent accumulate chains (sender / receiver projection), issued interleaved so that the tensor
+        // pipe overlaps them instead of running one dependent chain after the other
+        const uint64_t dxh = umma_desc(x_hi, kLboB), dxl = umma_desc(x_lo, kLboB);
+        const uint32_t dw = (uint32_t)(dxh >> 32), xh0 = (uint32_t)dxh, xl0 = (uint32_t)dxl;
+        constexpr uint32_t kStep = (2 * kLboB) >> 4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          umma_ts_d(acc_s, ws_lo + j * 8, xh0 + j * kStep, dw, j > 0 ? 1u : 0u, k2Idesc);
+          umma_ts_d(acc_r, wr_lo + j * 8, xh0 + j * kStep, dw, j > 0 ? 1u : 0u, k2Idesc);
+        }
+        umma_ts_d_rescale11(acc_s, ws_hi, xl0, dw, k2Idesc);
+        umma_ts_d_rescale11(acc_r, wr_hi, xl0, dw, k2Idesc);
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+          umma_ts_d(acc_s, ws_hi + j * 8, xl0 + j * kStep, dw, 1u, k2Idesc);
+          umma_ts_d(acc_r, wr_hi + j * 8, xl0 + j * kStep, dw, 1u, k2Idesc);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          umma_ts_d(acc_s, ws_hi + j * 8, xh0 + j * kStep, dw, 1u, k2Idesc);
+          umma_ts_d(acc_r, wr_hi + j * 8, xh0 + j * kStep, dw, 1u, k2Idesc);
+        }
+      }
       umma_commit(bar_g1);
     }
     LB_TRACE(31);

@@ -285,18 +285,6 @@ __device__ __forceinline__ void issue_gemm_ts(uint32_t a_hi, uint32_t a_lo, uint
   }
 }
 
-// issue_gemm_ts<false> with rolled loops (a quarter of the code; for kernels that run it once or twice per CTA tile)
-__device__ __forceinline__ void issue_gemm_ts_rolled(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                                     uint32_t acc, uint32_t idesc) {
-#pragma unroll 1
-  for (int j = 0; j < 8; ++j) umma_ts(acc, a_lo + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), j > 0 ? 1u : 0u, idesc);
-  umma_ts_rescale11(acc, a_hi, umma_desc(b_lo, kLboB), idesc);
-#pragma unroll 1
-  for (int j = 1; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_lo + j * 2 * kLboB, kLboB), 1u, idesc);
-#pragma unroll 1
-  for (int j = 0; j < 8; ++j) umma_ts(acc, a_hi + j * 8, umma_desc(b_hi + j * 2 * kLboB, kLboB), 1u, idesc);
-}
-
 // ---- the same GEMM with the B descriptor advanced by ONE 32-bit add per instruction: the descriptor of K slab j is
 // the descriptor of slab 0 plus j * (2 LBO >> 4) in its low word (start-address field; no carry: the field has 14 bits
 // and shared memory ends below 2^18).  Halves the uniform-datapath instructions the issuing warp spends per MMA.
