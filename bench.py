@@ -399,7 +399,9 @@ def run_ours(args):
     barrier()
     launches0 = lib.lb200_launch_count()
     realloc0 = engine.n_reallocations
-    sampler = ClockSampler(local_rank)
+    # NVML queries share a driver lock with the graph launches of the timed region: a 2 ms poll added up to 4 % of
+    # run-to-run spread (and ~1.5 % on average) to ms_per_step, 8 ms leaves 4-5 samples in the ~37 ms region
+    sampler = ClockSampler(local_rank, period_s=float(os.environ.get("BENCH_SAMPLER_MS", "8")) * 1e-3)
     if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
