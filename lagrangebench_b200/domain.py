@@ -70,81 +70,6 @@ class SlabDomain:
         return 0.0
 
 
-def exchange_rows(domain, to_left, to_right, group=None):
-    """Send ``to_left`` / ``to_right`` (2-D, same trailing shape and dtype on all ranks) to the
-    two neighbours; return ``(from_left, from_right)``.  Row counts are exchanged first.
-
-    Posting order is (left, right) for sends and (from right, from left) for receives so that
-    the messages pair up when both neighbours are the same rank (world == 2)."""
-    if domain.world == 1:
-        return to_left[:0], to_right[:0]
-    dev = to_left.device
-    counts = torch.tensor([to_left.shape[0], to_right.shape[0]], dtype=torch.int64, device=dev)
-    all_counts = torch.empty(domain.world * 2, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(all_counts, counts, group=group)
-    all_counts = all_counts.view(domain.world, 2).cpu()
-    n_from_right = int(all_counts[domain.right, 0])  # the right neighbour's left-going set
-    n_from_left = int(all_counts[domain.left, 1])
-    return exchange_rows_sized(domain, to_left, to_right, n_from_left, n_from_right, group)
-
-
-def exchange_rows_sized(domain, to_left, to_right, n_from_left, n_from_right, group=None, out_left=None,
-                        out_right=None):
-    """As :func:`exchange_rows` with known receive counts (the per-MP-step exchange of ``P``);
-    optionally receives straight into ``out_left`` / ``out_right``."""
-    tail = to_left.shape[1:]
-    from_right = out_right if out_right is not None else to_left.new_empty((n_from_right,) + tuple(tail))
-    from_left = out_left if out_left is not None else to_left.new_empty((n_from_left,) + tuple(tail))
-    ops = [dist.P2POp(dist.isend, to_left.contiguous(), domain.left, group),
-           dist.P2POp(dist.isend, to_right.contiguous(), domain.right, group),
-           dist.P2POp(dist.irecv, from_right, domain.right, group),
-           dist.P2POp(dist.irecv, from_left, domain.left, group)]
-    for req in dist.batch_isend_irecv(ops):
-        req.wait()
-    return from_left, from_right
-
-
-def halo_sets(domain, coord, group=None):
-    """Indices (ascending) of the owned particles the left / right neighbour needs as ghosts, and
-    the number of ghosts this rank will receive from each side: ``(send_left, send_right,
-    n_from_left, n_from_right)``.  One host synchronisation (the all-gathered counts)."""
-    m_left, m_right = domain.halo_masks(coord)
-    if domain.world == 1:
-        e = torch.empty(0, dtype=torch.int64, device=coord.device)
-        return e, e, 0, 0
-    counts = torch.stack([m_left.sum(), m_right.sum()]).to(torch.int64)
-    all_counts = torch.empty(domain.world * 2, dtype=torch.int64, device=coord.device)
-    dist.all_gather_into_tensor(all_counts, counts, group=group)
-    all_counts = all_counts.view(domain.world, 2).cpu()
-    n_left, n_right = int(all_counts[domain.rank, 0]), int(all_counts[domain.rank, 1])
-    # stable sort of the negated mask: the selected rows first, in ascending index order -- no
-    # second synchronisation (nonzero() would need one per mask)
-    send_left = torch.argsort((~m_left).to(torch.uint8), stable=True)[:n_left]
-    send_right = torch.argsort((~m_right).to(torch.uint8), stable=True)[:n_right]
-    return send_left, send_right, int(all_counts[domain.left, 1]), int(all_counts[domain.right, 0])
-
-
-def step_counts(domain, coord, group=None):
-    """ONE collective + ONE host synchronisation for everything a step needs to know about the other
-    ranks: the migration send-count matrix and every rank's (left, right) halo counts, both computed
-    from the same coordinates.  Returns ``(matrix (world, world), halo_counts (world, 2), order_left,
-    order_right)`` -- ``order_x[:halo_counts[rank, k]]`` are the ascending indices of the rows the
-    left / right neighbour needs; the halo part is only valid when the matrix is diagonal (nobody
-    changes owner)."""
-    w = domain.world
-    m_left, m_right = domain.halo_masks(coord)
-    payload = torch.cat([torch.bincount(domain.owner(coord), minlength=w).to(torch.int64),
-                         torch.stack([m_left.sum(), m_right.sum()]).to(torch.int64)])
-    allp = torch.empty(w * (w + 2), dtype=torch.int64, device=coord.device)
-    dist.all_gather_into_tensor(allp, payload, group=group)
-    # enqueued BEFORE the host read, so that the device is not idle while the host launches them:
-    # selected rows first, in ascending index order (the caller slices [:count])
-    order_left = torch.argsort((~m_left).to(torch.uint8), stable=True)
-    order_right = torch.argsort((~m_right).to(torch.uint8), stable=True)
-    allp = allp.view(w, w + 2).cpu()
-    return allp[:, :w], allp[:, w:], order_left, order_right
-
-
 def migrate(domain, coord, tensors, group=None, matrix=None):
     """Move rows to the rank that now owns them.  ``tensors``: list of tensors with the same
     leading dimension; returns the list with departed rows removed and arrivals appended

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from lagrangebench_b200.domain import SlabDomain, exchange_rows, exchange_rows_sized, halo_sets, migrate, step_counts
+from lagrangebench_b200.domain import SlabDomain, _p2p_rows, migrate, select_ghosts
 
 
 def test_slab_geometry():
@@ -35,39 +35,35 @@ def _worker(rank, world, port, results):
         pos = torch.rand((n, 3), generator=g)
         pos[:, 1] = dom.lo + pos[:, 1] * dom.width * 0.999
         gid = torch.arange(n) + 1000 * rank
-        # --- halo exchange: every ghost really comes from the right neighbour and region
+        # --- ghost selection (one collective) + the row exchange of selection time: every ghost really comes from
+        #     the right neighbour and region, counts and destination rows agree between the two sides
         m_l, m_r = dom.halo_masks(pos[:, 1])
         payload = torch.cat([pos, gid[:, None].to(pos.dtype)], dim=1)
-        from_left, from_right = exchange_rows(dom, payload[m_l], payload[m_r])
-        ok = True
-        if world > 1:
-            ok &= bool(((from_left[:, 3] // 1000).long() == dom.left).all())
-            ok &= bool(((from_right[:, 3] // 1000).long() == dom.right).all())
-            left_dom = SlabDomain(box, 1, world, dom.left, 0.1)
-            right_dom = SlabDomain(box, 1, world, dom.right, 0.1)
-            ok &= bool((from_left[:, 1] >= left_dom.hi - 0.1).all())   # the left neighbour's right face
-            ok &= bool((from_right[:, 1] < right_dom.lo + 0.1).all())  # the right neighbour's left face
-        # --- the single-synchronisation variant used by the rollout: same sets, same order, known counts
-        s_l, s_r, n_fl, n_fr = halo_sets(dom, pos[:, 1])
-        ok &= torch.equal(s_l, m_l.nonzero().squeeze(1)) and torch.equal(s_r, m_r.nonzero().squeeze(1))
-        if world > 1:
-            fl2, fr2 = exchange_rows_sized(dom, payload.index_select(0, s_l), payload.index_select(0, s_r), n_fl, n_fr)
-            ok &= torch.equal(fl2, from_left) and torch.equal(fr2, from_right)
-        else:
-            ok &= n_fl == 0 and n_fr == 0
-        # --- the merged collective of a rollout step: migration matrix + every rank's halo counts
-        matrix, halo_counts, o_l, o_r = step_counts(dom, pos[:, 1])
-        ok &= int(matrix.sum()) == int(matrix.diagonal().sum())  # everybody is at home
-        ok &= int(matrix[rank, rank]) == n
-        ok &= torch.equal(o_l[:int(m_l.sum())], s_l) and torch.equal(o_r[:int(m_r.sum())], s_r)
-        ok &= (int(halo_counts[rank, 0]), int(halo_counts[rank, 1])) == (int(m_l.sum()), int(m_r.sum()))
-        ok &= (int(halo_counts[dom.left, 1]), int(halo_counts[dom.right, 0])) == (n_fl, n_fr) or world == 1
+        sel = select_ghosts(dom, pos[:, 1])
+        ok = torch.equal(sel["send_left"], m_l.nonzero().squeeze(1)) and torch.equal(sel["send_right"], m_r.nonzero().squeeze(1))
+        counts = sel["counts_all"]
+        ok &= counts[rank] == [n, int(m_l.sum()), int(m_r.sum())]
+        ok &= (sel["n_ghost_left"], sel["n_ghost_right"]) == (counts[dom.left][2], counts[dom.right][1])
+        # my left-going rows land behind the left neighbour's own rows and its from-left block; right-going ones
+        # directly behind the right neighbour's own rows
+        ok &= sel["dst_row_left"] == counts[dom.left][0] + counts[(dom.left - 1) % world][2]
+        ok &= sel["dst_row_right"] == counts[dom.right][0]
+        ok &= sel["n_loc_max"] == max(counts[r][0] + counts[(r - 1) % world][2] + counts[(r + 1) % world][1]
+                                      for r in range(world))
+        from_left, from_right = _p2p_rows(dom, payload.index_select(0, sel["send_left"]),
+                                          payload.index_select(0, sel["send_right"]), sel["n_ghost_left"],
+                                          sel["n_ghost_right"])
+        ok &= bool(((from_left[:, 3] // 1000).long() == dom.left).all())
+        ok &= bool(((from_right[:, 3] // 1000).long() == dom.right).all())
+        left_dom = SlabDomain(box, 1, world, dom.left, 0.1)
+        right_dom = SlabDomain(box, 1, world, dom.right, 0.1)
+        ok &= bool((from_left[:, 1] >= left_dom.hi - 0.1).all())   # the left neighbour's right face
+        ok &= bool((from_right[:, 1] < right_dom.lo + 0.1).all())  # the right neighbour's left face
         # --- migration: move everything by +0.6 slab widths (periodic), rows are conserved
         moved = pos.clone()
         moved[:, 1] = torch.remainder(moved[:, 1] + 0.6 * dom.width, box[1])
-        matrix2 = step_counts(dom, moved[:, 1])[0]
-        ok &= world == 1 or int(matrix2.sum()) != int(matrix2.diagonal().sum())
-        new_pos, new_gid = migrate(dom, moved[:, 1], [moved, gid], matrix=matrix2 if world > 1 else None)
+        ok &= not bool((dom.owner(moved[:, 1]) == rank).all())  # somebody has to leave
+        new_pos, new_gid = migrate(dom, moved[:, 1], [moved, gid])
         ok &= bool((dom.owner(new_pos[:, 1]) == rank).all())
         stay = dom.owner(moved[:, 1]) == rank  # stayers first, in their original order
         ok &= torch.equal(new_gid[:int(stay.sum())], gid[stay])
