@@ -80,6 +80,10 @@ class ClockSampler:
         nv = self._nvml
         reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
             getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        # the first poll waits until the timed call has handed its launches to the driver (a fraction of a
+        # millisecond): NVML queries hold a driver lock, and a query right at the start delayed the first graph
+        # launch by up to a millisecond of device idle time inside the timed region
+        time.sleep(float(os.environ.get("BENCH_SAMPLER_DELAY_MS", "3")) * 1e-3)
         while not self._stop:
             try:
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM)))
