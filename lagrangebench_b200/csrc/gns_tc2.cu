@@ -71,7 +71,8 @@ constexpr uint32_t k2Smem = k2OffStage + k2Workers * k2StageBytes;
 // through predicated loads (143.5 us: the select chain costs more issue slots than the L1 wavefronts it saves);
 // deferring the issue of GEMM 1 into E2, behind the residual loads, where the issuing warp would otherwise wait for
 // GEMM 2 (same-box A/B: 128.9 vs 128.8 us); requesting the next tile's indices after the proxy fence of phase A instead
-// of before it (134.9 vs 129.9 us).
+// of before it (134.9 vs 129.9 us); GEMM 1 issued by warp 2 and the bulk copy started by warp 1, so that warp 0 keeps only
+// the index work (130.7 vs 129.6 us).
 #ifdef LB200_CROSSCHECK
 // phase timeline of CTA 0, worker 0, its four warps (cross-check builds): (id, SM clock) pairs of
 // the pipeline iterations 8..11; lb200_debug_edge_trace reads it
